@@ -1,0 +1,437 @@
+// Generic fp32 implicit-GEMM convolution on CUDA cores: forward / transposed-gather (dgrad) and
+// filter gradient.  This is the exact-arithmetic mode of the path (fp32 FMA, fp32 storage) used for
+// the 1e-3 rel-Linf parity gate and for the odd-shaped layers (Cin=3/9, 4x4 stride-2 discriminator
+// convs, Cout=1/3) that do not map onto tcgen05 tiles.
+//
+// Reference call sites replaced: nn.Conv2d in block.py:142-143 (conv_block), architecture.py:998-1018
+// (NLayerDiscriminator), architecture.py:1076 (VGG19 features); autograd's conv backward for them.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace dasr {
+
+static char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- gather: output coordinate + tap -> stored input coordinate ---------------------------------
+__device__ __forceinline__ bool gather_coord(const DasrConvF32Params& p, int oy, int ox, int dy, int dx,
+                                             int& iy, int& ix) {
+  if (p.mode == DASR_CONV_FWD) {
+    int ty = oy * p.stride - p.pad + dy;
+    int tx = ox * p.stride - p.pad + dx;
+    if (ty < 0 || tx < 0 || ty >= p.H * p.ups || tx >= p.W * p.ups) return false;
+    iy = (p.ups == 2) ? (ty >> 1) : ty;
+    ix = (p.ups == 2) ? (tx >> 1) : tx;
+    return true;
+  } else {
+    int ty = oy + p.pad - dy;
+    int tx = ox + p.pad - dx;
+    if (ty < 0 || tx < 0) return false;
+    if (p.stride > 1) {
+      if ((ty % p.stride) | (tx % p.stride)) return false;
+      ty /= p.stride;
+      tx /= p.stride;
+    }
+    if (ty >= p.H || tx >= p.W) return false;
+    iy = ty;
+    ix = tx;
+    return true;
+  }
+}
+
+constexpr int BM = 64, BN = 64, BK = 16, BMP = 68;
+
+// out[P x Cout] = gather(in)[P x K] * w[K x Cout],  K = taps*cin flattened tap-major.
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict__ in,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         const float* __restrict__ res1,
+                                                         const float* __restrict__ res2,
+                                                         float* __restrict__ out, DasrConvF32Params p) {
+  __shared__ __align__(16) float As[BK][BMP];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int t = threadIdx.x;
+  const long P = (long)p.N * p.OH * p.OW;
+  const int K = p.kh * p.kw * p.cin;
+  const long pm0 = (long)blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+
+  // A-load role: pixel a_pix, k-quad a_kq
+  const int a_pix = t >> 2, a_kq = t & 3;
+  long pa = pm0 + a_pix;
+  const bool pa_ok = pa < P;
+  int an = 0, aoy = 0, aox = 0;
+  if (pa_ok) {
+    an = (int)(pa / ((long)p.OH * p.OW));
+    int r = (int)(pa - (long)an * p.OH * p.OW);
+    aoy = r / p.OW;
+    aox = r - aoy * p.OW;
+  }
+  // B-load role: k row b_k, cout-quad b_cq
+  const int b_k = t >> 4, b_cq = t & 15;
+
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (int kk = 0; kk < K; kk += BK) {
+    // ---- load A tile (gathered activations) ----
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (VEC) {
+        int k0 = kk + a_kq * 4;  // cin % 16 == 0: the 16-wide k step stays inside one tap
+        int tap = k0 / p.cin, ci = k0 - tap * p.cin;
+        int dy = tap / p.kw, dx = tap - dy * p.kw;
+        int iy, ix;
+        if (pa_ok && gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
+          const float4 q = *reinterpret_cast<const float4*>(
+              in + ((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int k = kk + a_kq * 4 + j;
+          if (pa_ok && k < K) {
+            int tap = k / p.cin, ci = k - tap * p.cin;
+            int dy = tap / p.kw, dx = tap - dy * p.kw;
+            int iy, ix;
+            if (gather_coord(p, aoy, aox, dy, dx, iy, ix))
+              v[j] = in[((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) As[a_kq * 4 + j][a_pix] = v[j];
+    }
+    // ---- load B tile (filters) ----
+    {
+      int k = kk + b_k;
+      int c = co0 + b_cq * 4;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const float* wp = w + (long)k * p.cout + c;
+        if (VEC) {
+          if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);  // cout % 4 == 0
+        } else {
+          if (c + 0 < p.cout) q.x = wp[0];
+          if (c + 1 < p.cout) q.y = wp[1];
+          if (c + 2 < p.cout) q.z = wp[2];
+          if (c + 3 < p.cout) q.w = wp[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = q;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    long pm = pm0 + ty * 4 + i;
+    if (pm >= P) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int co = co0 + tx * 4 + j;
+      if (co >= p.cout) continue;
+      float v = acc[i][j] + (bias ? bias[co] : 0.f);
+      v = apply_act(v, p.act, p.slope);
+      v *= p.alpha;
+      if (res1) v = fmaf(p.beta1, res1[pm * p.res1_cs + p.res1_coff + co], v);
+      if (res2) v = fmaf(p.beta2, res2[pm * p.res2_cs + p.res2_coff + co], v);
+      out[pm * p.out_cs + p.out_coff + co] = v;
+    }
+  }
+}
+
+// part[split][K x Cout] = gather(in)^T[K x Pslice] * dout[Pslice x Cout]
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const float* __restrict__ in,
+                                                               const float* __restrict__ dout,
+                                                               float* __restrict__ part,
+                                                               DasrConvF32Params p, long pix_per_split) {
+  __shared__ __align__(16) float As[BK][BMP];  // [pixel][k]
+  __shared__ __align__(16) float Bs[BK][BN];   // [pixel][co]
+  const int t = threadIdx.x;
+  const long P = (long)p.N * p.OH * p.OW;
+  const int K = p.kh * p.kw * p.cin;
+  const int k0 = blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+  const long pbeg = (long)blockIdx.z * pix_per_split;
+  const long pend = min(P, pbeg + pix_per_split);
+
+  const int l_p = t >> 4, l_q = t & 15;  // load roles: pixel row, quad
+  // decode this thread's 4 k's once (VEC: same tap)
+  int ktap[4], kci[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int k = k0 + l_q * 4 + j;
+    if (k < K) {
+      ktap[j] = k / p.cin;
+      kci[j] = k - ktap[j] * p.cin;
+    } else {
+      ktap[j] = -1;
+      kci[j] = 0;
+    }
+  }
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (long pp = pbeg; pp < pend; pp += BK) {
+    long pix = pp + l_p;
+    bool ok = pix < pend;
+    int n = 0, oy = 0, ox = 0;
+    if (ok) {
+      n = (int)(pix / ((long)p.OH * p.OW));
+      int r = (int)(pix - (long)n * p.OH * p.OW);
+      oy = r / p.OW;
+      ox = r - oy * p.OW;
+    }
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        if (VEC) {
+          if (ktap[0] >= 0) {
+            int dy = ktap[0] / p.kw, dx = ktap[0] - dy * p.kw, iy, ix;
+            if (gather_coord(p, oy, ox, dy, dx, iy, ix)) {
+              const float4 q = *reinterpret_cast<const float4*>(
+                  in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[0]);
+              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (ktap[j] >= 0) {
+              int dy = ktap[j] / p.kw, dx = ktap[j] - dy * p.kw, iy, ix;
+              if (gather_coord(p, oy, ox, dy, dx, iy, ix))
+                v[j] = in[((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[j]];
+            }
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&As[l_p][l_q * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      int c = co0 + l_q * 4;
+      if (ok) {
+        const float* dp = dout + pix * p.out_cs + p.out_coff + c;
+        if (VEC) {
+          if (c < p.cout) q = *reinterpret_cast<const float4*>(dp);
+        } else {
+          if (c + 0 < p.cout) q.x = dp[0];
+          if (c + 1 < p.cout) q.y = dp[1];
+          if (c + 2 < p.cout) q.z = dp[2];
+          if (c + 3 < p.cout) q.w = dp[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[l_p][l_q * 4]) = q;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = part + (long)blockIdx.z * K * p.cout;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int co = co0 + tx * 4 + j;
+      if (co < p.cout) dst[(long)k * p.cout + co] = acc[i][j];
+    }
+  }
+}
+
+// dw_oihw[co][ci][tap] (+)= sum_s part[s][tap*cin+ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int K,
+                                    int cin, int cout, int ntaps, int accumulate) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)K * cout;
+  if (i >= total) return;
+  int k = (int)(i / cout), co = (int)(i - (long)k * cout);
+  float s = 0.f;
+  for (int sp = 0; sp < splits; sp++) s += part[(long)sp * total + i];
+  int tap = k / cin, ci = k - tap * cin;
+  long o = ((long)co * cin + ci) * ntaps + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// bias gradient: column sums of dout, two-stage deterministic
+__global__ void bgrad_partial_kernel(const float* __restrict__ dout, float* __restrict__ part, long P, int cout,
+                                     int cs, int coff, long pix_per_block) {
+  long pbeg = (long)blockIdx.x * pix_per_block, pend = min(P, pbeg + pix_per_block);
+  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+    float s = 0.f;
+    for (long pp = pbeg; pp < pend; pp++) s += dout[pp * cs + coff + c];
+    part[(long)blockIdx.x * cout + c] = s;
+  }
+}
+__global__ void bgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ db, int nblocks, int cout,
+                                    int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; b++) s += part[(long)b * cout + c];
+  db[c] = accumulate ? db[c] + s : s;
+}
+
+__global__ void pack_filter_f32_kernel(const float* __restrict__ w, float* __restrict__ o, int cout, int cin,
+                                       int ntaps, int for_dgrad) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)cout * cin * ntaps;
+  if (i >= total) return;
+  // i indexes OIHW: ((co*cin + ci)*ntaps + tap)
+  int tap = (int)(i % ntaps);
+  long r = i / ntaps;
+  int ci = (int)(r % cin), co = (int)(r / cin);
+  long dst = for_dgrad ? ((long)tap * cout + co) * cin + ci   // [tap][fwd cout][fwd cin]
+                       : ((long)tap * cin + ci) * cout + co;  // [tap][cin][cout]
+  o[dst] = w[i];
+}
+
+static int wgrad_splits(const DasrConvF32Params* p) {
+  long P = (long)p->N * p->OH * p->OW;
+  int K = p->kh * p->kw * p->cin;
+  int tiles = cdiv(K, BM) * cdiv(p->cout, BN);
+  int want = cdiv(2 * 148, tiles);
+  long maxs = (P + 255) / 256;
+  int s = (int)(want < maxs ? want : maxs);
+  if (s < 1) s = 1;
+  if (s > 128) s = 128;
+  return s;
+}
+static int bgrad_blocks(long P) {
+  long b = (P + 511) / 512;
+  if (b > 256) b = 256;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static int check_conv_params(const DasrConvF32Params* p) {
+  DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->OH > 0 && p->OW > 0, "conv_f32: bad dims");
+  DASR_REQUIRE(p->cin > 0 && p->cout > 0 && p->kh > 0 && p->kw > 0 && p->stride > 0, "conv_f32: bad conv");
+  DASR_REQUIRE(p->ups == 1 || (p->ups == 2 && p->mode == DASR_CONV_FWD), "conv_f32: ups must be 1 (or 2 in FWD)");
+  DASR_REQUIRE(p->in_cs >= p->in_coff + p->cin && p->out_cs >= p->out_coff + p->cout, "conv_f32: channel slice out of range");
+  return DASR_OK;
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" {
+
+const char* dasr_last_error(void) { return g_err; }
+int dasr_version(void) { return 100; }
+
+int dasr_conv2d_f32(const float* in, const float* w, const float* bias, const float* res1, const float* res2,
+                    float* out, const DasrConvF32Params* p, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  long P = (long)p->N * p->OH * p->OW;
+  dim3 grid(cdiv(P, BM), cdiv(p->cout, BN));
+  bool vec = (p->cin % 16 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
+             ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    conv2d_f32_kernel<true><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
+  else
+    conv2d_f32_kernel<false><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
+  return check_launch("conv2d_f32");
+}
+
+size_t dasr_conv2d_wgrad_f32_workspace(const DasrConvF32Params* p) {
+  long P = (long)p->N * p->OH * p->OW;
+  long K = (long)p->kh * p->kw * p->cin;
+  return (size_t)wgrad_splits(p) * K * p->cout * 4 + (size_t)bgrad_blocks(P) * p->cout * 4 + 256;
+}
+
+int dasr_conv2d_wgrad_f32(const float* in, const float* dout, float* dw, float* db, const DasrConvF32Params* p,
+                          int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  DASR_REQUIRE(p->mode == DASR_CONV_FWD, "wgrad_f32: params must describe the FWD conv");
+  DASR_REQUIRE(ws_bytes >= dasr_conv2d_wgrad_f32_workspace(p), "wgrad_f32: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  long P = (long)p->N * p->OH * p->OW;
+  int K = p->kh * p->kw * p->cin;
+  int splits = wgrad_splits(p);
+  long pps = ((P + splits - 1) / splits + BK - 1) / BK * BK;
+  float* part = (float*)ws;
+  dim3 grid(cdiv(K, BM), cdiv(p->cout, BN), splits);
+  bool vec = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
+             (p->out_cs % 4 == 0) && (p->out_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(dout) & 15) == 0);
+  if (vec)
+    conv2d_wgrad_f32_kernel<true><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
+  else
+    conv2d_wgrad_f32_kernel<false><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
+  long total = (long)K * p->cout;
+  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(part, dw, splits, K, p->cin, p->cout, p->kh * p->kw,
+                                                         accumulate);
+  if (db) {
+    float* bpart = part + (size_t)splits * total;
+    int nb = bgrad_blocks(P);
+    long ppb = (P + nb - 1) / nb;
+    bgrad_partial_kernel<<<nb, 128, 0, st>>>(dout, bpart, P, p->cout, p->out_cs, p->out_coff, ppb);
+    bgrad_reduce_kernel<<<cdiv(p->cout, 128), 128, 0, st>>>(bpart, db, nb, p->cout, accumulate);
+  }
+  return check_launch("conv2d_wgrad_f32");
+}
+
+int dasr_pack_filter_f32(const float* w, float* o, int cout, int cin, int kh, int kw, int for_dgrad, void* stream) {
+  DASR_REQUIRE(cout > 0 && cin > 0 && kh > 0 && kw > 0, "pack_filter_f32: bad dims");
+  long total = (long)cout * cin * kh * kw;
+  pack_filter_f32_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, o, cout, cin, kh * kw, for_dgrad);
+  return check_launch("pack_filter_f32");
+}
+
+}  // extern "C"

@@ -1,0 +1,610 @@
+// tcgen05 implicit-GEMM 3x3 convolution for sm_100a — the RRDB hot kernel.
+//
+// Replaces (reference, codes/SRN): ResidualDenseBlock_5C.conv1..5 + torch.cat + x5*0.2+x
+// (models/modules/block.py:262-286), RRDB / ShortcutBlock residuals (block.py:305-309, 103-105),
+// LR_conv / upconv / HR_conv0 (models/modules/architecture.py:182-201), and the same convs' input
+// gradients (dgrad = 3x3 conv with flipped, transposed filters).
+//
+// GEMM view per CTA tile:  D[128 pixels x nt couts] += A[128 x 32ch] * B[nt x 32ch]^T  for every
+// (tap, 32-channel chunk).  One tile = 16 rows x 8 cols of output pixels.
+//   * A: ONE TMA load per 32-channel chunk brings the (16+2)x(8+2) halo tile (zero fill outside the
+//     image) into shared memory as 180 rows x 64 B, 64B-swizzled.  Each of the 9 taps is then just a
+//     different UMMA shared-memory descriptor on that same tile: start address shifted by
+//     (dy*10+dx) rows, 8-row groups (= one image row of the tile) 10 rows apart (SBO = 640 B).
+//     Activations cross L2->SMEM once per chunk instead of once per tap (9x less than im2col/TMA-im2col).
+//   * B: the whole filter set of this CTA's Cout tile stays resident in shared memory for the
+//     lifetime of the persistent CTA ([tap][chunk][nt rows x 64 B], 64B-swizzled).
+//   * D: fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
+//     tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/act/residual/mask -> bf16 NHWC stores).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace dasr {
+
+constexpr int TILE_H = 16, TILE_W = 8;
+constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
+constexpr int CHUNK = 32;                      // channels per K chunk (64 B rows, SWIZZLE_64B)
+constexpr int ROW_B = CHUNK * 2;               // 64
+constexpr int A_HALO_BYTES = HALO_H * HALO_W * ROW_B;   // 11520
+constexpr int A_TAP_BYTES = TILE_H * TILE_W * ROW_B;    // 8192 (a_mode 1: one aligned tile per tap)
+constexpr int TC_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in max minus the kernel's 1 KB static allocation
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B shared-memory operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 |
+//   [46,48) version=1 (sm_100) | [49,52) base offset=0 | [61,64) layout type (4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24
+__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcKernelArgs {
+  DasrConvTcParams p;
+  const float* bias;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  const __nv_bfloat16* mask_src;
+  __nv_bfloat16* out;
+  int nchunks;       // cin / 32
+  int n_ntiles;      // cout / nt
+  int tiles_x, tiles_y;
+  long ntiles;       // N * tiles_y * tiles_x
+  int stages;
+  int w_bytes;       // resident filter bytes of one CTA
+  int a_stage_bytes; // bytes of one A stage
+  int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+               const TcKernelArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [W resident][A stages][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + a.w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.stages * a.a_stage_bytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]
+  uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;   // [2]
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+
+  const DasrConvTcParams& p = a.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int var = blockIdx.y / a.n_ntiles;       // variant (sub-pixel parity) of this CTA
+  const int ntile = blockIdx.y - var * a.n_ntiles;
+  const int nt = p.nt;
+  const int ntaps = p.ntaps;
+  const int acc_stride = a.tmem_cols >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < a.stages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      // resident filters: rows [(var*ntaps + tap)*nchunks + c]*cout + ntile*nt .. +nt of the packed filter
+      mbar_expect_tx(w_bar, (uint32_t)a.w_bytes);
+      for (int tap = 0; tap < ntaps; tap++)
+        for (int c = 0; c < a.nchunks; c++) {
+          int slot = tap * a.nchunks + c;
+          int row = ((var * ntaps + tap) * a.nchunks + c) * p.cout + ntile * nt;
+          tma_load_2d(sW + (size_t)slot * nt * ROW_B, &tmap_w, w_bar, 0, row);
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        int tx = (int)(tile % a.tiles_x);
+        long r = tile / a.tiles_x;
+        int ty = (int)(r % a.tiles_y);
+        int n = (int)(r / a.tiles_y);
+        int x0 = tx * TILE_W, y0 = ty * TILE_H;
+        for (int c = 0; c < a.nchunks; c++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = sA + (size_t)stage * a.a_stage_bytes;
+          if (p.a_mode == 0) {
+            mbar_expect_tx(&full_bar[stage], A_HALO_BYTES);
+            tma_load_4d(dst, &tmap_in, &full_bar[stage], p.in_coff + c * CHUNK, x0 - 1, y0 - 1, n);
+          } else {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(ntaps * A_TAP_BYTES));
+            for (int tap = 0; tap < ntaps; tap++)
+              tma_load_4d(dst + (size_t)tap * A_TAP_BYTES, &tmap_in, &full_bar[stage], p.in_coff + c * CHUNK,
+                          x0 - 1 + p.tap_dx[var][tap], y0 - 1 + p.tap_dy[var][tap], n);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, nt);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        for (int c = 0; c < a.nchunks; c++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + (size_t)stage * a.a_stage_bytes);
+          for (int tap = 0; tap < ntaps; tap++) {
+            uint32_t a_addr, a_sbo;
+            if (p.a_mode == 0) {
+              a_addr = a_base + (uint32_t)((p.tap_dy[var][tap] * HALO_W + p.tap_dx[var][tap]) * ROW_B);
+              a_sbo = HALO_W * ROW_B;  // 8-row group = one image row of the tile; next row is HALO_W pixels on
+            } else {
+              a_addr = a_base + (uint32_t)(tap * A_TAP_BYTES);
+              a_sbo = 8 * ROW_B;
+            }
+            const uint32_t b_addr = smem_u32(sW + (size_t)(tap * a.nchunks + c) * nt * ROW_B);
+#pragma unroll
+            for (int k = 0; k < CHUNK / 16; k++) {
+              uint64_t da = make_desc_sw64(a_addr + k * 32, a_sbo);
+              uint64_t db = make_desc_sw64(b_addr + k * 32, 8 * ROW_B);
+              umma_bf16(d_tmem, da, db, idesc, (uint32_t)((c | tap | k) != 0));
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue warps (2..5) ===========================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;            // accumulator row = tile pixel
+    const int py = m >> 3, px = m & 7;
+    const int co_base = ntile * nt;
+    uint32_t it = 0;
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int tx = (int)(tile % a.tiles_x);
+      long r = tile / a.tiles_x;
+      int ty = (int)(r % a.tiles_y);
+      int n = (int)(r / a.tiles_y);
+      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
+      const bool valid = (y < p.H) && (x < p.W);
+      const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
+      const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
+      const long opix = ((long)n * OH + oy) * OW + ox;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      for (int cg = 0; cg < nt; cg += 16) {
+        uint32_t rr[16];
+        tmem_ld16(t_addr + cg, rr);
+        tmem_ld_wait();
+        if (cg + 16 >= nt) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (valid) {
+          const int co = co_base + cg;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            float t = __uint_as_float(rr[j]);
+            if (a.bias) t += __ldg(a.bias + co + j);
+            t = apply_act(t, p.act, p.slope);
+            v[j] = t * p.alpha;
+          }
+          if (a.res1) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + opix * p.res1_cs + p.res1_coff + co);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              uint4 u = __ldg(rp + h);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                float2 f = __bfloat1622float2(b2[j]);
+                v[h * 8 + 2 * j] = fmaf(p.beta1, f.x, v[h * 8 + 2 * j]);
+                v[h * 8 + 2 * j + 1] = fmaf(p.beta1, f.y, v[h * 8 + 2 * j + 1]);
+              }
+            }
+          }
+          if (a.res2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + opix * p.res2_cs + p.res2_coff + co);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              uint4 u = __ldg(rp + h);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                float2 f = __bfloat1622float2(b2[j]);
+                v[h * 8 + 2 * j] = fmaf(p.beta2, f.x, v[h * 8 + 2 * j]);
+                v[h * 8 + 2 * j + 1] = fmaf(p.beta2, f.y, v[h * 8 + 2 * j + 1]);
+              }
+            }
+          }
+          if (a.mask_src && co + 16 > p.mask_c0 && co < p.mask_c1) {
+            const __nv_bfloat16* mp = a.mask_src + opix * p.mask_cs + p.mask_coff + (co - p.mask_c0);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              int cc = co + j;
+              if (cc >= p.mask_c0 && cc < p.mask_c1) {
+                float mv = __bfloat162float(mp[j]);
+                if (!(mv > 0.f)) v[j] *= p.mask_slope;
+              }
+            }
+          }
+          uint4 o[2];
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          uint4* op = reinterpret_cast<uint4*>(a.out + opix * p.out_cs + p.out_coff + co);
+          op[0] = o[0];
+          op[1] = o[1];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter packing: OIHW fp32 -> [variant][tap][chunk][cout][32] bf16
+// ---------------------------------------------------------------------------------------------
+// kind 0: plain 3x3 fprop        : 1 variant, tap = dy*3+dx, B[co][ci] = w[co][ci][dy][dx]
+// kind 1: dgrad of 3x3 s1 p1     : 1 variant, GEMM-N = fwd cin, GEMM-K = fwd cout,
+//                                  tap (dy,dx) uses w[kco][nci][2-dy][2-dx]
+// kind 2: nearest-x2 + 3x3       : 4 variants (py,px), taps (a,b) in {0,1}^2; halo row = py + a,
+//                                  filter rows summed:  py=0: a=0 -> {0}, a=1 -> {1,2};  py=1: a=0 -> {0,1}, a=1 -> {2}
+__global__ void pack_filter_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int cout, int cin,
+                                      int kind) {
+  const int gn = (kind == 1) ? cin : cout;   // GEMM N (output channels of this conv)
+  const int gk = (kind == 1) ? cout : cin;   // GEMM K channels
+  const int nvar = (kind == 2) ? 4 : 1, ntaps = (kind == 2) ? 4 : 9, nchunks = gk / CHUNK;
+  long total = (long)nvar * ntaps * nchunks * gn * CHUNK;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int kc = (int)(i % CHUNK);
+  long r = i / CHUNK;
+  int nn = (int)(r % gn); r /= gn;
+  int c = (int)(r % nchunks); r /= nchunks;
+  int tap = (int)(r % ntaps);
+  int var = (int)(r / ntaps);
+  int kk = c * CHUNK + kc;
+  float v = 0.f;
+  if (kind == 0) {
+    v = w[((long)nn * cin + kk) * 9 + tap];
+  } else if (kind == 1) {
+    int dy = tap / 3, dx = tap % 3;
+    v = w[((long)kk * cin + nn) * 9 + (2 - dy) * 3 + (2 - dx)];
+  } else {
+    int py = var >> 1, px = var & 1, ta = tap >> 1, tb = tap & 1;
+    int r0, r1, c0, c1;
+    if (py == 0) { r0 = ta ? 1 : 0; r1 = ta ? 2 : 0; } else { r0 = ta ? 2 : 0; r1 = ta ? 2 : 1; }
+    if (px == 0) { c0 = tb ? 1 : 0; c1 = tb ? 2 : 0; } else { c0 = tb ? 2 : 0; c1 = tb ? 2 : 1; }
+    for (int rr = r0; rr <= r1; rr++)
+      for (int cc = c0; cc <= c1; cc++) v += w[((long)nn * cin + kk) * 9 + rr * 3 + cc];
+  }
+  o[i] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int pow2_at_least(int v) {
+  int r = 32;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" {
+
+int dasr_conv_tc_setup(DasrConvTcParams* p, int kind) {
+  if (!p) return DASR_E_BADARG;
+  if (kind == 0 || kind == 1) {
+    p->nvar = 1;
+    p->ntaps = 9;
+    p->out_mul = 1;
+    for (int t = 0; t < 9; t++) {
+      p->tap_dy[0][t] = (int8_t)(t / 3);
+      p->tap_dx[0][t] = (int8_t)(t % 3);
+    }
+    p->out_py[0] = p->out_px[0] = 0;
+  } else if (kind == 2) {
+    p->nvar = 4;
+    p->ntaps = 4;
+    p->out_mul = 2;
+    for (int v = 0; v < 4; v++) {
+      int py = v >> 1, px = v & 1;
+      p->out_py[v] = py;
+      p->out_px[v] = px;
+      for (int t = 0; t < 4; t++) {
+        p->tap_dy[v][t] = (int8_t)(py + (t >> 1));
+        p->tap_dx[v][t] = (int8_t)(px + (t & 1));
+      }
+    }
+  } else {
+    set_error("conv_tc_setup: unknown kind %d", kind);
+    return DASR_E_BADARG;
+  }
+  return DASR_OK;
+}
+
+size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind) {
+  int nvar = (kind == 2) ? 4 : 1, ntaps = (kind == 2) ? 4 : 9;
+  return (size_t)nvar * ntaps * cout * cin * 2;
+}
+
+int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, void* stream) {
+  DASR_REQUIRE(kind >= 0 && kind <= 2, "pack_filter_tc: kind");
+  int gk = (kind == 1) ? cout : cin;
+  DASR_REQUIRE(gk % CHUNK == 0, "pack_filter_tc: contraction channels (%d) must be a multiple of 32", gk);
+  long total = (long)dasr_pack_filter_tc_bytes(cout, cin, kind) / 2;
+  pack_filter_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)o, cout, cin, kind);
+  return check_launch("pack_filter_tc");
+}
+
+int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* res1, const void* res2,
+                 const void* mask_src, void* out, const DasrConvTcParams* p, void* stream) {
+  DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
+  DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
+  DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc: cin must be a multiple of 32 (got %d)", p->cin);
+  DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc: input slice");
+  DASR_REQUIRE(p->nt >= 16 && p->nt <= 256 && p->nt % 16 == 0 && p->cout % p->nt == 0, "conv_tc: nt=%d cout=%d",
+               p->nt, p->cout);
+  DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc: output slice");
+  DASR_REQUIRE(p->nvar >= 1 && p->nvar <= 4 && p->ntaps >= 1 && p->ntaps <= 9, "conv_tc: variants/taps");
+  DASR_REQUIRE(p->out_mul == 1 || p->out_mul == 2, "conv_tc: out_mul");
+  if (res1) DASR_REQUIRE(p->res1_cs % 8 == 0 && p->res1_coff % 8 == 0, "conv_tc: res1 alignment");
+  if (res2) DASR_REQUIRE(p->res2_cs % 8 == 0 && p->res2_coff % 8 == 0, "conv_tc: res2 alignment");
+  DASR_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+               "conv_tc: pointers must be 16-byte aligned");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("conv_tc: cuTensorMapEncodeTiled not available");
+    return DASR_E_NODRIVER;
+  }
+
+  TcKernelArgs a;
+  a.p = *p;
+  a.bias = bias;
+  a.res1 = (const __nv_bfloat16*)res1;
+  a.res2 = (const __nv_bfloat16*)res2;
+  a.mask_src = (const __nv_bfloat16*)mask_src;
+  a.out = (__nv_bfloat16*)out;
+  a.nchunks = p->cin / CHUNK;
+  a.n_ntiles = p->cout / p->nt;
+  a.tiles_x = cdiv(p->W, TILE_W);
+  a.tiles_y = cdiv(p->H, TILE_H);
+  a.ntiles = (long)p->N * a.tiles_x * a.tiles_y;
+  a.w_bytes = p->ntaps * a.nchunks * p->nt * ROW_B;
+  a.a_stage_bytes = (p->a_mode == 0) ? ((A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
+  a.tmem_cols = pow2_at_least(2 * p->nt);
+  const int bar_bytes = (2 * MAX_STAGES + 5) * 8 + 16;
+  int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - bar_bytes;
+  int stages = avail / a.a_stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) {
+    set_error("conv_tc: resident filters (%d B) + 2 A stages do not fit shared memory; use a smaller nt", a.w_bytes);
+    return DASR_E_SMEM;
+  }
+  a.stages = stages;
+  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + bar_bytes;
+  // one CTA per SM is assumed by the TMEM allocation (2 x nt columns): make sure two CTAs never co-reside
+  if (smem < 120 * 1024) smem = 120 * 1024;
+
+  CUtensorMap tm_in, tm_w;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2,
+                          (cuuint64_t)p->H * p->W * p->in_cs * 2};
+    cuuint32_t box[4] = {CHUNK, (cuuint32_t)(p->a_mode == 0 ? HALO_W : TILE_W),
+                         (cuuint32_t)(p->a_mode == 0 ? HALO_H : TILE_H), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r);
+      return DASR_E_LAUNCH;
+    }
+  }
+  {
+    cuuint64_t rows = (cuuint64_t)p->nvar * p->ntaps * a.nchunks * p->cout;
+    cuuint64_t gdim[2] = {CHUNK, rows};
+    cuuint64_t gstr[1] = {ROW_B};
+    cuuint32_t box[2] = {CHUNK, (cuuint32_t)p->nt};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tc: cuTensorMapEncodeTiled(filter) failed: %d", (int)r);
+      return DASR_E_LAUNCH;
+    }
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return DASR_E_LAUNCH;
+    }
+    attr_set = true;
+  }
+  int gy = p->nvar * a.n_ntiles;
+  int gx = num_sms() / gy;
+  if (gx < 1) gx = 1;
+  if ((long)gx > a.ntiles) gx = (int)a.ntiles;
+  dim3 grid(gx, gy);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, a);
+  return check_launch("conv_tc");
+}
+
+}  // extern "C"

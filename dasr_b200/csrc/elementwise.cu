@@ -1,0 +1,575 @@
+// HBM-bound kernels of the DASR SRN path: layout changes, activation/upsample/pool backward,
+// InstanceNorm+LeakyReLU, Haar split, depthwise low/high-pass filter, bilinear resize, losses.
+// All reductions are two-stage and deterministic (no atomics).
+#include "common.cuh"
+
+namespace dasr {
+
+template <typename T> __device__ __forceinline__ float ld(const T* p);
+template <> __device__ __forceinline__ float ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st(T* p, float v);
+template <> __device__ __forceinline__ void st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// ---- NCHW fp32 <-> NHWC (tile transpose through shared memory: coalesced on both sides) --------
+// one block handles 32 pixels x up to 32 channels
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long HW, int dst_cs,
+                                    int dst_coff, const float* __restrict__ mean, const float* __restrict__ stdv) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    int c = c0 + cc;
+    long pp = p0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && pp < HW) {
+      v = src[((long)n * C + c) * HW + pp];
+      if (mean) v = (v - mean[c]) / stdv[c];
+    }
+    tile[cc][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int pi = threadIdx.y; pi < 32; pi += blockDim.y) {
+    long pp = p0 + pi;
+    int c = c0 + threadIdx.x;
+    if (c < C && pp < HW) st<T>(dst + ((long)n * HW + pp) * dst_cs + dst_coff + c, tile[threadIdx.x][pi]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long HW, int src_cs,
+                                    int src_coff, const float* __restrict__ inv_std) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int pi = threadIdx.y; pi < 32; pi += blockDim.y) {
+    long pp = p0 + pi;
+    int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && pp < HW) v = ld<T>(src + ((long)n * HW + pp) * src_cs + src_coff + c);
+    tile[pi][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    int c = c0 + cc;
+    long pp = p0 + threadIdx.x;
+    if (c < C && pp < HW) {
+      float v = tile[threadIdx.x][cc];
+      if (inv_std) v *= inv_std[c];
+      dst[((long)n * C + c) * HW + pp] = v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void act_bwd_kernel(T* __restrict__ g, const T* __restrict__ y, long npix, int C, int g_cs, int g_coff,
+                               int y_cs, int y_coff, float slope) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  long pp = i / C;
+  int c = (int)(i - pp * C);
+  float yv = ld<T>(y + pp * y_cs + y_coff + c);
+  if (!(yv > 0.f)) {
+    T* gp = g + pp * g_cs + g_coff + c;
+    st<T>(gp, ld<T>(gp) * slope);
+  }
+}
+
+template <typename T>
+__global__ void upsample2x_bwd_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C,
+                                      int src_cs, int src_coff, int dst_cs, int dst_coff) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * W * C;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long pp = i / C;
+  int x = (int)(pp % W);
+  long r = pp / W;
+  int y = (int)(r % H);
+  int n = (int)(r / H);
+  const long W2 = 2L * W;
+  long b = ((long)n * 2 * H + 2 * y) * W2 + 2 * x;
+  float s = ld<T>(src + b * src_cs + src_coff + c) + ld<T>(src + (b + 1) * src_cs + src_coff + c) +
+            ld<T>(src + (b + W2) * src_cs + src_coff + c) + ld<T>(src + (b + W2 + 1) * src_cs + src_coff + c);
+  st<T>(dst + pp * dst_cs + dst_coff + c, s);
+}
+
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ d, long npix, int C,
+                             int x_cs, int x_coff, int y_cs, int y_coff, int d_cs, int d_coff, float a, float b) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  long pp = i / C;
+  int c = (int)(i - pp * C);
+  float v = a * ld<T>(x + pp * x_cs + x_coff + c);
+  if (y) v += b * ld<T>(y + pp * y_cs + y_coff + c);
+  st<T>(d + pp * d_cs + d_coff + c, v);
+}
+
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * OH * OW * C;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long pp = i / C;
+  int ox = (int)(pp % OW);
+  long r = pp / OW;
+  int oy = (int)(r % OH);
+  int n = (int)(r / OH);
+  long b = (((long)n * H + 2 * oy) * W + 2 * ox) * C + c;
+  float v = fmaxf(fmaxf(in[b], in[b + C]), fmaxf(in[b + (long)W * C], in[b + (long)W * C + C]));
+  out[i] = v;
+}
+// gradient goes to the FIRST maximal element in (row-major) window order, like ATen's max_pool2d
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ in, const float* __restrict__ out,
+                                    const float* __restrict__ dout, float* __restrict__ din, int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * OH * OW * C;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long pp = i / C;
+  int ox = (int)(pp % OW);
+  long r = pp / OW;
+  int oy = (int)(r % OH);
+  int n = (int)(r / OH);
+  long b = (((long)n * H + 2 * oy) * W + 2 * ox) * C + c;
+  long offs[4] = {0, (long)C, (long)W * C, (long)W * C + C};
+  float m = out[i], g = dout[i];
+  bool done = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float v = in[b + offs[k]];
+    bool hit = !done && (v == m);
+    din[b + offs[k]] = hit ? g : 0.f;
+    done = done || hit;
+  }
+}
+
+// ---- InstanceNorm (biased var, eps, no affine) + LeakyReLU, NHWC fp32 ---------------------------
+// grid (C/32 , N), block (32 channels, 8 pixel lanes)
+__global__ void instnorm_lrelu_fwd_kernel(float* __restrict__ x, float* __restrict__ stats, int HW, int C, float eps,
+                                          float slope) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float* xp = x + (long)n * HW * C;
+  float a = 0.f;
+  if (c < C)
+    for (int pp = threadIdx.y; pp < HW; pp += 8) a += xp[(long)pp * C + c];
+  s1[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  float mean = 0.f;
+  for (int k = 0; k < 8; k++) mean += s1[k][threadIdx.x];
+  mean /= (float)HW;
+  float v = 0.f;
+  if (c < C)
+    for (int pp = threadIdx.y; pp < HW; pp += 8) {
+      float d = xp[(long)pp * C + c] - mean;
+      v += d * d;
+    }
+  s2[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float var = 0.f;
+  for (int k = 0; k < 8; k++) var += s2[k][threadIdx.x];
+  var /= (float)HW;
+  const float rstd = rsqrtf(var + eps);
+  if (c < C) {
+    if (threadIdx.y == 0) {
+      stats[((long)n * C + c) * 2 + 0] = mean;
+      stats[((long)n * C + c) * 2 + 1] = rstd;
+    }
+    for (int pp = threadIdx.y; pp < HW; pp += 8) {
+      float t = (xp[(long)pp * C + c] - mean) * rstd;
+      xp[(long)pp * C + c] = t > 0.f ? t : t * slope;
+    }
+  }
+}
+// y = lrelu(xhat); g = dy * lrelu'(y); dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
+__global__ void instnorm_lrelu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats,
+                                          const float* __restrict__ dy, float* __restrict__ dx, int HW, int C,
+                                          float slope) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long base = (long)n * HW * C;
+  float a = 0.f, b = 0.f;
+  if (c < C)
+    for (int pp = threadIdx.y; pp < HW; pp += 8) {
+      float yv = y[base + (long)pp * C + c];
+      float g = dy[base + (long)pp * C + c];
+      float xh = yv;
+      if (!(yv > 0.f)) { g *= slope; xh = yv / slope; }
+      a += g;
+      b += g * xh;
+    }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  float mg = 0.f, mgx = 0.f;
+  for (int k = 0; k < 8; k++) { mg += s1[k][threadIdx.x]; mgx += s2[k][threadIdx.x]; }
+  mg /= (float)HW;
+  mgx /= (float)HW;
+  if (c < C) {
+    const float rstd = stats[((long)n * C + c) * 2 + 1];
+    for (int pp = threadIdx.y; pp < HW; pp += 8) {
+      float yv = y[base + (long)pp * C + c];
+      float g = dy[base + (long)pp * C + c];
+      float xh = yv;
+      if (!(yv > 0.f)) { g *= slope; xh = yv / slope; }
+      dx[base + (long)pp * C + c] = rstd * (g - mg - xh * mgx);
+    }
+  }
+}
+
+// ---- Haar J=1 split (pytorch_wavelets DWTForward 'haar', even H,W) ------------------------------
+// a=x[2i,2j] b=x[2i,2j+1] c=x[2i+1,2j] d=x[2i+1,2j+1]
+// LL=(a+b+c+d)/2  LH=(a+b-c-d)/2  HL=(a-b+c-d)/2  HH=(a-b-c+d)/2 ; hc channel = band*C + ch
+__global__ void haar_fwd_kernel(const float* __restrict__ x, float* __restrict__ ll, float* __restrict__ hc, int N,
+                                int C, int H, int W, float s, float off) {
+  const int h2 = H / 2, w2 = W / 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * C * h2 * w2;
+  if (i >= total) return;
+  int j = (int)(i % w2);
+  long r = i / w2;
+  int ii = (int)(r % h2);
+  r /= h2;
+  int c = (int)(r % C);
+  int n = (int)(r / C);
+  const float* xp = x + (((long)n * C + c) * H + 2 * ii) * W + 2 * j;
+  const float2 top = *reinterpret_cast<const float2*>(xp);
+  const float2 bot = *reinterpret_cast<const float2*>(xp + W);
+  float a = top.x, b = top.y, cc = bot.x, d = bot.y;
+  if (ll) ll[i] = 0.5f * (a + b + cc + d) * s;
+  if (hc) {
+    long plane = (long)h2 * w2;
+    long o = ((long)n * 3 * C + c) * plane + (long)ii * w2 + j;
+    hc[o] = 0.5f * (a + b - cc - d) * s + off;
+    hc[o + (long)C * plane] = 0.5f * (a - b + cc - d) * s + off;
+    hc[o + 2L * C * plane] = 0.5f * (a - b - cc + d) * s + off;
+  }
+}
+__global__ void haar_bwd_kernel(const float* __restrict__ dll, const float* __restrict__ dhc, float* __restrict__ dx,
+                                int N, int C, int H, int W, float s) {
+  const int h2 = H / 2, w2 = W / 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * C * h2 * w2;
+  if (i >= total) return;
+  int j = (int)(i % w2);
+  long r = i / w2;
+  int ii = (int)(r % h2);
+  r /= h2;
+  int c = (int)(r % C);
+  int n = (int)(r / C);
+  float gl = dll ? dll[i] : 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  if (dhc) {
+    long plane = (long)h2 * w2;
+    long o = ((long)n * 3 * C + c) * plane + (long)ii * w2 + j;
+    g1 = dhc[o];
+    g2 = dhc[o + (long)C * plane];
+    g3 = dhc[o + 2L * C * plane];
+  }
+  const float k = 0.5f * s;
+  float* xp = dx + (((long)n * C + c) * H + 2 * ii) * W + 2 * j;
+  *reinterpret_cast<float2*>(xp) = make_float2(k * (gl + g1 + g2 + g3), k * (gl + g1 - g2 - g3));
+  *reinterpret_cast<float2*>(xp + W) = make_float2(k * (gl - g1 + g2 - g3), k * (gl - g1 - g2 + g3));
+}
+
+// ---- depthwise k x k stencil (Gaussian / box), zero padding, stride 1, NCHW fp32 ----------------
+// transpose=1 applies the adjoint (for symmetric taps it is the same stencil except for the
+// count_include_pad=0 box filter, whose divisor belongs to the OUTPUT position).
+__global__ void dwfilter_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ taps,
+                                int NC, int H, int W, int k, int mode, int count_include_pad, int transpose) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)NC * H * W;
+  if (i >= total) return;
+  int xw = (int)(i % W);
+  long r = i / W;
+  int yh = (int)(r % H);
+  long nc = r / H;
+  const int pad = (k - 1) / 2;
+  const float* xp = x + nc * H * W;
+  float low = 0.f;
+  for (int dy = 0; dy < k; dy++) {
+    int sy = yh + dy - pad;
+    if (sy < 0 || sy >= H) continue;
+    for (int dx = 0; dx < k; dx++) {
+      int sx = xw + dx - pad;
+      if (sx < 0 || sx >= W) continue;
+      float wgt;
+      if (taps) {
+        wgt = transpose ? taps[(k - 1 - dy) * k + (k - 1 - dx)] : taps[dy * k + dx];
+      } else if (count_include_pad) {
+        wgt = 1.f / (float)(k * k);
+      } else {
+        // divisor = number of in-image taps of the window centred at the OUTPUT position of the forward op
+        int cy = transpose ? sy : yh, cx = transpose ? sx : xw;
+        int ny = min(cy + pad, H - 1) - max(cy - pad, 0) + 1;
+        int nx = min(cx + pad, W - 1) - max(cx - pad, 0) + 1;
+        wgt = 1.f / (float)(ny * nx);
+      }
+      low = fmaf(wgt, xp[(long)sy * W + sx], low);
+    }
+  }
+  if (mode == 0)
+    out[i] = low;
+  else if (!transpose)
+    out[i] = 0.5f + 0.5f * (xp[(long)yh * W + xw] - low);
+  else
+    out[i] = 0.5f * (xp[(long)yh * W + xw] - low);
+}
+
+// ---- bilinear resize, align_corners=False (ATen upsample_bilinear2d semantics) -------------------
+__global__ void bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int NC, int H, int W, int OH,
+                                int OW) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)NC * OH * OW;
+  if (i >= total) return;
+  int ox = (int)(i % OW);
+  long r = i / OW;
+  int oy = (int)(r % OH);
+  long nc = r / OH;
+  const float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+  float fy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  float ly = fy - y0, lx = fx - x0;
+  const float* sp = src + nc * H * W;
+  float v = (1.f - ly) * ((1.f - lx) * sp[(long)y0 * W + x0] + lx * sp[(long)y0 * W + x1]) +
+            ly * ((1.f - lx) * sp[(long)y1 * W + x0] + lx * sp[(long)y1 * W + x1]);
+  dst[i] = v;
+}
+
+// ---- losses ---------------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 512, RED_THREADS = 256;
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sh[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+__global__ void final_sum_kernel(const float* __restrict__ part, float* __restrict__ out, int n, float scale) {
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = block_sum(v);
+  if (threadIdx.x == 0) *out = v * scale;
+}
+// kind 0: w*|a-b| (w nullable)   1: (a-b)^2   2: bce_with_logits(a, target)   3: a
+__global__ void loss_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                    const float* __restrict__ w, float* __restrict__ part, float* __restrict__ grad,
+                                    float gscale, long n, int C, long HW, int kind, float target) {
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float av = a[i];
+    float val, g = 0.f;
+    if (kind == 0) {
+      float d = av - b[i];
+      float wv = 1.f;
+      if (w) {
+        long nn = i / ((long)C * HW);
+        long hw = i % HW;
+        wv = w[nn * HW + hw];
+      }
+      val = wv * fabsf(d);
+      g = d > 0.f ? wv : (d < 0.f ? -wv : 0.f);
+    } else if (kind == 1) {
+      float d = av - b[i];
+      val = d * d;
+      g = 2.f * d;
+    } else if (kind == 2) {
+      // max(x,0) - x*t + log1p(exp(-|x|))   (ATen binary_cross_entropy_with_logits)
+      val = fmaxf(av, 0.f) - av * target + log1pf(expf(-fabsf(av)));
+      g = 1.f / (1.f + expf(-av)) - target;
+    } else {
+      val = av;
+    }
+    acc += val;
+    if (grad) grad[i] = g * gscale;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+static int run_loss(const float* a, const float* b, const float* w, float* loss, float* grad, float gscale, long n,
+                    int C, long HW, int kind, float target, float* partials, void* stream) {
+  DASR_REQUIRE(n > 0 && partials && loss, "loss: bad arguments");
+  int blocks = (int)((n + RED_THREADS - 1) / RED_THREADS);
+  if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+  cudaStream_t st = (cudaStream_t)stream;
+  loss_partial_kernel<<<blocks, RED_THREADS, 0, st>>>(a, b, w, partials, grad, gscale, n, C, HW, kind, target);
+  final_sum_kernel<<<1, 256, 0, st>>>(partials, loss, blocks, 1.f / (float)n);
+  return check_launch("loss");
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" {
+
+int dasr_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_cs, int dst_coff,
+                      int dst_is_bf16, const float* mean, const float* stdv, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && dst_cs >= dst_coff + C, "nchw_to_nhwc: bad dims");
+  long HW = (long)H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  if (dst_is_bf16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, HW, dst_cs,
+                                                                                dst_coff, mean, stdv);
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (float*)dst, C, HW, dst_cs, dst_coff, mean,
+                                                                        stdv);
+  return check_launch("nchw_to_nhwc");
+}
+
+int dasr_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_cs, int src_coff,
+                      int src_is_bf16, const float* inv_std, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && src_cs >= src_coff + C, "nhwc_to_nchw: bad dims");
+  long HW = (long)H * W;
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+  if (src_is_bf16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, HW,
+                                                                                src_cs, src_coff, inv_std);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, HW, src_cs, src_coff,
+                                                                        inv_std);
+  return check_launch("nhwc_to_nchw");
+}
+
+int dasr_act_bwd(void* g, const void* y, long npix, int C, int g_cs, int g_coff, int y_cs, int y_coff, float slope,
+                 int is_bf16, void* stream) {
+  DASR_REQUIRE(npix > 0 && C > 0, "act_bwd: bad dims");
+  long total = npix * C;
+  if (is_bf16)
+    act_bwd_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)g, (const __nv_bfloat16*)y, npix, C, g_cs, g_coff, y_cs, y_coff, slope);
+  else
+    act_bwd_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)g, (const float*)y, npix, C, g_cs,
+                                                                               g_coff, y_cs, y_coff, slope);
+  return check_launch("act_bwd");
+}
+
+int dasr_upsample2x_bwd(const void* src, void* dst, int N, int H, int W, int C, int src_cs, int src_coff, int dst_cs,
+                        int dst_coff, int is_bf16, void* stream) {
+  DASR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "upsample2x_bwd: bad dims");
+  long total = (long)N * H * W * C;
+  if (is_bf16)
+    upsample2x_bwd_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, H, W, C, src_cs, src_coff, dst_cs, dst_coff);
+  else
+    upsample2x_bwd_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)src, (float*)dst, N, H, W, C, src_cs, src_coff, dst_cs, dst_coff);
+  return check_launch("upsample2x_bwd");
+}
+
+int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff, int y_cs, int y_coff,
+               int d_cs, int d_coff, float a, float b, int is_bf16, void* stream) {
+  DASR_REQUIRE(npix > 0 && C > 0 && x && dst, "axpby: bad arguments");
+  long total = npix * C;
+  if (is_bf16)
+    axpby_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs,
+        d_coff, a, b);
+  else
+    axpby_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (const float*)y, (float*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs, d_coff, a, b);
+  return check_launch("axpby");
+}
+
+int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream) {
+  DASR_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: H,W must be even");
+  long total = (long)N * (H / 2) * (W / 2) * C;
+  maxpool2_fwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C);
+  return check_launch("maxpool2_fwd");
+}
+int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H, int W, int C,
+                      void* stream) {
+  DASR_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: H,W must be even");
+  long total = (long)N * (H / 2) * (W / 2) * C;
+  maxpool2_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, dout, din, N, H, W, C);
+  return check_launch("maxpool2_bwd");
+}
+
+int dasr_instnorm_lrelu_fwd(float* x, float* stats, int N, int HW, int C, float eps, float slope, void* stream) {
+  DASR_REQUIRE(N > 0 && HW > 0 && C > 0, "instnorm: bad dims");
+  dim3 grid(cdiv(C, 32), N), block(32, 8);
+  instnorm_lrelu_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, stats, HW, C, eps, slope);
+  return check_launch("instnorm_lrelu_fwd");
+}
+int dasr_instnorm_lrelu_bwd(const float* y, const float* stats, const float* dy, float* dx, int N, int HW, int C,
+                            float slope, void* stream) {
+  DASR_REQUIRE(N > 0 && HW > 0 && C > 0 && slope != 0.f, "instnorm bwd: bad dims / slope");
+  dim3 grid(cdiv(C, 32), N), block(32, 8);
+  instnorm_lrelu_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, stats, dy, dx, HW, C, slope);
+  return check_launch("instnorm_lrelu_bwd");
+}
+
+int dasr_haar_fwd(const float* x, float* ll, float* hc, int N, int C, int H, int W, int norm, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "haar: bad dims");
+  DASR_REQUIRE(H % 2 == 0 && W % 2 == 0, "haar: odd H or W (%dx%d) would need mode='reflect' padding; unsupported", H, W);
+  long total = (long)N * C * (H / 2) * (W / 2);
+  haar_fwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, ll, hc, N, C, H, W, norm ? 0.5f : 1.f,
+                                                                       norm ? 0.5f : 0.f);
+  return check_launch("haar_fwd");
+}
+int dasr_haar_bwd(const float* dll, const float* dhc, float* dx, int N, int C, int H, int W, int norm, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "haar bwd: bad dims");
+  long total = (long)N * C * (H / 2) * (W / 2);
+  haar_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dll, dhc, dx, N, C, H, W, norm ? 0.5f : 1.f);
+  return check_launch("haar_bwd");
+}
+
+int dasr_dwfilter_fwd(const float* x, float* out, const float* taps, int N, int C, int H, int W, int k, int mode,
+                      int count_include_pad, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && k > 0 && (k & 1), "dwfilter: k must be odd");
+  long total = (long)N * C * H * W;
+  dwfilter_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, taps, N * C, H, W, k, mode,
+                                                                       count_include_pad, 0);
+  return check_launch("dwfilter_fwd");
+}
+int dasr_dwfilter_bwd(const float* dout, float* dx, const float* taps, int N, int C, int H, int W, int k, int mode,
+                      int count_include_pad, void* stream) {
+  DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && k > 0 && (k & 1), "dwfilter: k must be odd");
+  long total = (long)N * C * H * W;
+  dwfilter_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dout, dx, taps, N * C, H, W, k, mode,
+                                                                       count_include_pad, 1);
+  return check_launch("dwfilter_bwd");
+}
+
+int dasr_bilinear_fwd(const float* src, float* dst, int NC, int H, int W, int OH, int OW, void* stream) {
+  DASR_REQUIRE(NC > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "bilinear: bad dims");
+  long total = (long)NC * OH * OW;
+  bilinear_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, NC, H, W, OH, OW);
+  return check_launch("bilinear");
+}
+
+int dasr_wl1_loss(const float* a, const float* b, const float* w, float* loss, float* grad_a, float gscale, int N,
+                  int C, int HW, float* partials, void* stream) {
+  long n = (long)N * C * HW;
+  return run_loss(a, b, w, loss, grad_a, gscale / (float)n, n, C, HW, 0, 0.f, partials, stream);
+}
+int dasr_mse_loss(const float* a, const float* b, float* loss, float* grad_a, float gscale, long n, float* partials,
+                  void* stream) {
+  return run_loss(a, b, nullptr, loss, grad_a, gscale / (float)n, n, 1, 1, 1, 0.f, partials, stream);
+}
+int dasr_bce_logits_loss(const float* x, float target, float* loss, float* grad_x, float gscale, long n,
+                         float* partials, void* stream) {
+  return run_loss(x, nullptr, nullptr, loss, grad_x, gscale / (float)n, n, 1, 1, 2, target, partials, stream);
+}
+int dasr_mean(const float* x, float* out, long n, float* partials, void* stream) {
+  return run_loss(x, nullptr, nullptr, out, nullptr, 0.f, n, 1, 1, 3, 0.f, partials, stream);
+}
+
+}  // extern "C"

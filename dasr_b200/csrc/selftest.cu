@@ -1,0 +1,368 @@
+// Standalone GPU self-test / micro-benchmark of the C-ABI library (no Python, no torch).
+// Usage: selftest [check] [bench]      (default: both)
+// `check` compares every conv kernel with a CPU double-precision loop nest on small shapes;
+// `bench` times the RRDB-shaped tcgen05 convs at BASELINE config 2 size (16 x 256 x 256).
+// Test infrastructure only — nothing here is on the product path.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/dasr_b200.h"
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+static unsigned long long rng_state = 0x1234567ULL;
+static inline unsigned rnd() {
+  rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
+  return (unsigned)(rng_state >> 33);
+}
+// small dyadic rationals: exactly representable in bf16, products/sums exact in fp32
+static inline float rnd_q(int range, float denom) { return (float)((int)(rnd() % (2 * range + 1)) - range) / denom; }
+
+static int g_fail = 0;
+static void report(const char* name, double maxerr, double tol) {
+  bool ok = maxerr <= tol;
+  printf("[%s] %-58s max_err=%.3e tol=%.1e\n", ok ? "PASS" : "FAIL", name, maxerr, tol);
+  if (!ok) g_fail++;
+}
+
+template <typename T> static T* dalloc(size_t n) { T* p; CK(cudaMalloc(&p, n * sizeof(T))); CK(cudaMemset(p, 0, n * sizeof(T))); return p; }
+template <typename T> static void h2d(T* d, const std::vector<T>& h) { CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+template <typename T> static std::vector<T> d2h(const T* d, size_t n) { std::vector<T> h(n); CK(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return h; }
+
+// CPU reference conv (NHWC in with stride, OIHW weights), double accumulation
+static void cpu_conv(const std::vector<float>& in, int N, int H, int W, int cin, int in_cs, int in_coff,
+                     const std::vector<float>& w, const std::vector<float>* bias, int cout, int kh, int kw, int stride,
+                     int pad, int ups, int OH, int OW, std::vector<double>& out) {
+  out.assign((size_t)N * OH * OW * cout, 0.0);
+  for (int n = 0; n < N; n++)
+    for (int oy = 0; oy < OH; oy++)
+      for (int ox = 0; ox < OW; ox++)
+        for (int co = 0; co < cout; co++) {
+          double s = bias ? (*bias)[co] : 0.0;
+          for (int dy = 0; dy < kh; dy++)
+            for (int dx = 0; dx < kw; dx++) {
+              int ty = oy * stride - pad + dy, tx = ox * stride - pad + dx;
+              if (ty < 0 || tx < 0 || ty >= H * ups || tx >= W * ups) continue;
+              int iy = ty / ups, ix = tx / ups;
+              for (int ci = 0; ci < cin; ci++)
+                s += (double)in[((size_t)(n * H + iy) * W + ix) * in_cs + in_coff + ci] *
+                     (double)w[((size_t)(co * cin + ci) * kh + dy) * kw + dx];
+            }
+          out[((size_t)(n * OH + oy) * OW + ox) * cout + co] = s;
+        }
+}
+
+static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, int pad, int ups) {
+  char name[160];
+  int in_cs = cin + 8, in_coff = 4;
+  int OH = (H * ups + 2 * pad - k) / stride + 1, OW = (W * ups + 2 * pad - k) / stride + 1;
+  std::vector<float> in((size_t)N * H * W * in_cs), w((size_t)cout * cin * k * k), b(cout);
+  for (auto& v : in) v = rnd_q(8, 8.f);
+  for (auto& v : w) v = rnd_q(8, 16.f);
+  for (auto& v : b) v = rnd_q(8, 8.f);
+  std::vector<double> ref;
+  cpu_conv(in, N, H, W, cin, in_cs, in_coff, w, &b, cout, k, k, stride, pad, ups, OH, OW, ref);
+  float *din = dalloc<float>(in.size()), *dw = dalloc<float>(w.size()), *dwp = dalloc<float>(w.size()),
+        *db = dalloc<float>(cout), *dout = dalloc<float>(ref.size());
+  h2d(din, in); h2d(dw, w); h2d(db, b);
+  DasrConvF32Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = in_cs; p.in_coff = in_coff; p.OH = OH; p.OW = OW;
+  p.cout = cout; p.out_cs = cout; p.out_coff = 0; p.kh = k; p.kw = k; p.stride = stride; p.pad = pad; p.ups = ups;
+  p.mode = DASR_CONV_FWD; p.act = DASR_ACT_NONE; p.alpha = 1.f;
+  int rc = dasr_pack_filter_f32(dw, dwp, cout, cin, k, k, 0, 0);
+  rc |= dasr_conv2d_f32(din, dwp, db, nullptr, nullptr, dout, &p, 0);
+  CK(cudaDeviceSynchronize());
+  if (rc) printf("  rc=%d err=%s\n", rc, dasr_last_error());
+  auto got = d2h(dout, ref.size());
+  double me = 0;
+  for (size_t i = 0; i < ref.size(); i++) me = fmax(me, fabs(got[i] - ref[i]));
+  snprintf(name, sizeof(name), "conv_f32 fwd N%d %dx%d cin%d cout%d k%d s%d p%d ups%d", N, H, W, cin, cout, k, stride, pad, ups);
+  report(name, me, 1e-4);
+
+  // ---- dgrad: <dY, conv(X)> == <dgrad(dY), X>  checked element-wise against CPU transpose ----
+  if (ups == 1) {
+    std::vector<float> dy((size_t)N * OH * OW * cout);
+    for (auto& v : dy) v = rnd_q(8, 8.f);
+    std::vector<double> dxref((size_t)N * H * W * cin, 0.0);
+    for (int n = 0; n < N; n++)
+      for (int oy = 0; oy < OH; oy++)
+        for (int ox = 0; ox < OW; ox++)
+          for (int co = 0; co < cout; co++) {
+            double g = dy[((size_t)(n * OH + oy) * OW + ox) * cout + co];
+            for (int dyy = 0; dyy < k; dyy++)
+              for (int dxx = 0; dxx < k; dxx++) {
+                int iy = oy * stride - pad + dyy, ix = ox * stride - pad + dxx;
+                if (iy < 0 || ix < 0 || iy >= H || ix >= W) continue;
+                for (int ci = 0; ci < cin; ci++)
+                  dxref[((size_t)(n * H + iy) * W + ix) * cin + ci] += g * w[((size_t)(co * cin + ci) * k + dyy) * k + dxx];
+              }
+          }
+    float *ddy = dalloc<float>(dy.size()), *ddx = dalloc<float>(dxref.size()), *dwd = dalloc<float>(w.size());
+    h2d(ddy, dy);
+    DasrConvF32Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = N; q.H = OH; q.W = OW; q.cin = cout; q.in_cs = cout; q.in_coff = 0; q.OH = H; q.OW = W; q.cout = cin;
+    q.out_cs = cin; q.out_coff = 0; q.kh = k; q.kw = k; q.stride = stride; q.pad = pad; q.ups = 1;
+    q.mode = DASR_CONV_DGRAD; q.alpha = 1.f;
+    rc = dasr_pack_filter_f32(dw, dwd, cout, cin, k, k, 1, 0);
+    rc |= dasr_conv2d_f32(ddy, dwd, nullptr, nullptr, nullptr, ddx, &q, 0);
+    CK(cudaDeviceSynchronize());
+    if (rc) printf("  rc=%d err=%s\n", rc, dasr_last_error());
+    auto gx = d2h(ddx, dxref.size());
+    me = 0;
+    for (size_t i = 0; i < dxref.size(); i++) me = fmax(me, fabs(gx[i] - dxref[i]));
+    snprintf(name, sizeof(name), "conv_f32 dgrad N%d %dx%d cin%d cout%d k%d s%d p%d", N, H, W, cin, cout, k, stride, pad);
+    report(name, me, 1e-4);
+
+    // ---- wgrad ----
+    std::vector<double> dwref(w.size(), 0.0), dbref(cout, 0.0);
+    for (int n = 0; n < N; n++)
+      for (int oy = 0; oy < OH; oy++)
+        for (int ox = 0; ox < OW; ox++)
+          for (int co = 0; co < cout; co++) {
+            double g = dy[((size_t)(n * OH + oy) * OW + ox) * cout + co];
+            dbref[co] += g;
+            for (int dyy = 0; dyy < k; dyy++)
+              for (int dxx = 0; dxx < k; dxx++) {
+                int iy = oy * stride - pad + dyy, ix = ox * stride - pad + dxx;
+                if (iy < 0 || ix < 0 || iy >= H || ix >= W) continue;
+                for (int ci = 0; ci < cin; ci++)
+                  dwref[((size_t)(co * cin + ci) * k + dyy) * k + dxx] +=
+                      g * in[((size_t)(n * H + iy) * W + ix) * in_cs + in_coff + ci];
+              }
+          }
+    size_t wsb = dasr_conv2d_wgrad_f32_workspace(&p);
+    void* ws; CK(cudaMalloc(&ws, wsb));
+    float *ddw = dalloc<float>(w.size()), *ddb = dalloc<float>(cout);
+    rc = dasr_conv2d_wgrad_f32(din, ddy, ddw, ddb, &p, 0, ws, wsb, 0);
+    CK(cudaDeviceSynchronize());
+    if (rc) printf("  rc=%d err=%s\n", rc, dasr_last_error());
+    auto gw = d2h(ddw, w.size());
+    auto gb = d2h(ddb, (size_t)cout);
+    me = 0;
+    for (size_t i = 0; i < w.size(); i++) me = fmax(me, fabs(gw[i] - dwref[i]));
+    for (int i = 0; i < cout; i++) me = fmax(me, fabs(gb[i] - dbref[i]));
+    snprintf(name, sizeof(name), "conv_f32 wgrad N%d %dx%d cin%d cout%d k%d s%d p%d", N, H, W, cin, cout, k, stride, pad);
+    report(name, me, 2e-3);
+    cudaFree(ddy); cudaFree(ddx); cudaFree(dwd); cudaFree(ws); cudaFree(ddw); cudaFree(ddb);
+  }
+  cudaFree(din); cudaFree(dw); cudaFree(dwp); cudaFree(db); cudaFree(dout);
+}
+
+static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); i++) o[i] = __float2bfloat16(v[i]);
+  return o;
+}
+
+// tcgen05 conv vs CPU reference. kind 0 fprop, 1 dgrad, 2 upsample-fused
+static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, int a_mode, bool epi) {
+  char name[200];
+  const int gk = (kind == 1) ? cout : cin;   // contraction channels
+  const int gn = (kind == 1) ? cin : cout;   // produced channels
+  const int in_cs = gk + 32, in_coff = 8;
+  const int mul = (kind == 2) ? 2 : 1;
+  const int OH = H * mul, OW = W * mul;
+  const int out_cs = gn + 16, out_coff = 8;
+  std::vector<float> in((size_t)N * H * W * in_cs), w((size_t)cout * cin * 9), b(gn);
+  for (auto& v : in) v = rnd_q(8, 8.f);
+  for (auto& v : w) v = rnd_q(4, 16.f);
+  for (auto& v : b) v = rnd_q(8, 8.f);
+  // reference = plain conv with the right filter
+  std::vector<float> wref;
+  if (kind == 1) {  // dgrad: out[nci] = sum_{kco,tap} in[.., kco] * w[kco][nci][2-dy][2-dx]
+    wref.assign((size_t)gn * gk * 9, 0.f);
+    for (int kco = 0; kco < cout; kco++)
+      for (int nci = 0; nci < cin; nci++)
+        for (int t = 0; t < 9; t++) wref[((size_t)nci * gk + kco) * 9 + t] = w[((size_t)kco * cin + nci) * 9 + (8 - t)];
+  } else {
+    wref = w;
+  }
+  std::vector<double> ref;
+  cpu_conv(in, N, H, W, gk, in_cs, in_coff, wref, &b, gn, 3, 3, 1, 1, mul, OH, OW, ref);
+  std::vector<float> res1((size_t)N * OH * OW * gn), msk((size_t)N * OH * OW * gn);
+  for (auto& v : res1) v = rnd_q(8, 8.f);
+  for (auto& v : msk) v = rnd_q(8, 8.f);
+  const float slope = 0.25f, alpha = 0.5f, beta1 = 2.f, mslope = 0.25f;
+  const int mc0 = gn >= 32 ? gn - 24 : 0, mc1 = gn;
+  if (epi)
+    for (size_t i = 0; i < ref.size(); i++) {
+      double v = ref[i];
+      v = v > 0 ? v : v * slope;
+      v = alpha * v + beta1 * res1[i];
+      int c = (int)(i % gn);
+      if (c >= mc0 && c < mc1 && !(msk[i] > 0.f)) v *= mslope;
+      ref[i] = v;
+    }
+  auto in_b = to_bf16(in);
+  auto res_b = to_bf16(res1);
+  auto msk_b = to_bf16(msk);
+  __nv_bfloat16* din = dalloc<__nv_bfloat16>(in_b.size());
+  __nv_bfloat16* dres = dalloc<__nv_bfloat16>(res_b.size());
+  __nv_bfloat16* dmsk = dalloc<__nv_bfloat16>(msk_b.size());
+  __nv_bfloat16* dout = dalloc<__nv_bfloat16>((size_t)N * OH * OW * out_cs);
+  float *dw = dalloc<float>(w.size()), *db = dalloc<float>(gn);
+  size_t wpb = dasr_pack_filter_tc_bytes(cout, cin, kind);
+  void* dwp; CK(cudaMalloc(&dwp, wpb));
+  h2d(din, in_b); h2d(dres, res_b); h2d(dmsk, msk_b); h2d(dw, w); h2d(db, b);
+  DasrConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = dasr_conv_tc_setup(&p, kind);
+  p.N = N; p.H = H; p.W = W; p.cin = gk; p.in_cs = in_cs; p.in_coff = in_coff;
+  p.cout = gn; p.out_cs = out_cs; p.out_coff = out_coff; p.nt = nt;
+  p.act = epi ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = epi ? alpha : 1.f;
+  p.beta1 = beta1; p.res1_cs = gn; p.res1_coff = 0;
+  p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
+  p.a_mode = a_mode;
+  rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
+  rc |= dasr_conv_tc(din, dwp, db, epi ? dres : nullptr, nullptr, epi ? dmsk : nullptr, dout, &p, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d", kind, a_mode, N, H, W, gk, gn, nt, (int)epi);
+  if (rc || e != cudaSuccess) {
+    printf("[FAIL] %s rc=%d err=%s cuda=%s\n", name, rc, dasr_last_error(), cudaGetErrorString(e));
+    g_fail++;
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  auto got = d2h(dout, (size_t)N * OH * OW * out_cs);
+  double me = 0, mref = 0;
+  for (size_t pix = 0; pix < (size_t)N * OH * OW; pix++)
+    for (int c = 0; c < gn; c++) {
+      double r = ref[pix * gn + c];
+      double g = __bfloat162float(got[pix * out_cs + out_coff + c]);
+      me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
+      mref = fmax(mref, fabs(r));
+    }
+  report(name, me, 8e-3);
+  cudaFree(din); cudaFree(dres); cudaFree(dmsk); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
+}
+
+static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, int a_mode, int iters) {
+  const int in_cs = 192;
+  const int mul = (kind == 2) ? 2 : 1;
+  size_t in_n = (size_t)N * H * W * in_cs, out_n = (size_t)N * H * mul * W * mul * in_cs;
+  __nv_bfloat16* din = dalloc<__nv_bfloat16>(in_n);
+  __nv_bfloat16* dout = dalloc<__nv_bfloat16>(out_n);
+  std::vector<float> w((size_t)cout * cin * 9);
+  for (auto& v : w) v = rnd_q(4, 64.f);
+  float *dw = dalloc<float>(w.size()), *db = dalloc<float>(256);
+  h2d(dw, w);
+  void* dwp; CK(cudaMalloc(&dwp, dasr_pack_filter_tc_bytes(cout, cin, kind)));
+  DasrConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  dasr_conv_tc_setup(&p, kind);
+  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = in_cs; p.in_coff = 0;
+  p.cout = cout; p.out_cs = in_cs; p.out_coff = (cout <= 128) ? 64 : 0; p.nt = nt;
+  p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.a_mode = a_mode;
+  if (kind == 1) dasr_pack_filter_tc(dw, dwp, cin, cout, kind, 0);  // fwd conv had cout=K(cin here), cin=N(cout here)
+  else dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
+  int rc = 0;
+  for (int i = 0; i < 3; i++) rc |= dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc || e != cudaSuccess) {
+    printf("bench conv_tc cin%d cout%d nt%d kind%d amode%d: rc=%d %s cuda=%s\n", cin, cout, nt, kind, a_mode, rc,
+           dasr_last_error(), cudaGetErrorString(e));
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; i++) dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
+  cudaEventRecord(e1);
+  CK(cudaEventSynchronize(e1));
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  double taps = (kind == 2) ? 9.0 : 9.0;  // algorithmic FLOPs: always the 3x3 conv on the output grid
+  double flops = 2.0 * N * H * mul * W * mul * cin * cout * taps;
+  printf("bench conv_tc kind%d amode%d %dx%dx%d cin%-3d cout%-3d nt%-3d : %8.3f ms  %7.1f TFLOP/s (algorithmic)\n", kind,
+         a_mode, N, H, W, cin, cout, nt, ms, flops / ms * 1e-9);
+  cudaFree(din); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
+}
+
+static void bench_f32(int N, int H, int W, int cin, int cout, int iters) {
+  size_t in_n = (size_t)N * H * W * cin, out_n = (size_t)N * H * W * cout;
+  float *din = dalloc<float>(in_n), *dout = dalloc<float>(out_n), *dw = dalloc<float>((size_t)9 * cin * cout), *db = dalloc<float>(cout);
+  DasrConvF32Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = cin; p.OH = H; p.OW = W; p.cout = cout; p.out_cs = cout;
+  p.kh = p.kw = 3; p.stride = 1; p.pad = 1; p.ups = 1; p.alpha = 1.f;
+  for (int i = 0; i < 2; i++) dasr_conv2d_f32(din, dw, db, nullptr, nullptr, dout, &p, 0);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; i++) dasr_conv2d_f32(din, dw, db, nullptr, nullptr, dout, &p, 0);
+  cudaEventRecord(e1);
+  CK(cudaEventSynchronize(e1));
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("bench conv_f32 %dx%dx%d cin%-3d cout%-3d : %8.3f ms  %7.2f TFLOP/s\n", N, H, W, cin, cout, ms,
+         2.0 * N * H * W * cin * cout * 9 / ms * 1e-9);
+  cudaFree(din); cudaFree(dout); cudaFree(dw); cudaFree(db);
+}
+
+int main(int argc, char** argv) {
+  bool do_check = argc == 1, do_bench = argc == 1;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "check")) do_check = true;
+    if (!strcmp(argv[i], "bench")) do_bench = true;
+  }
+  setvbuf(stdout, NULL, _IOLBF, 0);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d SMs=%d smem_optin=%zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+         prop.sharedMemPerBlockOptin);
+  if (do_check) {
+    test_f32(2, 9, 11, 3, 64, 3, 1, 1, 1);
+    test_f32(2, 8, 8, 32, 32, 3, 1, 1, 1);
+    test_f32(1, 7, 5, 64, 3, 3, 1, 1, 1);
+    test_f32(2, 12, 10, 9, 64, 4, 2, 1, 1);
+    test_f32(1, 9, 9, 16, 20, 4, 1, 1, 1);
+    test_f32(1, 6, 7, 16, 16, 3, 1, 1, 2);
+    test_f32(1, 8, 8, 8, 1, 4, 1, 1, 1);
+    test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
+    // tcgen05: validation path first (one aligned tile per tap), then shifted-descriptor halo path
+    for (int am = 1; am >= 0; am--) {
+      test_tc(1, 16, 8, 32, 32, 32, 0, am, false);
+      test_tc(2, 32, 32, 64, 32, 32, 0, am, false);
+      test_tc(1, 20, 13, 96, 32, 32, 0, am, true);
+      test_tc(2, 32, 24, 192, 64, 32, 0, am, true);
+      test_tc(1, 32, 16, 64, 64, 64, 0, am, true);
+      test_tc(1, 24, 24, 160, 32, 160, 1, am, true);   // dgrad conv4-like: K=32 -> N=160
+      test_tc(1, 16, 16, 192, 64, 96, 1, am, false);   // dgrad conv5-like: K=64 -> N=192 split 2x96
+      test_tc(1, 16, 16, 64, 64, 64, 2, am, true);     // upsample-fused
+      test_tc(2, 19, 9, 64, 64, 32, 2, am, false);
+    }
+  }
+  if (do_bench) {
+    const int N = 16, H = 256, W = 256;
+    for (int am = 0; am <= 1; am++) {
+      bench_tc(N, H, W, 64, 32, 32, 0, am, 10);
+      bench_tc(N, H, W, 96, 32, 32, 0, am, 10);
+      bench_tc(N, H, W, 128, 32, 32, 0, am, 10);
+      bench_tc(N, H, W, 160, 32, 32, 0, am, 10);
+      bench_tc(N, H, W, 192, 64, 32, 0, am, 10);
+      bench_tc(N, H, W, 64, 64, 64, 0, am, 10);
+    }
+    bench_tc(N, H, W, 192, 64, 64, 0, 0, 10);
+    bench_tc(N, H, W, 64, 64, 64, 2, 0, 5);
+    bench_tc(N, H, W, 32, 192, 192, 1, 0, 10);
+    bench_f32(4, 256, 256, 64, 64, 3);
+    bench_f32(4, 256, 256, 192, 64, 3);
+  }
+  printf("selftest done: %d failure(s)\n", g_fail);
+  return g_fail ? 1 : 0;
+}

@@ -1,0 +1,203 @@
+/*
+ * dasr_b200 — C ABI of the B200-native DASR SRN hot path.
+ *
+ * The reference (ShuhangGu/DASR, codes/SRN) has no FFI layer: its hot path is a chain of
+ * torch.nn library calls (cuDNN/ATen).  Each entry point below replaces one such call site; the
+ * reference file:line it stands in for is cited next to it.  All entry points
+ *   - take raw DEVICE pointers, plain ints/floats and a cudaStream_t (passed as void*),
+ *   - never allocate, never synchronise, never throw; they return 0 or a negative DASR_E_* code,
+ *   - run on the stream they are given.
+ * Activations inside the path are NHWC ("pixels x channels") with an explicit channel stride, so a
+ * conv can read a channel prefix of a dense-block concat buffer and write its output into a channel
+ * slice of another one (kills torch.cat, block.py:280-286).
+ *
+ * Two arithmetic modes exist for every convolution:
+ *   *_f32 : CUDA-core fp32 FMA, fp32 storage     (the 1e-3 rel-Linf parity gate, BASELINE north_star)
+ *   *_tc  : tcgen05.mma bf16 x bf16 -> fp32 TMEM accumulators, bf16 storage (the performance path)
+ */
+#ifndef DASR_B200_H
+#define DASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DASR_OK 0
+#define DASR_E_BADARG (-1)   /* shape/alignment/argument outside what the kernel supports */
+#define DASR_E_LAUNCH (-2)   /* cudaLaunch / driver error (cudaGetLastError text via dasr_last_error) */
+#define DASR_E_NODRIVER (-3) /* cuTensorMapEncodeTiled entry point not found */
+#define DASR_E_SMEM (-4)     /* resident filter set does not fit shared memory: split Cout (nt) */
+
+/* activation enum used by conv epilogues */
+#define DASR_ACT_NONE 0
+#define DASR_ACT_LRELU 1 /* LeakyReLU(slope)  block.py:10-23 (slope 0.2) */
+#define DASR_ACT_RELU 2  /* ReLU, VGG19 features  architecture.py:1076 */
+
+/* gather mode of the generic fp32 conv */
+#define DASR_CONV_FWD 0   /* cross-correlation, zero padding               nn.Conv2d, block.py:142-143 */
+#define DASR_CONV_DGRAD 1 /* transposed gather: gradient w.r.t. the input of a FWD conv */
+
+const char* dasr_last_error(void);
+int dasr_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fp32 convolution (any k, stride, pad; optional nearest x2 upsample of the input folded
+ * into the gather: block.py:854-861 upconv_blcok = nn.Upsample(2,'nearest') + conv).
+ * Replaces: nn.Conv2d forward (block.py:142-143; architecture.py:998-1018 NLayerDiscriminator
+ * 4x4 s2/s1 convs; architecture.py:1076 VGG19 features) and, in DGRAD mode, its input gradient.
+ *
+ * out[n,oy,ox,co] = alpha * act(bias[co] + sum_{tap,ci} in[n,gy,gx,ci] * w[tap][ci][co])
+ *                   + beta1 * res1[n,oy,ox,co] + beta2 * res2[n,oy,ox,co]
+ * w is the PACKED filter [kh*kw][cin][cout] fp32 (see dasr_pack_filter_f32).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, H, W;            /* stored input dims (before the optional upsample) */
+  int cin, in_cs, in_coff;/* channels consumed, channel stride and channel offset of `in` */
+  int OH, OW;             /* output dims */
+  int cout, out_cs, out_coff;
+  int kh, kw, stride, pad;
+  int ups;                /* 1, or 2 = nearest x2 upsample of `in` before the conv (FWD only) */
+  int mode;               /* DASR_CONV_FWD / DASR_CONV_DGRAD */
+  int act; float slope;
+  float alpha;
+  float beta1; int res1_cs, res1_coff;
+  float beta2; int res2_cs, res2_coff;
+} DasrConvF32Params;
+
+int dasr_conv2d_f32(const float* in, const float* w_packed, const float* bias, const float* res1,
+                    const float* res2, float* out, const DasrConvF32Params* p, void* stream);
+
+/* Filter gradient of a FWD conv: dW (OIHW fp32, same layout as the nn.Parameter) and db.
+ * Replaces autograd's conv weight/bias gradient for the convs above.  Deterministic (two-stage
+ * split-K reduction, no atomics).  workspace >= dasr_conv2d_wgrad_f32_workspace(p) bytes. */
+size_t dasr_conv2d_wgrad_f32_workspace(const DasrConvF32Params* p);
+int dasr_conv2d_wgrad_f32(const float* in, const float* dout, float* dw_oihw, float* dbias /*nullable*/,
+                          const DasrConvF32Params* p, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* OIHW fp32 nn.Parameter -> packed [tap][cin][cout] fp32 (FWD) or the transposed/flipped-free
+ * [tap][cout][cin] layout DGRAD mode consumes. */
+int dasr_pack_filter_f32(const float* w_oihw, float* w_packed, int cout, int cin, int kh, int kw,
+                         int for_dgrad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 bf16 3x3 (and 2x2 sub-pixel) convolution — the RRDB hot kernel.
+ * Replaces: ResidualDenseBlock_5C.conv1..5 (block.py:262-286), RRDB / ShortcutBlock residuals
+ * (block.py:305-309, 103-105), LR_conv / upconv / HR_conv0 (architecture.py:182-201).
+ *
+ * in  : NHWC bf16, channel stride in_cs; the first `cin` channels starting at in_coff are consumed
+ *       in chunks of 32 (cin % 32 == 0).
+ * w   : packed by dasr_pack_filter_tc: [variant][tap][chunk][cout][32] bf16.
+ * out : NHWC bf16; pixel (y,x) of variant v goes to (y*out_mul + py[v], x*out_mul + px[v]).
+ * epilogue: v = alpha*act(acc + bias) + beta1*res1 + beta2*res2 ;
+ *           channels [mask_c0,mask_c1) additionally multiplied by (mask_src>0 ? 1 : mask_slope)
+ *           (LeakyReLU backward fused into the dgrad that completes a dense-block gradient slice).
+ * One variant with the 9 taps of a 3x3 = plain conv.  Four variants with 2x2 taps and pre-summed
+ * filters = nearest-x2 upsample + 3x3 conv without materialising the upsampled tensor.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, H, W;                 /* input dims == tile grid dims */
+  int cin, in_cs, in_coff;
+  int cout, out_cs, out_coff;
+  int nt;                      /* Cout tile per CTA (multiple of 16, <= 256, divides cout) */
+  int out_mul;                 /* 1 or 2 */
+  int nvar, ntaps;             /* variants (1 or 4), taps per variant (<= 9) */
+  int8_t tap_dy[4][9];         /* halo-tile row/col of each tap: 0,1,2  (1 = centre) */
+  int8_t tap_dx[4][9];
+  int out_py[4], out_px[4];
+  int act; float slope;
+  float alpha;
+  float beta1; int res1_cs, res1_coff;
+  float beta2; int res2_cs, res2_coff;
+  int mask_cs, mask_coff, mask_c0, mask_c1; float mask_slope;
+  int a_mode;                  /* 0 = one halo tile per chunk + shifted UMMA descriptors (fast);
+                                  1 = one aligned TMA tile per tap (validation path) */
+} DasrConvTcParams;
+
+int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias,
+                 const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16,
+                 void* out_bf16, const DasrConvTcParams* p, void* stream);
+
+/* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
+ *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)
+ *                                            2 = nearest-x2-upsample + 3x3 (4 variants x 4 taps, pre-summed)
+ * Fills the tap tables / variant fields of *p as well (host side). */
+int dasr_conv_tc_setup(DasrConvTcParams* p, int kind);
+size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind);
+int dasr_pack_filter_tc(const float* w_oihw, void* w_packed_bf16, int cout, int cin, int kind,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / elementwise / reductions (all HBM-bound).
+ * ---------------------------------------------------------------------------------------------- */
+/* NCHW fp32 <-> NHWC (fp32 or bf16) with channel stride/offset; optional per-channel (x-mean)/std
+ * (VGGFeatureExtractor input norm, architecture.py:1073-1086).  mean/std may be NULL. */
+int dasr_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_cs,
+                      int dst_coff, int dst_is_bf16, const float* mean, const float* std, void* stream);
+int dasr_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_cs,
+                      int src_coff, int src_is_bf16, const float* inv_std /*nullable: dst=src*inv_std*/,
+                      void* stream);
+/* g[...,c] *= (y[...,c] > 0 ? 1 : slope) on a channel slice (LeakyReLU/ReLU backward, block.py:18) */
+int dasr_act_bwd(void* g, const void* y, long npix, int C, int g_cs, int g_coff, int y_cs, int y_coff,
+                 float slope, int is_bf16, void* stream);
+/* dst[n,y,x,c] = sum of the 2x2 block of src (backward of nn.Upsample(2,'nearest'), block.py:858) */
+int dasr_upsample2x_bwd(const void* src, void* dst, int N, int H, int W, int C, int src_cs,
+                        int src_coff, int dst_cs, int dst_coff, int is_bf16, void* stream);
+/* dst = a*x + b*y on channel slices (gradient accumulation across concat consumers) */
+int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff,
+               int y_cs, int y_coff, int d_cs, int d_coff, float a, float b, int is_bf16, void* stream);
+/* 2x2 s2 max-pool NHWC fp32 fwd / bwd (VGG19 features, architecture.py:1076) */
+int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
+int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H,
+                      int W, int C, void* stream);
+
+/* InstanceNorm2d(affine=False, eps) + LeakyReLU(slope), NHWC fp32, in place on x.
+ * Replaces architecture.py:1005-1007,1013-1015.  stats[n][c][2] = (mean, rstd). */
+int dasr_instnorm_lrelu_fwd(float* x, float* stats, int N, int HW, int C, float eps, float slope,
+                            void* stream);
+/* dy (grad wrt post-activation output) -> dx, given the saved post-activation y and stats */
+int dasr_instnorm_lrelu_bwd(const float* y, const float* stats, const float* dy, float* dx, int N,
+                            int HW, int C, float slope, void* stream);
+
+/* Haar DWT J=1 frequency split with DASR's normalisation, NCHW fp32 in/out.
+ * Replaces DASR_Model.wavelet_s (DASR_model.py:442-452) -> pytorch_wavelets.DWTForward.
+ * ll[N,C,H/2,W/2] = LL*(norm?0.5:1); hc[N,3C,H/2,W/2] band-major (LH_c.., HL_c.., HH_c..),
+ * = band*(norm?0.5:1) + (norm?0.5:0). */
+int dasr_haar_fwd(const float* x, float* ll, float* hc, int N, int C, int H, int W, int norm, void* stream);
+int dasr_haar_bwd(const float* dll /*nullable*/, const float* dhc /*nullable*/, float* dx, int N, int C,
+                  int H, int W, int norm, void* stream);
+
+/* Depthwise k x k filter with one shared kernel (Gaussian low-pass, architecture.py:1177-1205) or
+ * box filter (AvgPool2d, :1218), zero padding (k-1)/2, stride 1, NCHW fp32.
+ * mode 0: out = low ; mode 1: out = 0.5 + 0.5*(x - low) (FilterHigh :1239-1241).
+ * count_include_pad only matters for the box filter (taps==NULL). */
+int dasr_dwfilter_fwd(const float* x, float* out, const float* taps /*k*k or NULL*/, int N, int C, int H,
+                      int W, int k, int mode, int count_include_pad, void* stream);
+int dasr_dwfilter_bwd(const float* dout, float* dx, const float* taps, int N, int C, int H, int W, int k,
+                      int mode, int count_include_pad, void* stream);
+
+/* Bilinear resize, align_corners=False, NCHW fp32 (F.interpolate in feed_data, DASR_model.py:172-174) */
+int dasr_bilinear_fwd(const float* src, float* dst, int NC, int H, int W, int OH, int OW, void* stream);
+
+/* Losses.  Each writes ONE fp32 scalar to *loss (deterministic two-stage reduction through
+ * `partials`, >= 1024 floats) and, if grad != NULL, the gradient scaled by gscale.
+ *   wl1 : mean(w[n,0,y,x] * |a - b|) over N*C*H*W           DASR_model.py:212-215
+ *         (w == NULL -> plain L1 mean, nn.L1Loss :75-80, :220-222, :225-229)
+ *   mse : mean((a-b)^2)
+ *   bce : BCEWithLogits(x, target) mean                      loss.py:16,36-40  (GANLoss vanilla)
+ */
+int dasr_wl1_loss(const float* a, const float* b, const float* w, float* loss, float* grad_a, float gscale,
+                  int N, int C, int HW, float* partials, void* stream);
+int dasr_mse_loss(const float* a, const float* b, float* loss, float* grad_a, float gscale, long n,
+                  float* partials, void* stream);
+int dasr_bce_logits_loss(const float* x, float target, float* loss, float* grad_x, float gscale, long n,
+                         float* partials, void* stream);
+int dasr_mean(const float* x, float* out, long n, float* partials, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASR_B200_H */
