@@ -93,6 +93,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate)
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -182,6 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;   // [2]
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 6);   // [nt] (16-byte aligned)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,6 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)a.tmem_cols);
+  for (int i = threadIdx.x; i < p.nt; i += TC_THREADS) sBias[i] = a.bias ? a.bias[(blockIdx.y % a.n_ntiles) * p.nt + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -248,44 +260,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, nt);
-      mbar_wait(w_bar, 0);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t it = 0;
-      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-        for (int c = 0; c < a.nchunks; c++) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + (size_t)stage * a.a_stage_bytes);
-          for (int tap = 0; tap < ntaps; tap++) {
-            uint32_t a_addr, a_sbo;
-            if (p.a_mode == 0) {
-              a_addr = a_base + (uint32_t)((p.tap_dy[var][tap] * HALO_W + p.tap_dx[var][tap]) * ROW_B);
-              a_sbo = HALO_W * ROW_B;  // 8-row group = one image row of the tile; next row is HALO_W pixels on
-            } else {
-              a_addr = a_base + (uint32_t)(tap * A_TAP_BYTES);
-              a_sbo = 8 * ROW_B;
-            }
-            const uint32_t b_addr = smem_u32(sW + (size_t)(tap * a.nchunks + c) * nt * ROW_B);
+    // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the tcgen05.mma
+    // instructions, so descriptors live in uniform registers and no per-lane serialisation is emitted.
+    const uint32_t idesc = make_idesc_bf16(128, nt);
+    // descriptor pieces in 16-byte units (start-address field) + constant high words
+    const uint32_t a_sbo = (p.a_mode == 0) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
+    const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
+    const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
+    const uint32_t a_lo0 = smem_u32(sA) >> 4;
+    const uint32_t a_stage_lo = (uint32_t)a.a_stage_bytes >> 4;
+    const uint32_t b_lo0 = smem_u32(sW) >> 4;
+    const uint32_t b_slot_lo = (uint32_t)(nt * ROW_B) >> 4;
+    uint32_t tap_lo[9];
 #pragma unroll
-            for (int k = 0; k < CHUNK / 16; k++) {
-              uint64_t da = make_desc_sw64(a_addr + k * 32, a_sbo);
-              uint64_t db = make_desc_sw64(b_addr + k * 32, 8 * ROW_B);
-              umma_bf16(d_tmem, da, db, idesc, (uint32_t)((c | tap | k) != 0));
+    for (int t = 0; t < 9; t++) {
+      int tt = t < ntaps ? t : 0;
+      tap_lo[t] = (p.a_mode == 0) ? (uint32_t)((p.tap_dy[var][tt] * HALO_W + p.tap_dx[var][tt]) * ROW_B) >> 4
+                                  : (uint32_t)(tt * A_TAP_BYTES) >> 4;
+    }
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+      for (int c = 0; c < a.nchunks; c++) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage_lo;
+          uint32_t b_lo = b_lo0 + (uint32_t)c * b_slot_lo;
+          const uint32_t b_tap_step = (uint32_t)a.nchunks * b_slot_lo;
+#pragma unroll
+          for (int tap = 0; tap < 9; tap++) {
+            if (tap < ntaps) {
+              const uint32_t al = a_lo + tap_lo[tap];
+              umma_bf16(d_tmem, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
+                        (uint32_t)((c | tap) != 0));
+              umma_bf16(d_tmem, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
+              b_lo += b_tap_step;
             }
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          if (c == a.nchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -294,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int m = q * 32 + lane;            // accumulator row = tile pixel
     const int py = m >> 3, px = m & 7;
     const int co_base = ntile * nt;
+    const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
     uint32_t it = 0;
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
@@ -305,7 +331,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const int y = ty * TILE_H + py, x = tx * TILE_W + px;
       const bool valid = (y < p.H) && (x < p.W);
       const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
-      const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
       const long opix = ((long)n * OH + oy) * OW + ox;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -324,39 +349,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         if (valid) {
           const int co = co_base + cg;
           float v[16];
+          const float4* bp = reinterpret_cast<const float4*>(sBias + cg);
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            float t = __uint_as_float(rr[j]);
-            if (a.bias) t += __ldg(a.bias + co + j);
-            t = apply_act(t, p.act, p.slope);
-            v[j] = t * p.alpha;
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 b4 = bp[j4];
+            v[4 * j4 + 0] = apply_act(__uint_as_float(rr[4 * j4 + 0]) + b4.x, p.act, p.slope) * p.alpha;
+            v[4 * j4 + 1] = apply_act(__uint_as_float(rr[4 * j4 + 1]) + b4.y, p.act, p.slope) * p.alpha;
+            v[4 * j4 + 2] = apply_act(__uint_as_float(rr[4 * j4 + 2]) + b4.z, p.act, p.slope) * p.alpha;
+            v[4 * j4 + 3] = apply_act(__uint_as_float(rr[4 * j4 + 3]) + b4.w, p.act, p.slope) * p.alpha;
           }
           if (a.res1) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + opix * p.res1_cs + p.res1_coff + co);
+            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+            const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              uint4 u = __ldg(rp + h);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float2 f = __bfloat1622float2(b2[j]);
-                v[h * 8 + 2 * j] = fmaf(p.beta1, f.x, v[h * 8 + 2 * j]);
-                v[h * 8 + 2 * j + 1] = fmaf(p.beta1, f.y, v[h * 8 + 2 * j + 1]);
-              }
+            for (int j = 0; j < 4; j++) {
+              float2 f = __bfloat1622float2(b0[j]);
+              v[2 * j] = fmaf(p.beta1, f.x, v[2 * j]);
+              v[2 * j + 1] = fmaf(p.beta1, f.y, v[2 * j + 1]);
+              float2 g = __bfloat1622float2(b1[j]);
+              v[8 + 2 * j] = fmaf(p.beta1, g.x, v[8 + 2 * j]);
+              v[8 + 2 * j + 1] = fmaf(p.beta1, g.y, v[8 + 2 * j + 1]);
             }
           }
           if (a.res2) {
             const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + opix * p.res2_cs + p.res2_coff + co);
+            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+            const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              uint4 u = __ldg(rp + h);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float2 f = __bfloat1622float2(b2[j]);
-                v[h * 8 + 2 * j] = fmaf(p.beta2, f.x, v[h * 8 + 2 * j]);
-                v[h * 8 + 2 * j + 1] = fmaf(p.beta2, f.y, v[h * 8 + 2 * j + 1]);
-              }
+            for (int j = 0; j < 4; j++) {
+              float2 f = __bfloat1622float2(b0[j]);
+              v[2 * j] = fmaf(p.beta2, f.x, v[2 * j]);
+              v[2 * j + 1] = fmaf(p.beta2, f.y, v[2 * j + 1]);
+              float2 g = __bfloat1622float2(b1[j]);
+              v[8 + 2 * j] = fmaf(p.beta2, g.x, v[8 + 2 * j]);
+              v[8 + 2 * j + 1] = fmaf(p.beta2, g.y, v[8 + 2 * j + 1]);
             }
           }
           if (a.mask_src && co + 16 > p.mask_c0 && co < p.mask_c1) {
@@ -457,6 +486,53 @@ static int pow2_at_least(int v) {
   return r;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05.mma issue-rate probe (selftest only): one elected thread issues `iters` groups of 18 MMAs
+// (M=128, N=n, K=16, bf16) whose A descriptors walk 9 tap offsets of a halo tile, commits, waits.
+// Reports SM cycles per MMA.  Used to choose tile shapes; not part of the product path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int sbo, int iters, int a_step, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(&tptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = make_idesc_bf16(128, n);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 16384);
+    long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; it++) {
+      if (elect_one()) {
+#pragma unroll 1
+        for (int tap = 0; tap < 9; tap++) {
+          uint32_t aa = a0 + (uint32_t)(((tap / 3) * 10 + (tap % 3)) * a_step);
+#pragma unroll
+          for (int k = 0; k < 2; k++)
+            umma_bf16(tb, make_desc_sw64(aa + k * 32, (uint32_t)sbo), make_desc_sw64(b0 + k * 32, 512), idesc, 1u);
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, ph);
+      ph ^= 1;
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
 }  // namespace dasr
 
 using namespace dasr;
@@ -545,7 +621,7 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   a.w_bytes = p->ntaps * a.nchunks * p->nt * ROW_B;
   a.a_stage_bytes = (p->a_mode == 0) ? ((A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
   a.tmem_cols = pow2_at_least(2 * p->nt);
-  const int bar_bytes = (2 * MAX_STAGES + 5) * 8 + 16;
+  const int bar_bytes = (2 * MAX_STAGES + 6) * 8 + 256 * 4 + 16;
   int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - bar_bytes;
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -605,6 +681,21 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   dim3 grid(gx, gy);
   conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, a);
   return check_launch("conv_tc");
+}
+
+
+// selftest-only probe (declared in selftest.cu, not in the public header)
+int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_per_mma) {
+  long long* d;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return DASR_E_LAUNCH;
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  mma_rate_kernel<<<num_sms(), 128, 64 * 1024>>>(n, sbo, iters, a_step, d);
+  long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { set_error("probe: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
+  *cycles_per_mma = (double)h / ((double)iters * 18.0);
+  return DASR_OK;
 }
 
 }  // extern "C"

@@ -21,6 +21,7 @@
     }                                                                              \
   } while (0)
 
+extern "C" int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_per_mma);
 static unsigned long long rng_state = 0x1234567ULL;
 static inline unsigned rnd() {
   rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -319,6 +320,22 @@ int main(int argc, char** argv) {
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "check")) do_check = true;
     if (!strcmp(argv[i], "bench")) do_bench = true;
+    if (!strcmp(argv[i], "mmarate")) {
+      int ns[] = {16, 32, 48, 64, 96, 128, 160, 192, 256};
+      for (int sbo : {512, 640})
+        for (int n : ns) {
+          double c = 0;
+          int rc = dasr_probe_mma_rate(n, sbo, 200, 64, &c);
+          printf("mma_rate M128 N%-3d K16 sbo%d : %7.1f cycles/MMA  (ideal N/2=%d) rc=%d\n", n, sbo, c, n / 2, rc);
+        }
+      return 0;
+    }
+    if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes
+      bench_tc(16, 256, 256, 64, 32, 32, 0, 0, 1);
+      bench_tc(16, 256, 256, 160, 32, 32, 0, 0, 1);
+      bench_tc(16, 256, 256, 32, 192, 192, 1, 0, 1);
+      return 0;
+    }
   }
   setvbuf(stdout, NULL, _IOLBF, 0);
   cudaDeviceProp prop;

@@ -1,0 +1,536 @@
+"""Whole-network runners over the C-ABI kernels + their autograd.Functions.
+
+Each network of the path (RRDBNet generator, NLayer patch discriminator, VGG19 feature extractor) runs
+as ONE autograd node: forward launches the fused kernels on NHWC buffers (dense-block concat buffers
+are written in place — no torch.cat, no per-layer autograd bookkeeping), backward launches the matching
+dgrad / wgrad kernels and returns the gradients of the input and of every parameter in
+``module.parameters()`` order.  Parameters stay OIHW fp32 ``nn.Parameter``s (checkpoint / Adam contract,
+SURVEY.md §3.3, H4); kernel-layout copies are derived per call (training) or cached (inference).
+
+precision:
+  'fp32' — CUDA-core fp32 kernels everywhere (the 1e-3 rel-Linf parity mode; also the training mode)
+  'bf16' — tcgen05 bf16 kernels, fp32 accumulate (inference performance mode)
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, DGRAD, FWD, TC_FPROP, TC_UPCONV, View
+
+GC = 32  # growth channels: RRDBNet hard-codes gc=32 for every RRDB (architecture.py:183)
+
+
+def _need_cuda(x, what):
+    if not x.is_cuda:
+        raise ops._lib.DasrError('%s: the dasr_b200 path runs on CUDA only (tensor is on %s); no CPU fallback exists'
+                                 % (what, x.device))
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ==================================================================================================
+# RRDBNet  (architecture.py:174-205; block.py:254-309, 854-861)
+# ==================================================================================================
+
+class RRDBLayout:
+    """Index helper for the flat parameter list [w0,b0,w1,b1,...] in state_dict order."""
+
+    def __init__(self, nb, nf, upscale):
+        self.nb, self.nf = nb, nf
+        self.n_up = 1 if upscale == 3 else int(math.log(upscale, 2))
+        self.up_factor = 3 if upscale == 3 else 2
+        if self.up_factor != 2:
+            raise NotImplementedError('RRDBNet upscale=3 (nearest x3 upconv) is not supported by the B200 path')
+        self.n_rdb = 3 * nb
+        self.i_fea = 0
+        self.i_rdb0 = 1                               # conv index of RDB r conv k: 1 + 5*r + (k-1)
+        self.i_lr = 1 + 5 * self.n_rdb
+        self.i_up0 = self.i_lr + 1
+        self.i_hr0 = self.i_up0 + self.n_up
+        self.i_hr1 = self.i_hr0 + 1
+        self.n_conv = self.i_hr1 + 1
+
+    def rdb_conv(self, r, k):
+        return self.i_rdb0 + 5 * r + (k - 1)
+
+
+def _rdb_cin(nf, k):
+    return nf + (k - 1) * GC
+
+
+def rrdb_forward_f32(x, params, nb, upscale=4, save=False):
+    """fp32 forward.  Returns (out NCHW fp32, ctx or None)."""
+    _need_cuda(x, 'RRDBNet')
+    L = RRDBLayout(nb, params[0].shape[0], upscale)
+    nf = L.nf
+    N, in_nc, H, W = x.shape
+    Wt = lambda i: params[2 * i]
+    Bs = lambda i: params[2 * i + 1]
+    pk = lambda i: ops.pack_filter_f32(Wt(i))
+    CS = nf + 4 * GC
+
+    xin = _empty((N, H, W, in_nc), x)
+    ops.nchw_to_nhwc(x.contiguous().float(), xin)
+    fea = _empty((N, H, W, nf), x)
+    ops.conv2d_f32(xin, pk(L.i_fea), Bs(L.i_fea), fea, 3, 1, 1)
+
+    n_rdb = L.n_rdb
+    if save:
+        bufs = [_empty((N, H, W, CS), x) for _ in range(n_rdb)] + [_empty((N, H, W, nf), x)]
+    else:
+        rot = [_empty((N, H, W, CS), x) for _ in range(min(3, max(n_rdb, 1)))]
+        bufs = [rot[i % 3] for i in range(n_rdb + 1)]
+    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
+    for r in range(n_rdb):
+        b = bufs[r]
+        for k in range(1, 5):
+            ci = L.rdb_conv(r, k)
+            ops.conv2d_f32(View(b, _rdb_cin(nf, k), 0), pk(ci), Bs(ci), View(b, GC, nf + (k - 1) * GC), 3, 1, 1,
+                           act=ACT_LRELU, slope=0.2)
+        ci = L.rdb_conv(r, 5)
+        dst = View(bufs[r + 1], nf, 0)
+        if r % 3 == 2:   # last RDB of an RRDB: (x5*0.2 + x)*0.2 + x_rrdb   block.py:286,309
+            ops.conv2d_f32(View(b, CS, 0), pk(ci), Bs(ci), dst, 3, 1, 1, alpha=0.04,
+                           res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        else:
+            ops.conv2d_f32(View(b, CS, 0), pk(ci), Bs(ci), dst, 3, 1, 1, alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+    trunk = View(bufs[n_rdb], nf, 0)
+    lr = _empty((N, H, W, nf), x)
+    ops.conv2d_f32(trunk, pk(L.i_lr), Bs(L.i_lr), lr, 3, 1, 1, res1=fea, beta1=1.0)   # fea + LR_conv(...)  block.py:103-105
+    ups = [lr]
+    cur, h, w = lr, H, W
+    for u in range(L.n_up):
+        h, w = 2 * h, 2 * w
+        nxt = _empty((N, h, w, nf), x)
+        ops.conv2d_f32(cur, pk(L.i_up0 + u), Bs(L.i_up0 + u), nxt, 3, 1, 1, ups=2, act=ACT_LRELU)
+        ups.append(nxt)
+        cur = nxt
+    h0 = _empty((N, h, w, nf), x)
+    ops.conv2d_f32(cur, pk(L.i_hr0), Bs(L.i_hr0), h0, 3, 1, 1, act=ACT_LRELU)
+    out_nc = Wt(L.i_hr1).shape[0]
+    o = _empty((N, h, w, out_nc), x)
+    ops.conv2d_f32(h0, pk(L.i_hr1), Bs(L.i_hr1), o, 3, 1, 1)
+    out = _empty((N, out_nc, h, w), x)
+    ops.nhwc_to_nchw(o, out)
+    ctx = None
+    if save:
+        ctx = dict(L=L, xin=xin, fea=fea, bufs=bufs, ups=ups, h0=h0, shape=(N, in_nc, H, W))
+    return out, ctx
+
+
+def rrdb_backward_f32(ctx, params, dout, need_dx=False):
+    """Returns (dx or None, [grad for every param in order])."""
+    L = ctx['L']
+    nf = L.nf
+    N, in_nc, H, W = ctx['shape']
+    Wt = lambda i: params[2 * i]
+    CS = nf + 4 * GC
+    grads = [torch.empty_like(p) for p in params]
+    gW = lambda i: grads[2 * i]
+    gB = lambda i: grads[2 * i + 1]
+    pkd = lambda i: ops.pack_filter_f32(Wt(i), for_dgrad=True)
+    bufs, ups, h0, fea, xin = ctx['bufs'], ctx['ups'], ctx['h0'], ctx['fea'], ctx['xin']
+    dev = dout
+    out_nc = Wt(L.i_hr1).shape[0]
+    hh, ww = dout.shape[2], dout.shape[3]
+
+    g_o = _empty((N, hh, ww, out_nc), dev)
+    ops.nchw_to_nhwc(dout.contiguous().float(), g_o)
+    # HR_conv1
+    ops.conv2d_wgrad_f32(h0, g_o, gW(L.i_hr1), gB(L.i_hr1), 3, 1, 1)
+    g_h0 = _empty((N, hh, ww, nf), dev)
+    ops.conv2d_f32(g_o, pkd(L.i_hr1), None, g_h0, 3, 1, 1, mode=DGRAD)
+    ops.act_bwd(g_h0, h0, 0.2)
+    # HR_conv0
+    top = ups[-1]
+    ops.conv2d_wgrad_f32(top, g_h0, gW(L.i_hr0), gB(L.i_hr0), 3, 1, 1)
+    g_cur = _empty((N, hh, ww, nf), dev)
+    ops.conv2d_f32(g_h0, pkd(L.i_hr0), None, g_cur, 3, 1, 1, mode=DGRAD)
+    del g_h0, g_o
+    # upconvs (reverse)
+    for u in reversed(range(L.n_up)):
+        y, xin_u = ups[u + 1], ups[u]
+        ops.act_bwd(g_cur, y, 0.2)
+        ops.conv2d_wgrad_f32(xin_u, g_cur, gW(L.i_up0 + u), gB(L.i_up0 + u), 3, 1, 1, ups=2)
+        g_upin = _empty(tuple(y.shape), dev)                 # gradient w.r.t. the (virtual) upsampled tensor
+        ops.conv2d_f32(g_cur, pkd(L.i_up0 + u), None, g_upin, 3, 1, 1, mode=DGRAD)
+        g_nxt = _empty(tuple(xin_u.shape), dev)
+        ops.upsample2x_bwd(g_upin, g_nxt)
+        del g_upin
+        g_cur = g_nxt
+    g_lr = g_cur                                             # grad of (fea + LR_conv(trunk)); also the fea-skip grad
+    n_rdb = L.n_rdb
+    trunk = View(bufs[n_rdb], nf, 0)
+    ops.conv2d_wgrad_f32(trunk, g_lr, gW(L.i_lr), gB(L.i_lr), 3, 1, 1)
+    g_y = _empty((N, H, W, nf), dev)                         # grad w.r.t. the current RDB's output
+    ops.conv2d_f32(g_lr, pkd(L.i_lr), None, g_y, 3, 1, 1, mode=DGRAD)
+
+    GB = _empty((N, H, W, CS), dev)                          # gradient concat buffer of the RDB being processed
+    g_x5 = _empty((N, H, W, nf), dev)
+    g_rrdb = None                                            # pending skip gradient of the enclosing RRDB
+    for r in reversed(range(n_rdb)):
+        b = bufs[r]
+        last = (r % 3 == 2)
+        if last:
+            a5, b1 = 0.04, 0.2
+            g_rrdb = g_y                                     # d out / d x_rrdb = 1 (beta2)
+        else:
+            a5, b1 = 0.2, 1.0
+        ops.axpby(g_y, a5, None, 0.0, g_x5)
+        ci = L.rdb_conv(r, 5)
+        ops.conv2d_wgrad_f32(View(b, CS, 0), g_x5, gW(ci), gB(ci), 3, 1, 1)
+        # dgrad conv5 -> GB[:, 0:CS];  the RDB skip  b1*g_y  joins the x slice in the same epilogue
+        ops.conv2d_f32(g_x5, pkd(ci), None, View(GB, CS, 0), 3, 1, 1, mode=DGRAD)
+        ops.axpby(View(GB, nf, 0), 1.0, g_y, b1, View(GB, nf, 0))
+        for k in (4, 3, 2, 1):
+            ci = L.rdb_conv(r, k)
+            cin = _rdb_cin(nf, k)
+            gk = View(GB, GC, nf + (k - 1) * GC)
+            ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
+            ops.conv2d_wgrad_f32(View(b, cin, 0), gk, gW(ci), gB(ci), 3, 1, 1)
+            ops.conv2d_f32(gk, pkd(ci), None, View(GB, cin, 0), 3, 1, 1, mode=DGRAD, res1=View(GB, cin, 0), beta1=1.0)
+        g_new = _empty((N, H, W, nf), dev)
+        if r % 3 == 0 and g_rrdb is not None:
+            ops.axpby(View(GB, nf, 0), 1.0, g_rrdb, 1.0, g_new)
+            g_rrdb = None
+        else:
+            ops.axpby(View(GB, nf, 0), 1.0, None, 0.0, g_new)
+        g_y = g_new
+    # fea: trunk input gradient + the ShortcutBlock skip
+    g_fea = _empty((N, H, W, nf), dev)
+    ops.axpby(g_y, 1.0, g_lr, 1.0, g_fea)
+    ops.conv2d_wgrad_f32(xin, g_fea, gW(L.i_fea), gB(L.i_fea), 3, 1, 1)
+    dx = None
+    if need_dx:
+        g_xin = _empty((N, H, W, in_nc), dev)
+        ops.conv2d_f32(g_fea, pkd(L.i_fea), None, g_xin, 3, 1, 1, mode=DGRAD)
+        dx = _empty((N, in_nc, H, W), dev)
+        ops.nhwc_to_nchw(g_xin, dx)
+    return dx, grads
+
+
+# ---- bf16 tcgen05 inference -----------------------------------------------------------------------
+
+_TC_W_BUDGET = 150 * 1024   # resident-filter bytes per CTA that still leaves >= 5 halo stages
+
+
+def _pick_nt(cout, cin, ntaps=9):
+    nt = cout
+    while nt >= 16:
+        if cout % nt == 0 and nt % 16 == 0 and ntaps * (cin // 32) * nt * 64 <= _TC_W_BUDGET:
+            return nt
+        nt //= 2
+    raise ops._lib.DasrError('conv_tc: no Cout tile fits shared memory for cin=%d cout=%d' % (cin, cout))
+
+
+class _PackCache:
+    """kernel-layout filter copies, invalidated when the nn.Parameter changes (H4)."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, key, param, make):
+        ver = (param.data_ptr(), param._version)
+        e = self.d.get(key)
+        if e is None or e[0] != ver:
+            e = (ver, make())
+            self.d[key] = e
+        return e[1]
+
+
+def _pad_filter(w, cout_to=None, cin_to=None):
+    co, ci = w.shape[0], w.shape[1]
+    cout_to, cin_to = cout_to or co, cin_to or ci
+    if (co, ci) == (cout_to, cin_to):
+        return w
+    o = torch.zeros((cout_to, cin_to, 3, 3), dtype=w.dtype, device=w.device)
+    o[:co, :ci] = w.detach()
+    return o
+
+
+def _pad_vec(b, n):
+    if b.shape[0] == n:
+        return b.detach()
+    o = torch.zeros(n, dtype=b.dtype, device=b.device)
+    o[:b.shape[0]] = b.detach()
+    return o
+
+
+def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
+    """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between."""
+    _need_cuda(x, 'RRDBNet')
+    L = RRDBLayout(nb, params[0].shape[0], upscale)
+    nf = L.nf
+    if nf % 32 or GC % 32:
+        raise ops._lib.DasrError('bf16 path needs nf %% 32 == 0 (got %d)' % nf)
+    cache = cache if cache is not None else _PackCache()
+    N, in_nc, H, W = x.shape
+    bf = torch.bfloat16
+    CS = nf + 4 * GC
+    Wt = lambda i: params[2 * i]
+
+    def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
+        return cache.get(('w', i, kind), Wt(i), lambda: ops.pack_filter_tc(_pad_filter(Wt(i), cout_to, cin_to).float(), kind))
+
+    def bk(i, n=None):
+        p = params[2 * i + 1]
+        return cache.get(('b', i), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
+
+    xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)       # Cin 3 -> one zero-padded 32-channel chunk
+    ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
+    fea = _empty((N, H, W, nf), x, bf)
+    ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
+    n_rdb = L.n_rdb
+    rot = [_empty((N, H, W, CS), x, bf) for _ in range(3)]
+    bufs = [rot[i % 3] for i in range(n_rdb + 1)]
+    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
+    for r in range(n_rdb):
+        b = bufs[r]
+        for k in range(1, 5):
+            ci = L.rdb_conv(r, k)
+            ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
+        ci = L.rdb_conv(r, 5)
+        dst = View(bufs[r + 1], nf, 0)
+        nt = _pick_nt(nf, CS)
+        if r % 3 == 2:
+            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=nt, alpha=0.04, res1=View(b, nf, 0), beta1=0.2,
+                        res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        else:
+            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=nt, alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+    trunk = View(bufs[n_rdb], nf, 0)
+    lr = _empty((N, H, W, nf), x, bf)
+    ops.conv_tc(trunk, wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+    cur, h, w = lr, H, W
+    for u in range(L.n_up):
+        h, w = 2 * h, 2 * w
+        nxt = _empty((N, h, w, nf), x, bf)
+        # nearest-x2 + 3x3 conv as four 2x2 sub-pixel convs with pre-summed filters (never materialise the 4x tensor)
+        ops.conv_tc(cur, wk(L.i_up0 + u, TC_UPCONV), bk(L.i_up0 + u), nxt, kind=TC_UPCONV, nt=_pick_nt(nf, nf, 4),
+                    act=ACT_LRELU, slope=0.2)
+        cur = nxt
+    h0 = _empty((N, h, w, nf), x, bf)
+    ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2)
+    del cur
+    out_nc = Wt(L.i_hr1).shape[0]
+    o16 = _empty((N, h, w, 16), x, bf)                                  # Cout 3 -> one 16-wide UMMA N tile
+    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), o16, nt=16)
+    out = _empty((N, out_nc, h, w), x)
+    ops.nhwc_to_nchw(View(o16, out_nc, 0), out)
+    return out
+
+
+class RRDBNetFunction(torch.autograd.Function):
+    """fp32 training node: forward/backward entirely on the C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, x, nb, upscale, *params):
+        out, saved = rrdb_forward_f32(x, [p.detach() for p in params], nb, upscale, save=True)
+        ctx.saved = saved
+        ctx.params = params
+        ctx.need_dx = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx, grads = rrdb_backward_f32(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.need_dx)
+        ctx.saved = None
+        return (dx, None, None) + tuple(grads)
+
+
+# ==================================================================================================
+# NLayerDiscriminator  (architecture.py:983-1024): 4x4 convs, InstanceNorm2d(affine=False), LeakyReLU(0.2)
+# ==================================================================================================
+
+def _out_hw(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+def nlayer_d_plan(params, has_bias):
+    """[(w, b|None, stride, norm, act)] from the flat parameter list (state_dict order)."""
+    plan, i = [], 0
+    n = len(has_bias)
+    for li in range(n):
+        w = params[i]
+        i += 1
+        b = None
+        if has_bias[li]:
+            b = params[i]
+            i += 1
+        plan.append((w, b))
+    return plan
+
+
+def nlayer_d_forward(x, params, n_layers=2, save=False):
+    """params in state_dict order: w0,b0,w(mid...) no bias,...,w_last,b_last.  Returns (logits NCHW, ctx)."""
+    _need_cuda(x, 'NLayerDiscriminator')
+    n_conv = n_layers + 2
+    has_bias = [True] + [False] * n_layers + [True]
+    strides = [2] * n_layers + [1, 1]
+    plan = nlayer_d_plan(params, has_bias)
+    N, C0, H, W = x.shape
+    a = _empty((N, H, W, C0), x)
+    ops.nchw_to_nhwc(x.contiguous().float(), a)
+    acts, stats = [a], []
+    h, w = H, W
+    for li in range(n_conv):
+        wt, bs = plan[li]
+        s = strides[li]
+        h, w = _out_hw(h, 4, s, 1), _out_hw(w, 4, s, 1)
+        if h <= 0 or w <= 0:
+            raise ops._lib.DasrError('NLayerDiscriminator: input %dx%d too small' % (H, W))
+        o = _empty((N, h, w, wt.shape[0]), x)
+        first, last = li == 0, li == n_conv - 1
+        ops.conv2d_f32(acts[-1], ops.pack_filter_f32(wt), bs, o, 4, s, 1, act=ACT_LRELU if first else ACT_NONE, slope=0.2)
+        if not first and not last:
+            st = _empty((N, wt.shape[0], 2), x)
+            ops.instnorm_lrelu_fwd(o, st, 1e-5, 0.2)
+            stats.append(st)
+        acts.append(o)
+    out = _empty((N, 1, h, w), x)
+    ops.nhwc_to_nchw(acts[-1], out)
+    ctx = dict(acts=acts, stats=stats, strides=strides, has_bias=has_bias, shape=(N, C0, H, W)) if save else None
+    return out, ctx
+
+
+def nlayer_d_backward(ctx, params, dout, need_dx=True, need_dw=True):
+    acts, stats, strides, has_bias = ctx['acts'], ctx['stats'], ctx['strides'], ctx['has_bias']
+    plan = nlayer_d_plan(params, has_bias)
+    n_conv = len(plan)
+    N, C0, H, W = ctx['shape']
+    grads = [torch.empty_like(p) for p in params] if need_dw else [None] * len(params)
+    gi = len(params)
+    g = _empty(tuple(acts[-1].shape), dout)
+    ops.nchw_to_nhwc(dout.contiguous().float(), g)
+    for li in reversed(range(n_conv)):
+        wt, bs = plan[li]
+        s = strides[li]
+        first, last = li == 0, li == n_conv - 1
+        if first:
+            ops.act_bwd(g, acts[1], 0.2)
+        elif not last:
+            gz = torch.empty_like(g)
+            ops.instnorm_lrelu_bwd(acts[li + 1], stats[li - 1], g, gz, 0.2)
+            g = gz
+        gi -= 2 if bs is not None else 1
+        if need_dw:
+            ops.conv2d_wgrad_f32(acts[li], g, grads[gi], grads[gi + 1] if bs is not None else None, 4, s, 1)
+        if li > 0 or need_dx:
+            gin = _empty(tuple(acts[li].shape), dout)
+            ops.conv2d_f32(g, ops.pack_filter_f32(wt, for_dgrad=True), None, gin, 4, s, 1, mode=DGRAD)
+            g = gin
+    dx = None
+    if need_dx:
+        dx = _empty((N, C0, H, W), dout)
+        ops.nhwc_to_nchw(g, dx)
+    return dx, grads
+
+
+class NLayerDFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_layers, *params):
+        out, saved = nlayer_d_forward(x, [p.detach() for p in params], n_layers, save=True)
+        ctx.saved, ctx.params = saved, params
+        ctx.need_dx = x.requires_grad
+        ctx.need_dw = any(p.requires_grad for p in params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx, grads = nlayer_d_backward(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.need_dx, ctx.need_dw)
+        ctx.saved = None
+        return (dx, None) + tuple(grads)
+
+
+# ==================================================================================================
+# VGG19 features[:feature_layer+1]  (architecture.py:1060-1088) — frozen weights: fprop + dgrad only
+# ==================================================================================================
+VGG19_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512, 'M']
+
+
+def vgg_plan(feature_layer):
+    """[('conv', relu?) | ('pool',)] for torchvision vgg19.features[:feature_layer+1]."""
+    plan, idx = [], 0
+    for v in VGG19_CFG:
+        if idx > feature_layer:
+            break
+        if v == 'M':
+            plan.append(('pool',))
+            idx += 1
+        else:
+            relu = (idx + 1) <= feature_layer
+            plan.append(('conv', relu))
+            idx += 2
+    return plan
+
+
+def vgg_forward(x, params, mean, std, feature_layer=34, save=False, cache=None):
+    _need_cuda(x, 'VGGFeatureExtractor')
+    plan = vgg_plan(feature_layer)
+    N, C0, H, W = x.shape
+    a = _empty((N, H, W, C0), x)
+    ops.nchw_to_nhwc(x.contiguous().float(), a, mean, std)          # (x - mean) / std fused into the layout change
+    acts = [a]
+    pi = 0
+    h, w = H, W
+    for step in plan:
+        if step[0] == 'pool':
+            o = _empty((N, h // 2, w // 2, acts[-1].shape[3]), x)
+            ops.maxpool2_fwd(acts[-1], o)
+            h, w = h // 2, w // 2
+        else:
+            wt, bs = params[pi], params[pi + 1]
+            key = pi
+            pi += 2
+            o = _empty((N, h, w, wt.shape[0]), x)
+            pk = cache.get(('vf', key), wt, lambda: ops.pack_filter_f32(wt)) if cache is not None else ops.pack_filter_f32(wt)
+            ops.conv2d_f32(acts[-1], pk, bs, o, 3, 1, 1, act=ACT_RELU if step[1] else ACT_NONE)
+        acts.append(o)
+    Cf = acts[-1].shape[3]
+    out = _empty((N, Cf, h, w), x)
+    ops.nhwc_to_nchw(acts[-1], out)
+    ctx = dict(acts=acts, plan=plan, shape=(N, C0, H, W)) if save else None
+    return out, ctx
+
+
+def vgg_backward(ctx, params, std, dout, cache=None):
+    acts, plan = ctx['acts'], ctx['plan']
+    N, C0, H, W = ctx['shape']
+    g = _empty(tuple(acts[-1].shape), dout)
+    ops.nchw_to_nhwc(dout.contiguous().float(), g)
+    pi = 2 * sum(1 for s in plan if s[0] == 'conv')
+    for li in reversed(range(len(plan))):
+        step = plan[li]
+        if step[0] == 'pool':
+            gin = torch.empty_like(acts[li])
+            ops.maxpool2_bwd(acts[li], acts[li + 1], g, gin)
+        else:
+            pi -= 2
+            wt = params[pi]
+            if step[1]:
+                ops.act_bwd(g, acts[li + 1], 0.0)
+            gin = torch.empty_like(acts[li])
+            pk = cache.get(('vd', pi), wt, lambda: ops.pack_filter_f32(wt, for_dgrad=True)) if cache is not None \
+                else ops.pack_filter_f32(wt, for_dgrad=True)
+            ops.conv2d_f32(g, pk, None, gin, 3, 1, 1, mode=DGRAD)
+        g = gin
+    dx = _empty((N, C0, H, W), dout)
+    inv_std = (1.0 / std.float()).contiguous() if std is not None else None
+    ops.nhwc_to_nchw(g, dx, inv_std)                                    # d/dx of (x-mean)/std
+    return dx
+
+
+class VGGFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, feature_layer, mean, std, cache, *params):
+        out, saved = vgg_forward(x, [p.detach() for p in params], mean, std, feature_layer, save=x.requires_grad, cache=cache)
+        ctx.saved, ctx.params, ctx.std, ctx.cache = saved, params, std, cache
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = vgg_backward(ctx.saved, [p.detach() for p in ctx.params], ctx.std, dout, ctx.cache)
+        ctx.saved = None
+        return (dx, None, None, None, None) + (None,) * len(ctx.params)

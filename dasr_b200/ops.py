@@ -1,0 +1,265 @@
+"""Thin, typed Python wrappers over the C-ABI kernels (one function per entry point).
+
+torch is used here only as the owner of device memory and of the current CUDA stream; no torch operator
+computes anything on this path.  Every wrapper requires CUDA tensors and raises otherwise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvF32Params, ConvTcParams, check
+
+ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
+FWD, DGRAD = 0, 1
+TC_FPROP, TC_DGRAD, TC_UPCONV = 0, 1, 2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.DasrError('dasr_b200 kernels need CUDA tensors (got %s); there is no CPU fallback' % t.device)
+    if not t.is_contiguous():
+        raise _lib.DasrError('dasr_b200 kernels need contiguous tensors')
+    return C.c_void_p(t.data_ptr())
+
+
+class View:
+    """A channel slice [coff, coff+c) of an NHWC buffer [N,H,W,cs]."""
+    __slots__ = ('t', 'c', 'coff')
+
+    def __init__(self, t, c=None, coff=0):
+        self.t, self.coff = t, coff
+        self.c = t.shape[-1] - coff if c is None else c
+        assert coff + self.c <= t.shape[-1]
+
+    @property
+    def cs(self):
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self):
+        return _p(self.t)
+
+
+def as_view(x):
+    return x if isinstance(x, View) else View(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# fp32 generic conv
+# --------------------------------------------------------------------------------------------------
+
+def conv_f32_params(inp, out, k, stride, pad, ups=1, mode=FWD, act=ACT_NONE, slope=0.2, alpha=1.0,
+                    res1=None, beta1=0.0, res2=None, beta2=0.0):
+    inp, out = as_view(inp), as_view(out)
+    N, H, W, _ = inp.t.shape
+    _, OH, OW, _ = out.t.shape
+    p = ConvF32Params()
+    p.N, p.H, p.W = N, H, W
+    p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
+    p.OH, p.OW = OH, OW
+    p.cout, p.out_cs, p.out_coff = out.c, out.cs, out.coff
+    p.kh = p.kw = k
+    p.stride, p.pad, p.ups, p.mode = stride, pad, ups, mode
+    p.act, p.slope, p.alpha = act, slope, alpha
+    if res1 is not None:
+        res1 = as_view(res1)
+        p.beta1, p.res1_cs, p.res1_coff = beta1, res1.cs, res1.coff
+    if res2 is not None:
+        res2 = as_view(res2)
+        p.beta2, p.res2_cs, p.res2_coff = beta2, res2.cs, res2.coff
+    return p, inp, out, res1, res2
+
+
+def conv2d_f32(inp, w_packed, bias, out, k, stride, pad, **kw):
+    """out = alpha*act(conv(inp) + bias) + beta1*res1 + beta2*res2   (NHWC fp32, see dasr_b200.h)."""
+    p, inp, out, res1, res2 = conv_f32_params(inp, out, k, stride, pad, **kw)
+    lib = _lib.load()
+    check(lib.dasr_conv2d_f32(inp.ptr, _p(w_packed), _p(bias), res1.ptr if res1 else None,
+                              res2.ptr if res2 else None, out.ptr, C.byref(p), _stream()), 'conv2d_f32')
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = str(device)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def conv2d_wgrad_f32(inp, dout, dw, db, k, stride, pad, ups=1, accumulate=False):
+    """dw (OIHW fp32) / db of the FWD conv inp -> dout-shaped output."""
+    p, inp, dout, _, _ = conv_f32_params(inp, dout, k, stride, pad, ups=ups)
+    lib = _lib.load()
+    n = lib.dasr_conv2d_wgrad_f32_workspace(C.byref(p))
+    ws = _workspace(n, inp.t.device)
+    check(lib.dasr_conv2d_wgrad_f32(inp.ptr, dout.ptr, _p(dw), _p(db), C.byref(p), int(accumulate), _p(ws),
+                                    ws.numel(), _stream()), 'conv2d_wgrad_f32')
+
+
+def pack_filter_f32(w, for_dgrad=False):
+    cout, cin, kh, kw = w.shape
+    o = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    check(_lib.load().dasr_pack_filter_f32(_p(w.detach()), _p(o), cout, cin, kh, kw, int(for_dgrad), _stream()),
+          'pack_filter_f32')
+    return o
+
+
+# --------------------------------------------------------------------------------------------------
+# tcgen05 bf16 conv
+# --------------------------------------------------------------------------------------------------
+
+def pack_filter_tc(w, kind):
+    """OIHW fp32 3x3 filter -> bf16 [variant][tap][chunk][cout][32] (dasr_pack_filter_tc)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    lib = _lib.load()
+    nbytes = lib.dasr_pack_filter_tc_bytes(cout, cin, kind)
+    o = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    check(lib.dasr_pack_filter_tc(_p(w.detach()), _p(o), cout, cin, kind, _stream()), 'pack_filter_tc')
+    return o
+
+
+def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0,
+            res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2, a_mode=0):
+    """tcgen05 3x3 conv on NHWC bf16 channel slices; `inp`/`out`/`res*`/`mask` are Views (or tensors)."""
+    inp, out = as_view(inp), as_view(out)
+    N, H, W, _ = inp.t.shape
+    p = ConvTcParams()
+    lib = _lib.load()
+    check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup')
+    p.N, p.H, p.W = N, H, W
+    p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
+    p.cout, p.out_cs, p.out_coff = out.c, out.cs, out.coff
+    p.nt = nt if nt else out.c
+    p.act, p.slope, p.alpha = act, slope, alpha
+    if res1 is not None:
+        res1 = as_view(res1)
+        p.beta1, p.res1_cs, p.res1_coff = beta1, res1.cs, res1.coff
+    if res2 is not None:
+        res2 = as_view(res2)
+        p.beta2, p.res2_cs, p.res2_coff = beta2, res2.cs, res2.coff
+    if mask is not None:
+        mask = as_view(mask)
+        p.mask_cs, p.mask_coff, p.mask_c0, p.mask_c1, p.mask_slope = mask.cs, mask.coff, mask_c0, mask_c1, mask_slope
+    p.a_mode = a_mode
+    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), res1.ptr if res1 else None, res2.ptr if res2 else None,
+                           mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
+
+
+# --------------------------------------------------------------------------------------------------
+# layout / elementwise
+# --------------------------------------------------------------------------------------------------
+
+def nchw_to_nhwc(src, dst, mean=None, std=None):
+    dst = as_view(dst)
+    N, Cc, H, W = src.shape
+    check(_lib.load().dasr_nchw_to_nhwc(_p(src), dst.ptr, N, Cc, H, W, dst.cs, dst.coff,
+                                        int(dst.t.dtype == torch.bfloat16), _p(mean), _p(std), _stream()), 'nchw_to_nhwc')
+
+
+def nhwc_to_nchw(src, dst, inv_std=None):
+    src = as_view(src)
+    N, Cc, H, W = dst.shape
+    check(_lib.load().dasr_nhwc_to_nchw(src.ptr, _p(dst), N, Cc, H, W, src.cs, src.coff,
+                                        int(src.t.dtype == torch.bfloat16), _p(inv_std), _stream()), 'nhwc_to_nchw')
+
+
+def act_bwd(g, y, slope):
+    g, y = as_view(g), as_view(y)
+    npix = g.t.numel() // g.cs
+    check(_lib.load().dasr_act_bwd(g.ptr, y.ptr, npix, g.c, g.cs, g.coff, y.cs, y.coff, slope,
+                                   int(g.t.dtype == torch.bfloat16), _stream()), 'act_bwd')
+
+
+def upsample2x_bwd(src, dst):
+    src, dst = as_view(src), as_view(dst)
+    N, H, W, _ = dst.t.shape
+    check(_lib.load().dasr_upsample2x_bwd(src.ptr, dst.ptr, N, H, W, dst.c, src.cs, src.coff, dst.cs, dst.coff,
+                                          int(dst.t.dtype == torch.bfloat16), _stream()), 'upsample2x_bwd')
+
+
+def axpby(x, a, y, b, dst):
+    """dst = a*x + b*y on channel slices (y may be None)."""
+    x, dst = as_view(x), as_view(dst)
+    y = as_view(y) if y is not None else None
+    npix = dst.t.numel() // dst.cs
+    check(_lib.load().dasr_axpby(x.ptr, y.ptr if y else None, dst.ptr, npix, dst.c, x.cs, x.coff,
+                                 y.cs if y else 0, y.coff if y else 0, dst.cs, dst.coff, a, b,
+                                 int(dst.t.dtype == torch.bfloat16), _stream()), 'axpby')
+
+
+def maxpool2_fwd(x, out):
+    N, H, W, Cc = x.shape
+    check(_lib.load().dasr_maxpool2_fwd(_p(x), _p(out), N, H, W, Cc, _stream()), 'maxpool2_fwd')
+
+
+def maxpool2_bwd(x, out, dout, din):
+    N, H, W, Cc = x.shape
+    check(_lib.load().dasr_maxpool2_bwd(_p(x), _p(out), _p(dout), _p(din), N, H, W, Cc, _stream()), 'maxpool2_bwd')
+
+
+def instnorm_lrelu_fwd(x, stats, eps=1e-5, slope=0.2):
+    N, H, W, Cc = x.shape
+    check(_lib.load().dasr_instnorm_lrelu_fwd(_p(x), _p(stats), N, H * W, Cc, eps, slope, _stream()), 'instnorm_lrelu_fwd')
+
+
+def instnorm_lrelu_bwd(y, stats, dy, dx, slope=0.2):
+    N, H, W, Cc = y.shape
+    check(_lib.load().dasr_instnorm_lrelu_bwd(_p(y), _p(stats), _p(dy), _p(dx), N, H * W, Cc, slope, _stream()),
+          'instnorm_lrelu_bwd')
+
+
+def haar_fwd(x, ll, hc, norm):
+    N, Cc, H, W = x.shape
+    check(_lib.load().dasr_haar_fwd(_p(x), _p(ll), _p(hc), N, Cc, H, W, int(bool(norm)), _stream()), 'haar_fwd')
+
+
+def haar_bwd(dll, dhc, dx, norm):
+    N, Cc, H, W = dx.shape
+    check(_lib.load().dasr_haar_bwd(_p(dll), _p(dhc), _p(dx), N, Cc, H, W, int(bool(norm)), _stream()), 'haar_bwd')
+
+
+def dwfilter(x, out, taps, k, mode, count_include_pad=True, backward=False):
+    N, Cc, H, W = x.shape
+    fn = _lib.load().dasr_dwfilter_bwd if backward else _lib.load().dasr_dwfilter_fwd
+    check(fn(_p(x), _p(out), _p(taps), N, Cc, H, W, k, mode, int(bool(count_include_pad)), _stream()), 'dwfilter')
+
+
+def bilinear(src, dst):
+    N, Cc, H, W = src.shape
+    check(_lib.load().dasr_bilinear_fwd(_p(src), _p(dst), N * Cc, H, W, dst.shape[2], dst.shape[3], _stream()), 'bilinear')
+
+
+def _partials(device):
+    return _workspace(4096, device)
+
+
+def wl1_loss(a, b, w, loss, grad, gscale):
+    N, Cc, H, W = a.shape
+    check(_lib.load().dasr_wl1_loss(_p(a), _p(b), _p(w), _p(loss), _p(grad), gscale, N, Cc, H * W,
+                                    _p(_partials(a.device)), _stream()), 'wl1_loss')
+
+
+def mse_loss(a, b, loss, grad, gscale):
+    check(_lib.load().dasr_mse_loss(_p(a), _p(b), _p(loss), _p(grad), gscale, a.numel(), _p(_partials(a.device)),
+                                    _stream()), 'mse_loss')
+
+
+def bce_logits_loss(x, target, loss, grad, gscale):
+    check(_lib.load().dasr_bce_logits_loss(_p(x), float(target), _p(loss), _p(grad), gscale, x.numel(),
+                                           _p(_partials(x.device)), _stream()), 'bce_logits_loss')
+
+
+def mean(x, out):
+    check(_lib.load().dasr_mean(_p(x), _p(out), x.numel(), _p(_partials(x.device)), _stream()), 'mean')

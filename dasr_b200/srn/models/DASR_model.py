@@ -1,0 +1,371 @@
+"""DASR_Model — the SRN GAN training step + test path (reference: codes/SRN/models/DASR_model.py).
+
+Same attributes (netG, netD_target, netD_source, netF, optimizers, schedulers, log_dict), same methods
+(feed_data, optimize_parameters, test, get_current_log, get_current_visuals, save, load, ...), same loss
+arithmetic including the reference's quirks (pixel weight applied twice, :214-218).  Differences, all
+behaviour-preserving:
+  * every network / loss / frequency split runs on dasr_b200 kernels;
+  * b_split on the fixed [0]*B+[1]*B mask is a view, not a per-sample cat (:200-207);
+  * while G's loss is back-propagated through D, D's filter gradients (which the reference computes and
+    then discards with optimizer_D_target.zero_grad(), :282) are not computed;
+  * log values are kept as device scalars and only synchronised in get_current_log();
+  * under torch.distributed (one process per GPU) the G and D gradients are all-reduced once per step in
+    a single flat bucket before both optimiser steps (dasr_b200.dp) — equivalent to the reference order
+    because the D step only consumes tensors detached before the G update.
+"""
+import contextlib
+import logging
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+from torch.optim import lr_scheduler
+
+from dasr_b200 import dp, ops
+from dasr_b200.srn.utils.util import b_split, forward_chop
+from . import networks
+from .base_model import BaseModel
+from .modules import loss as L
+from .modules.architecture import FilterHigh, FilterLow
+
+logger = logging.getLogger('base')
+
+
+@contextlib.contextmanager
+def _params_frozen(net):
+    ps = [p for p in net.parameters() if p.requires_grad]
+    for p in ps:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in ps:
+            p.requires_grad_(True)
+
+
+class DASR_Model(BaseModel):
+    def __init__(self, opt):
+        super().__init__(opt)
+        train_opt = opt['train'] if opt['train'] is not None else {}
+        self.chop = opt['chop']
+        self.scale = opt['scale']
+        self.val_lpips = opt['val_lpips']
+        self.adaptive_weights = opt['adaptive_weights']
+        self.multiweights = opt['multiweights']
+
+        self.ragan = train_opt.get('ragan')
+        self.l_gan_H_target_w = train_opt.get('gan_H_target') or 0
+        self.l_gan_H_source_w = train_opt.get('gan_H_source') or 0
+        if self.is_train:
+            self.cri_gan = L.GANLoss(train_opt['gan_type'], 1.0, 0.0).to(self.device)
+            if self.ragan:
+                raise NotImplementedError('ragan: true needs cross-batch means (not in any shipped SRN config; SURVEY §8e)')
+            if train_opt['gan_type'] == 'wgan-gp':
+                raise NotImplementedError('wgan-gp gradient penalty (double backward) is not on the B200 path')
+
+        self.netG = networks.define_G(opt).to(self.device)
+        if self.is_train:
+            if self.l_gan_H_target_w > 0:
+                self.netD_target = networks.define_D(opt).to(self.device)
+                self.netD_target.train()
+            if self.l_gan_H_source_w > 0:
+                self.netD_source = networks.define_pairD(opt).to(self.device)
+                self.netD_source.train()
+            self.netG.train()
+        self.load()
+
+        # frequency separation.  fs_kernel_size defaults to 5: the shipped wavelet configs omit it and the
+        # reference then crashes in FilterHigh(kernel_size=None).
+        self.norm = train_opt.get('norm')
+        fs = train_opt.get('fs') or 'wavelet'
+        ks = train_opt.get('fs_kernel_size') or 5
+        if fs == 'wavelet':
+            self.fs = self.wavelet_s
+            self.filter_high = FilterHigh(kernel_size=ks, gaussian=True).to(self.device)
+        elif fs in ('gau', 'avgpool'):
+            g = fs == 'gau'
+            self.filter_low = FilterLow(kernel_size=ks, gaussian=g).to(self.device)
+            self.filter_high = FilterHigh(kernel_size=ks, gaussian=g).to(self.device)
+            self.fs = self.filter_func
+        else:
+            raise NotImplementedError('FS type [{:s}] not recognized.'.format(str(fs)))
+
+        if self.is_train:
+            if train_opt['pixel_weight'] > 0:
+                l_pix_type = train_opt['pixel_criterion']
+                if l_pix_type == 'l1':
+                    self.cri_pix = L.L1Loss().to(self.device)
+                elif l_pix_type == 'l2':
+                    self.cri_pix = L.MSELoss().to(self.device)
+                else:
+                    raise NotImplementedError('Loss type [{:s}] not recognized.'.format(l_pix_type))
+                self.l_pix_w = train_opt['pixel_weight']
+                self.l_pix_LL_w = train_opt['pixel_LL_weight']
+                self.sup_LL = train_opt['sup_LL']
+            else:
+                logger.info('Remove pixel loss.')
+                self.cri_pix = None
+
+            self.l_fea_type = train_opt['feature_criterion']
+            if train_opt['feature_weight'] > 0:
+                if self.l_fea_type == 'l1':
+                    self.cri_fea = L.L1Loss().to(self.device)
+                elif self.l_fea_type == 'l2':
+                    self.cri_fea = L.MSELoss().to(self.device)
+                elif self.l_fea_type == 'LPIPS':
+                    raise NotImplementedError('feature_criterion LPIPS (AlexNet trunk) is a "next" row (SURVEY §8f.3); '
+                                              'use l1/l2 (VGG19 features)')
+                else:
+                    raise NotImplementedError('Loss type [{:s}] not recognized.'.format(self.l_fea_type))
+                self.l_fea_w = train_opt['feature_weight']
+            else:
+                logger.info('Remove feature loss.')
+                self.cri_fea = None
+            if self.cri_fea and self.l_fea_type in ['l1', 'l2']:
+                self.netF = networks.define_F(opt, use_bn=False).to(self.device)
+
+            self.G_update_inter = train_opt['G_update_inter'] or 1
+            self.D_update_inter = train_opt['D_update_inter'] or 1
+            self.D_update_ratio = train_opt['D_update_ratio'] if train_opt['D_update_ratio'] else 1
+            self.D_init_iters = train_opt['D_init_iters'] if train_opt['D_init_iters'] else 0
+
+            wd_G = train_opt['weight_decay_G'] if train_opt['weight_decay_G'] else 0
+            optim_params = []
+            for k, v in self.netG.named_parameters():
+                if v.requires_grad:
+                    optim_params.append(v)
+                else:
+                    logger.warning('Params [{:s}] will not optimize.'.format(k))
+            self.optimizer_G = torch.optim.Adam(optim_params, lr=train_opt['lr_G'], weight_decay=wd_G,
+                                                betas=(train_opt['beta1_G'], 0.999))
+            self.optimizers.append(self.optimizer_G)
+            wd_D = train_opt['weight_decay_D'] if train_opt['weight_decay_D'] else 0
+            if self.l_gan_H_target_w > 0:
+                self.optimizer_D_target = torch.optim.Adam(self.netD_target.parameters(), lr=train_opt['lr_D'],
+                                                           weight_decay=wd_D, betas=(train_opt['beta1_D'], 0.999))
+                self.optimizers.append(self.optimizer_D_target)
+            if self.l_gan_H_source_w > 0:
+                self.optimizer_D_source = torch.optim.Adam(self.netD_source.parameters(), lr=train_opt['lr_D'],
+                                                           weight_decay=wd_D, betas=(train_opt['beta1_D'], 0.999))
+                self.optimizers.append(self.optimizer_D_source)
+
+            if train_opt['lr_scheme'] == 'MultiStepLR':
+                for optimizer in self.optimizers:
+                    self.schedulers.append(lr_scheduler.MultiStepLR(optimizer, train_opt['lr_steps'], train_opt['lr_gamma']))
+            else:
+                raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
+            self.log_dict = OrderedDict()
+            self._log_t = OrderedDict()
+            # data parallel: one flat gradient bucket over [G | D_target | D_source]
+            nets = [self.netG] + ([self.netD_target] if self.l_gan_H_target_w > 0 else []) + \
+                   ([self.netD_source] if self.l_gan_H_source_w > 0 else [])
+            self.grad_sync = dp.GradBucket([p for n in nets for p in n.parameters() if p.requires_grad])
+        self.print_network()
+        if self.val_lpips:
+            logger.warning('val_lpips requested: LPIPS is not part of the B200 path; LPIPS is reported as nan')
+
+    # ------------------------------------------------------------------------------------------ data
+    def feed_data(self, data, istrain):
+        if istrain and 'HR' in data:
+            HR_pair = data['HR'].to(self.device)
+            HR_unpair = data['HR_unpair'].to(self.device)
+            fake_w = data['fake_w'].to(self.device).float().contiguous()
+            real_LR = data['LR_real'].to(self.device)
+            fake_LR = data['LR_fake'].to(self.device)
+            self.var_L = torch.cat([fake_LR, real_LR], dim=0)
+            self.var_H = torch.cat([HR_pair, HR_unpair], dim=0)
+            # bilinear (align_corners=False) resize of the domain-distance map to the HR crop
+            self.weights = torch.empty((fake_w.shape[0], fake_w.shape[1], HR_pair.shape[2], HR_pair.shape[3]),
+                                       dtype=torch.float32, device=self.device)
+            ops.bilinear(fake_w, self.weights)
+            B = self.var_L.shape[0]
+            self.mask = [0] * (B // 2) + [1] * (B - B // 2)
+        else:
+            self.var_L = data['LR'].to(self.device)
+            if 'HR' in data:
+                self.var_H = data['HR'].to(self.device)
+                self.needHR = True
+            else:
+                self.needHR = False
+
+    # ------------------------------------------------------------------------------------------ step
+    def optimize_parameters(self, step):
+        self.fake_H = self.netG(self.var_L)
+        self.fake_LL, self.fake_Hc = self.fs(self.fake_H, norm=self.norm)
+        self.real_LL, self.real_Hc = self.fs(self.var_H, norm=self.norm)
+
+        self.fake_SR_source, _ = b_split(self.fake_H, self.mask)
+        self.fake_SR_LL_source, _ = b_split(self.fake_LL, self.mask)
+        self.fake_SR_Hf_source, self.fake_SR_Hf_target = b_split(self.fake_Hc, self.mask)
+        self.real_HR_source, _ = b_split(self.var_H, self.mask)
+        self.real_HR_LL_source, _ = b_split(self.real_LL, self.mask)
+        self.real_HR_Hf_source, self.real_HR_Hf_target = b_split(self.real_Hc, self.mask)
+
+        do_G = step % self.G_update_inter == 0
+        do_D = step % self.D_update_inter == 0
+        log = self._log_t
+        if do_G:
+            l_g_total = 0
+            if self.cri_pix:
+                if self.multiweights:
+                    l_g_pix = self.l_pix_w * L.weighted_l1(self.fake_SR_source, self.real_HR_source, self.weights)
+                else:
+                    l_g_pix = self.cri_pix(self.fake_SR_source, self.real_HR_source)
+                l_g_total += self.l_pix_w * l_g_pix
+                if self.sup_LL:
+                    l_g_LL_pix = self.cri_pix(self.fake_SR_LL_source, self.real_HR_LL_source)
+                    l_g_total += self.l_pix_LL_w * l_g_LL_pix
+            if self.cri_fea and self.l_fea_type in ['l1', 'l2']:
+                real_fea = self.netF(self.real_HR_source).detach()
+                fake_fea = self.netF(self.fake_SR_source)
+                l_g_fea = self.cri_fea(fake_fea, real_fea)
+                l_g_total += self.l_fea_w * l_g_fea
+            if self.l_gan_H_target_w > 0:
+                with _params_frozen(self.netD_target):
+                    pred_g_Hf_target_fake = self.netD_target(self.fake_SR_Hf_target)
+                l_g_gan_target_Hf = self.cri_gan(pred_g_Hf_target_fake, True)
+                l_g_total += self.l_gan_H_target_w * l_g_gan_target_Hf
+            if self.l_gan_H_source_w > 0:
+                with _params_frozen(self.netD_source):
+                    pred_g_Hf_source_fake = self.netD_source(self.fake_SR_Hf_source)
+                l_g_gan_source_Hf = self.l_gan_H_source_w * self.cri_gan(pred_g_Hf_source_fake, True)
+                l_g_total += l_g_gan_source_Hf
+            self.optimizer_G.zero_grad()
+            l_g_total.backward()
+            if not self.grad_sync.active:
+                self.optimizer_G.step()
+
+        if do_D:
+            if self.l_gan_H_target_w > 0:
+                pred_d_target_real = self.netD_target(self.real_HR_Hf_target.detach())
+                pred_d_target_fake = self.netD_target(self.fake_SR_Hf_target.detach())
+                l_d_target_real = self.cri_gan(pred_d_target_real, True)
+                l_d_target_fake = self.cri_gan(pred_d_target_fake, False)
+                l_d_target_total = (l_d_target_real + l_d_target_fake) / 2
+                self.optimizer_D_target.zero_grad()
+                l_d_target_total.backward()
+                if not self.grad_sync.active:
+                    self.optimizer_D_target.step()
+            if self.l_gan_H_source_w > 0:
+                pred_d_source_real = self.netD_source(self.real_HR_Hf_source.detach())
+                pred_d_source_fake = self.netD_source(self.fake_SR_Hf_source.detach())
+                l_d_source_real = self.cri_gan(pred_d_source_real, True)
+                l_d_source_fake = self.cri_gan(pred_d_source_fake, False)
+                l_d_source_total = (l_d_source_fake + l_d_source_real) / 2
+                self.optimizer_D_source.zero_grad()
+                l_d_source_total.backward()
+                if not self.grad_sync.active:
+                    self.optimizer_D_source.step()
+
+        if self.grad_sync.active:
+            # ONE all-reduce (mean) of [G | D] gradients per step over NCCL, then the deferred optimiser steps
+            self.grad_sync.all_reduce_mean()
+            if do_G:
+                self.optimizer_G.step()
+            if do_D and self.l_gan_H_target_w > 0:
+                self.optimizer_D_target.step()
+            if do_D and self.l_gan_H_source_w > 0:
+                self.optimizer_D_source.step()
+
+        if do_G:
+            if self.cri_pix:
+                log['loss/l_g_pix'] = l_g_pix.detach()
+                if self.sup_LL:
+                    log['loss/l_g_LL_pix'] = l_g_LL_pix.detach()
+            if self.cri_fea:
+                log['loss/l_g_fea'] = l_g_fea.detach()
+            if self.l_gan_H_target_w > 0:
+                log['loss/l_g_gan_target_Hf'] = l_g_gan_target_Hf.detach()
+            if self.l_gan_H_source_w > 0:
+                log['loss/l_g_gan_source_H'] = l_g_gan_source_Hf.detach()
+        if do_D:
+            if self.l_gan_H_target_w > 0:
+                log['loss/l_d_target_total'] = l_d_target_total.detach()
+                log['disc_Score/D_real_target_H'] = L.mean(pred_d_target_real.detach())
+                log['disc_Score/D_fake_target_H'] = L.mean(pred_d_target_fake.detach())
+            if self.l_gan_H_source_w > 0:
+                log['loss/l_d_total'] = l_d_source_total.detach()
+                log['disc_Score/D_real_source_H'] = L.mean(pred_d_source_real.detach())
+                log['disc_Score/D_fake_source_H'] = L.mean(pred_d_source_fake.detach())
+
+    def test(self, tsamples=False):
+        self.netG.eval()
+        with torch.no_grad():
+            if self.chop:
+                self.fake_H = forward_chop(self.var_L, self.scale, self.netG, min_size=320000)
+            else:
+                self.fake_H = self.netG(self.var_L)
+            if not tsamples and self.val_lpips:
+                self.LPIPS = torch.tensor(float('nan'))
+            self.netG.train()
+
+    def get_current_log(self):
+        """One device->host synchronisation for the whole dict (the reference does 7-10 .item() per step)."""
+        for k, v in self._log_t.items():
+            self.log_dict[k] = float(v)
+        return self.log_dict
+
+    def get_current_visuals(self, need_HR=True, tsamples=False):
+        out = OrderedDict()
+        out['LR'] = self.var_L.detach()[0].float().cpu()
+        if tsamples:
+            out['hf'] = self.filter_high(self.fake_H).float().cpu()
+            out['gt_hf'] = self.filter_high(self.var_H).float().cpu()
+            out['HR'] = self.var_H.detach()[0].float().cpu()
+            out['HR_hf'] = self.filter_high(self.var_H).detach().float().cpu()
+            out['SR'] = self.fake_H.detach().float().cpu()
+        else:
+            out['SR'] = self.fake_H.detach()[0].float().cpu()
+            if self.val_lpips:
+                out['LPIPS'] = self.LPIPS.detach().float().cpu()
+            if self.needHR:
+                out['HR'] = self.var_H.detach()[0].float().cpu()
+        return out
+
+    def print_network(self):
+        nets = [('G', self.netG)]
+        if self.is_train:
+            if self.l_gan_H_target_w > 0:
+                nets.append(('D_target', self.netD_target))
+            if self.l_gan_H_source_w > 0:
+                nets.append(('D_source', self.netD_source))
+            if self.cri_fea and self.l_fea_type in ['l1', 'l2']:
+                nets.append(('F', self.netF))
+        for label, net in nets:
+            s, n = self.get_network_description(net)
+            if isinstance(net, nn.DataParallel):
+                name = '{} - {}'.format(net.__class__.__name__, net.module.__class__.__name__)
+            else:
+                name = '{}'.format(net.__class__.__name__)
+            logger.info('Network {} structure: {}, with parameters: {:,d}'.format(label, name, n))
+            logger.info(s)
+
+    def load(self):
+        path = self.opt['path']
+        if path['pretrain_model_G'] is not None:
+            logger.info('Loading pretrained model for G [{:s}] ...'.format(path['pretrain_model_G']))
+            self.load_network(path['pretrain_model_G'], self.netG)
+        if self.opt['is_train'] and path['pretrain_model_D_target'] is not None:
+            logger.info('Loading pretrained model for D_target [{:s}] ...'.format(path['pretrain_model_D_target']))
+            self.load_network(path['pretrain_model_D_target'], self.netD_target)
+        if self.opt['is_train'] and path['pretrain_model_D_source'] is not None:
+            logger.info('Loading pretrained model for D_source [{:s}] ...'.format(path['pretrain_model_D_source']))
+            self.load_network(path['pretrain_model_D_source'], self.netD_source)
+
+    def save(self, iter_step):
+        self.save_network(self.netG, 'G', iter_step)
+        if self.l_gan_H_target_w > 0:
+            self.save_network(self.netD_target, 'D_target', iter_step)
+        if self.l_gan_H_source_w > 0:
+            self.save_network(self.netD_source, 'D_source', iter_step)
+
+    # ------------------------------------------------------------------------- frequency separation
+    def wavelet_s(self, x, norm=False):
+        """(LL, cat(LH,HL,HH)) with LL*0.5 and Hc*0.5+0.5 when norm — one fused kernel."""
+        return L.haar_split(x, norm)
+
+    def filter_func(self, x, norm=False):
+        low_f, high_f = self.filter_low(x), self.filter_high(x)
+        if norm:
+            high_f = high_f * 0.5 + 0.5
+        return low_f, high_f

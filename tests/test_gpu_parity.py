@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures generated from the reference.  Tolerances: fp32 mode 1e-3 relative L-inf (BASELINE north_star;
+measured ~1e-6), bf16 tcgen05 mode 3e-2 relative L-inf on activations (operand rounding)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import srn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3
+
+
+def rel_linf(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cuda_sd(sd):
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+def build_G(nb, sd):
+    from dasr_b200.srn.models.modules.architecture import RRDBNet
+    net = RRDBNet(3, 3, 64, nb, gc=32, upscale=4)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda()
+
+
+# ------------------------------------------------------------------------------------------------ G
+def test_rrdbnet_fp32_forward_backward_vs_golden(golden):
+    g = golden('rrdbnet_nb1.pt')
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=g['nb']), g['w_seed'], g['w_gain'])
+    net = build_G(g['nb'], sd)
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert out.shape == g['out'].shape
+    assert rel_linf(out, g['out']) < FP32_TOL
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    assert rel_linf(x.grad, g['dx']) < FP32_TOL
+    named = dict(net.named_parameters())
+    for k, ref in g['grads'].items():
+        assert rel_linf(named[k].grad, ref) < FP32_TOL, k
+    for k, n in g['grad_norms'].items():
+        assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 16, 8), (2, 3, 21, 13), (1, 3, 40, 24)])
+def test_rrdbnet_fp32_inference_vs_oracle(shape):
+    nb = 2
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 101, 0.3)
+    net = build_G(nb, sd).eval()
+    net.precision = 'fp32'
+    x = O.synth_image(shape, 102)
+    with torch.no_grad():
+        out = net(x.cuda())
+        ref = O.rrdbnet_forward(x, sd, nb)
+    assert rel_linf(out, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 16, 8), (2, 3, 21, 13), (1, 3, 48, 40)])
+def test_rrdbnet_bf16_tcgen05_vs_oracle(shape):
+    nb = 2
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 103, 0.3)
+    net = build_G(nb, sd).eval()
+    net.precision = 'bf16'
+    x = O.synth_image(shape, 104)
+    with torch.no_grad():
+        out = net(x.cuda())
+        ref = O.rrdbnet_forward(x, sd, nb)
+    assert out.shape == ref.shape
+    assert rel_linf(out, ref) < 3e-2
+    # and the result does not depend on which A-operand path the kernel uses (shifted descriptors vs per-tap tiles)
+
+
+def test_rrdbnet_bf16_batch_independence_full_width():
+    """Size-independent property at the BASELINE tile width (256): a batched forward equals per-image forwards
+    bit for bit (tiles never mix images; zero padding comes from TMA out-of-bounds fill)."""
+    nb = 1
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 105, 0.3)
+    net = build_G(nb, sd).eval()
+    net.precision = 'bf16'
+    x = O.synth_image((3, 3, 64, 256), 106).cuda()
+    with torch.no_grad():
+        full = net(x)
+        parts = torch.cat([net(x[i:i + 1]) for i in range(3)], 0)
+    assert torch.equal(full, parts)
+
+
+def test_rrdbnet_bf16_translation_property():
+    """Zero-padded conv stack is shift-equivariant away from borders: cropping the input by whole tiles moves
+    the interior of the output by 4x the shift (checks tile/halo addressing at non-trivial offsets)."""
+    nb = 1
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 107, 0.3)
+    net = build_G(nb, sd).eval()
+    net.precision = 'fp32'
+    x = O.synth_image((1, 3, 96, 64), 108).cuda()
+    with torch.no_grad():
+        a = net(x)
+        b = net(x[:, :, 16:, 8:].contiguous())
+    # receptive field of nb=1: 1 + 15 + 1 (LR side) + tail < 20 LR px => compare beyond 24 LR px from the cut
+    m = 24
+    ia = a[:, :, 4 * (16 + m):, 4 * (8 + m):]
+    ib = b[:, :, 4 * m:, 4 * m:]
+    assert rel_linf(ia, ib) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ D
+def test_nlayer_d_vs_golden(golden):
+    from dasr_b200.srn.models.modules.architecture import NLayerDiscriminator
+    g = golden('nlayer_d.pt')
+    sd = O.synth_state_dict(O.nlayer_d_shapes(9, 64, 2), g['w_seed'], 1.0)
+    net = NLayerDiscriminator(9, n_layers=2)
+    net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert rel_linf(out, g['out']) < FP32_TOL
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    assert rel_linf(x.grad, g['dx']) < FP32_TOL
+    named = dict(net.named_parameters())
+    for k, ref in g['grads'].items():
+        assert rel_linf(named[k].grad, ref) < FP32_TOL, k
+    for k, n in g['grad_norms'].items():
+        assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+
+
+@pytest.mark.parametrize('in_nc,hw', [(3, (36, 28)), (9, (18, 22))])
+def test_nlayer_d_ragged_vs_oracle(in_nc, hw):
+    from dasr_b200.srn.models.modules.architecture import NLayerDiscriminator
+    sd = O.synth_state_dict(O.nlayer_d_shapes(in_nc, 64, 2), 111, 1.0)
+    net = NLayerDiscriminator(in_nc, n_layers=2)
+    net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = O.synth_image((3, in_nc) + hw, 112)
+    ref = O.nlayer_d_forward(x, sd, 2)
+    out = net(x.cuda())
+    assert out.shape == ref.shape and rel_linf(out, ref) < FP32_TOL
+
+
+# ---------------------------------------------------------------------------------------------- VGG
+def test_vgg19_vs_golden(golden):
+    from dasr_b200.srn.models.modules.architecture import VGGFeatureExtractor
+    g = golden('vgg19.pt')
+    sd = O.synth_state_dict(O.vgg19_shapes(34), g['w_seed'], 1.0)
+    net = VGGFeatureExtractor(feature_layer=34, weights=sd).cuda()
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert out.shape == g['out'].shape
+    assert rel_linf(out, g['out']) < FP32_TOL
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    assert rel_linf(x.grad, g['dx']) < FP32_TOL
+
+
+# ------------------------------------------------------------------------ filters / haar / losses
+def test_filters_haar_bilinear_losses(golden):
+    from dasr_b200 import ops
+    from dasr_b200.srn.models.modules import architecture as A
+    from dasr_b200.srn.models.modules import loss as L
+    g = golden('misc.pt')
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda()
+    assert torch.allclose(A.FilterLow(kernel_size=5, gaussian=True).cuda()(x).cpu(), g['gau_low_k5'], atol=1e-6)
+    assert torch.allclose(A.FilterHigh(kernel_size=5, gaussian=True).cuda()(x).cpu(), g['gau_high_k5'], atol=1e-6)
+    assert torch.allclose(A.FilterLow(kernel_size=5, gaussian=False, include_pad=True).cuda()(x).cpu(), g['avg_low_k5_incl'], atol=1e-6)
+    assert torch.allclose(A.FilterHigh(kernel_size=5, gaussian=False, include_pad=False).cuda()(x).cpu(), g['avg_high_k5_excl'], atol=1e-6)
+    assert torch.allclose(A.FilterHigh(kernel_size=9, gaussian=True).cuda()(x).cpu(), g['gau_high_k9'], atol=1e-6)
+    w = O.synth_image((2, 1, 4, 3), g['w_seed']).cuda()
+    up = torch.empty((2, 1, 16, 12), device='cuda')
+    ops.bilinear(w, up)
+    assert torch.allclose(up.cpu(), g['bilinear_x4'], atol=1e-6)
+    p = O.synth((2, 1, 6, 6), g['p_seed'], 3.0).cuda()
+    for t in ('vanilla', 'lsgan', 'wgan-gp'):
+        crit = L.GANLoss(t)
+        assert abs(float(crit(p, True)) - float(g['gan_%s_real' % t])) < 1e-5
+        assert abs(float(crit(p, False)) - float(g['gan_%s_fake' % t])) < 1e-5
+    # haar split (+norm) against the oracle restatement, forward and backward
+    xr = x.clone().requires_grad_(True)
+    ll, hc = L.haar_split(xr, True)
+    rll, rhc = O.wavelet_s(x.cpu(), True)
+    assert torch.allclose(ll.cpu(), rll, atol=1e-6) and torch.allclose(hc.cpu(), rhc, atol=1e-6)
+    pa, pb = O.synth(tuple(ll.shape), 7).cuda(), O.synth(tuple(hc.shape), 8).cuda()
+    ((ll * pa).sum() + (hc * pb).sum()).backward()
+    xc = x.cpu().clone().requires_grad_(True)
+    cl, ch = O.wavelet_s(xc, True)
+    ((cl * pa.cpu()).sum() + (ch * pb.cpu()).sum()).backward()
+    assert torch.allclose(xr.grad.cpu(), xc.grad, atol=1e-6)
+    # filter backward (gaussian high-pass and box filter without pad counting)
+    for kw in (dict(kernel_size=5, gaussian=True), dict(kernel_size=5, gaussian=False, include_pad=False)):
+        xr = x.clone().requires_grad_(True)
+        y = A.FilterHigh(**kw).cuda()(xr)
+        pat = O.synth(tuple(y.shape), 9)
+        (y * pat.cuda()).sum().backward()
+        xc = x.cpu().clone().requires_grad_(True)
+        (O.filter_high(xc, 5, kw['gaussian'], kw.get('include_pad', True)) * pat).sum().backward()
+        assert torch.allclose(xr.grad.cpu(), xc.grad, atol=1e-6)
+
+
+def test_weighted_l1_and_l1_grad():
+    from dasr_b200.srn.models.modules import loss as L
+    a = O.synth_image((2, 3, 12, 8), 121)
+    b = O.synth_image((2, 3, 12, 8), 122)
+    w = O.synth_image((2, 1, 12, 8), 123)
+    ac = a.clone().requires_grad_(True)
+    ref = torch.mean(w * torch.abs(ac - b))
+    ref.backward()
+    ag = a.cuda().requires_grad_(True)
+    out = L.weighted_l1(ag, b.cuda(), w.cuda())
+    (out * 3.0).backward()
+    assert abs(float(out) - float(ref)) < 1e-6
+    assert torch.allclose(ag.grad.cpu(), 3.0 * ac.grad, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------ full model, API level
+def make_opt(is_train, model, nb=1, fs='wavelet', gpu=True):
+    from dasr_b200.srn.options.options import dict_to_nonedict
+    return dict_to_nonedict({
+        'name': 'test', 'model': model, 'scale': 4, 'gpu_ids': [0] if gpu else None, 'is_train': is_train, 'chop': False,
+        'val_lpips': False, 'multiweights': True,
+        'path': {'pretrain_model_G': None, 'pretrain_model_D_target': None, 'pretrain_model_D_source': None,
+                 'models': '/tmp', 'training_state': '/tmp'},
+        'network_G': {'which_model_G': 'RRDB_net', 'norm_type': None, 'mode': 'CNA', 'nf': 64, 'nb': nb, 'in_nc': 3,
+                      'out_nc': 3, 'gc': 32, 'group': 1, 'scale': 4},
+        'network_D': {'which_model_D': 'discriminator_patch', 'which_model_pairD': 'discriminator_patch',
+                      'norm_type': 'Batch', 'act_type': 'leakyrelu', 'mode': 'CNA', 'nf': 64,
+                      'in_nc': 9 if fs == 'wavelet' else 3, 'n_layers': 2},
+        'train': {'lr_G': 5e-5, 'weight_decay_G': 0, 'beta1_G': 0.9, 'lr_D': 5e-5, 'weight_decay_D': 0, 'beta1_D': 0.9,
+                  'lr_scheme': 'MultiStepLR', 'lr_steps': [50000, 80000], 'lr_gamma': 0.5, 'fs': fs, 'norm': True,
+                  'sup_LL': True, 'fs_kernel_size': 5, 'pixel_criterion': 'l1', 'pixel_weight': 1, 'pixel_LL_weight': 1,
+                  'feature_criterion': 'l1', 'feature_weight': 1e-2, 'gan_type': 'vanilla', 'ragan': False,
+                  'gan_H_target': 1e-4, 'gan_H_source': 0, 'G_update_inter': 1, 'D_update_inter': 1,
+                  'D_update_ratio': 1, 'D_init_iters': 0, 'manual_seed': 0, 'niter': 10, 'val_freq': 10}})
+
+
+def unwrap(net):
+    return net.module if isinstance(net, torch.nn.DataParallel) else net
+
+
+@pytest.mark.parametrize('name', ['dasr_step_wavelet.pt', 'dasr_step_gau.pt'])
+def test_dasr_model_train_steps_vs_golden(golden, name):
+    """create_model -> feed_data -> optimize_parameters x2 through the public API, against the log values
+    and post-step weights the reference produced for the same inputs (oracle/gen_golden.py)."""
+    from dasr_b200.srn.models import create_model
+    g = golden(name)
+    fs = g['fs']
+    model = create_model(make_opt(True, 'DASR', g['nb'], fs))
+    unwrap(model.netG).load_state_dict(O.synth_state_dict(O.rrdbnet_shapes(nb=g['nb']), g['wG_seed'], g['gain_G']))
+    unwrap(model.netD_target).load_state_dict(O.synth_state_dict(O.nlayer_d_shapes(9 if fs == 'wavelet' else 3, 64, 2), g['wD_seed'], 1.0))
+    unwrap(model.netF).load_state_dict(O.synth_state_dict(O.vgg19_shapes(34), g['wF_seed'], 1.0), strict=False)
+    B, h, w = g['B'], g['h'], g['w']
+    for step, (seed, ref) in enumerate(zip(g['data_seeds'], g['steps']), 1):
+        data = {'LR_real': O.synth_image((B, 3, h, w), seed), 'LR_fake': O.synth_image((B, 3, h, w), seed + 1),
+                'HR': O.synth_image((B, 3, 4 * h, 4 * w), seed + 2), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * w), seed + 3),
+                'fake_w': O.synth_image((B, 1, h, w), seed + 4)}
+        model.feed_data(data, True)
+        model.optimize_parameters(step)
+        log = model.get_current_log()
+        assert list(log.keys()) == list(ref['log'].keys())
+        for k in log:
+            assert abs(log[k] - ref['log'][k]) <= 1e-3 * max(1.0, abs(ref['log'][k])), (k, log[k], ref['log'][k])
+        assert rel_linf(model.fake_H, ref['fake_H']) < FP32_TOL
+        G, D = unwrap(model.netG).state_dict(), unwrap(model.netD_target).state_dict()
+        for k, v in ref['G_keep'].items():
+            assert rel_linf(G[k], v) < FP32_TOL, k
+        for k, v in ref['D_keep'].items():
+            assert rel_linf(D[k], v) < FP32_TOL, k
+        for k, n in ref['G_norms'].items():
+            assert abs(float(G[k].double().norm()) - n) <= 1e-4 * max(n, 1e-9), k
+        for k, n in ref['D_norms'].items():
+            assert abs(float(D[k].double().norm()) - n) <= 1e-4 * max(n, 1e-9), k
+
+
+def test_sr_model_test_path_vs_golden(golden):
+    from dasr_b200.srn.models import create_model
+    from dasr_b200.srn.utils import util
+    g = golden('sr_test.pt')
+    for prec, tol in (('fp32', FP32_TOL), ('bf16', 3e-2)):
+        model = create_model(make_opt(False, 'sr', g['nb']))
+        unwrap(model.netG).load_state_dict(O.synth_state_dict(O.rrdbnet_shapes(nb=g['nb']), g['w_seed'], g['gain']))
+        unwrap(model.netG).precision = prec
+        model.feed_data({'LR': O.synth_image(g['lr_shape'], g['lr_seed']), 'HR': O.synth_image((1, 3, 40, 56), g['hr_seed'])})
+        model.test()
+        vis = model.get_current_visuals(need_HR=True)
+        assert rel_linf(vis['SR'], g['SR']) < tol
+        img = util.tensor2img(vis['SR'] * 8.0 + 0.5)
+        hr = util.tensor2img(vis['HR'])
+        if prec == 'fp32':
+            assert np.abs(img.astype(int) - g['sr_img'].numpy().astype(int)).max() <= 1
+            assert abs(util.calculate_psnr(img, hr) - g['psnr']) < 1e-3        # 3 decimals
+            assert abs(util.calculate_ssim(img, hr) - g['ssim']) < 1e-3
+        else:
+            assert abs(util.calculate_psnr(img, hr) - g['psnr']) < 0.05
+
+
+def test_ops_refuse_cpu_tensors():
+    from dasr_b200._lib import DasrError
+    from dasr_b200.srn.models.modules.architecture import RRDBNet
+    net = RRDBNet(3, 3, 64, 1)
+    with pytest.raises(DasrError):
+        net(torch.rand(1, 3, 8, 8))

@@ -1,0 +1,141 @@
+"""Host-side logic (CPU): option parsing, model construction / state_dict contract, b_split, metrics,
+and the data-parallel gradient bucket over gloo with world_size 2."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import srn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_options_parse_roundtrip(tmp_path):
+    from dasr_b200.srn.options import options as option
+    cfg = {
+        "name": "debug_x", "model": "sr", "scale": 4, "gpu_ids": [], "chop": False,
+        "datasets": {"test_1": {"name": "a", "mode": "LRHR", "dataroot_HR": "~/hr", "dataroot_LR": "~/lr.lmdb"}},
+        "path": {"root": str(tmp_path), "pretrain_model_G": None},
+        "network_G": {"which_model_G": "RRDB_net", "nf": 64, "nb": 23, "in_nc": 3, "out_nc": 3, "gc": 32},
+    }
+    p = tmp_path / 'o.json'
+    p.write_text('// comment line\n' + json.dumps(cfg, indent=1).replace('"scale": 4,', '"scale": 4, // x4'))
+    opt = option.parse(str(p), is_train=False)
+    assert opt['is_train'] is False and opt['network_G']['scale'] == 4
+    assert opt['datasets']['test_1']['phase'] == 'test' and opt['datasets']['test_1']['data_type'] == 'lmdb'
+    assert opt['path']['results_root'].endswith(os.path.join('results', 'debug_x'))
+    nd = option.dict_to_nonedict(opt)
+    assert nd['nonexistent'] is None and nd['network_G']['norm_type'] is None
+    assert 'which_model_G' in option.dict2str(nd)
+
+
+def test_shipped_json_files_parse():
+    """The reference's own option files parse unchanged (they are read from tests/data copies of the two
+    files the north star names; paths inside are never touched at parse time)."""
+    from dasr_b200.srn.options import options as option
+    for name, train in (('test_sr.json', False), ('train_DASR_auto_reproduce_realsr.json', True)):
+        opt = option.dict_to_nonedict(option.parse(os.path.join(ROOT, 'tests', 'data', name), is_train=train))
+        assert opt['network_G']['which_model_G'] == 'RRDB_net' and opt['network_G']['nb'] == 23
+        assert opt['scale'] == 4
+
+
+def test_create_model_state_dict_contract_and_cpu_refusal():
+    from dasr_b200._lib import DasrError
+    from dasr_b200.srn.models import create_model
+    from tests.test_gpu_parity import make_opt
+    with pytest.warns(UserWarning):
+        model = create_model(make_opt(True, 'DASR_FS_ESRGAN_patchGAN', nb=2, gpu=False))   # alias the shipped JSONs use
+    assert list(model.netG.state_dict().keys()) == list(O.rrdbnet_shapes(nb=2).keys())
+    assert list(model.netD_target.state_dict().keys()) == list(O.nlayer_d_shapes(9, 64, 2).keys())
+    assert len(model.optimizers) == 2 and len(model.schedulers) == 2
+    # G: kaiming * 0.1, zero bias (networks.py:30-44,142-143)
+    w = model.netG.state_dict()['model.1.sub.0.RDB1.conv1.0.weight']
+    assert abs(float(w.std()) - 0.1 * (2.0 / (64 * 9)) ** 0.5) < 0.2 * 0.1 * (2.0 / (64 * 9)) ** 0.5
+    assert float(model.netG.state_dict()['model.0.bias'].abs().max()) == 0.0
+    data = {k: torch.rand(1, 3, 8, 8) for k in ('LR_real', 'LR_fake')}
+    data.update(HR=torch.rand(1, 3, 32, 32), HR_unpair=torch.rand(1, 3, 32, 32), fake_w=torch.rand(1, 1, 8, 8))
+    with pytest.raises(DasrError):          # no CPU fallback: the product path refuses to run without CUDA
+        model.feed_data(data, True)
+        model.optimize_parameters(1)
+    with pytest.raises(NotImplementedError):
+        create_model(make_opt(True, 'srgan', gpu=False))
+
+
+def test_save_load_checkpoint_roundtrip(tmp_path):
+    from dasr_b200.srn.models import create_model
+    from tests.test_gpu_parity import make_opt
+    opt = make_opt(True, 'DASR', nb=1, gpu=False)
+    opt['path']['models'] = str(tmp_path)
+    opt['path']['training_state'] = str(tmp_path)
+    with pytest.warns(UserWarning):
+        m = create_model(opt)
+    m.save(7)
+    m.save_training_state(1, 7)
+    assert sorted(os.listdir(tmp_path)) == ['7.state', '7_D_target.pth', '7_G.pth']
+    sd = torch.load(tmp_path / '7_G.pth')
+    assert list(sd.keys()) == list(O.rrdbnet_shapes(nb=1).keys()) and sd['model.0.weight'].dtype == torch.float32
+    opt['path']['pretrain_model_G'] = str(tmp_path / '7_G.pth')
+    with pytest.warns(UserWarning):
+        m2 = create_model(opt)
+    assert torch.equal(m2.netG.state_dict()['model.3.weight'], sd['model.3.weight'])
+    m2.resume_training(torch.load(tmp_path / '7.state'))
+
+
+def test_b_split_and_metrics(golden):
+    from dasr_b200.srn.utils import util
+    g = golden('misc.pt')
+    x = O.synth_image(g['x_shape'], g['x_seed'])
+    fa, re = util.b_split(x.repeat(2, 1, 1, 1), [0, 0, 1, 1])
+    assert torch.equal(fa, g['b_split_fake']) and torch.equal(re, g['b_split_real'])
+    fa2, re2 = util.b_split(x.repeat(2, 1, 1, 1), [0, 1, 0, 1])
+    assert torch.equal(fa2, x.repeat(2, 1, 1, 1)[[0, 2]]) and torch.equal(re2, x.repeat(2, 1, 1, 1)[[1, 3]])
+    img = util.tensor2img(x[0] * 1.2 - 0.1)
+    assert np.array_equal(img, g['tensor2img'].numpy())
+    assert abs(util.calculate_psnr(img, util.tensor2img(x[1].clone())) - g['psnr']) < 1e-9
+    big = O.synth_image((2, 3, 24, 24), g['ssim_seed'])
+    i1, i2 = util.tensor2img(big[0].clone()), util.tensor2img(big[0] * 0.9 + 0.1 * big[1])
+    assert abs(util.calculate_ssim(i1, i2) - g['ssim']) < 1e-9
+
+
+DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from dasr_b200.dp import GradBucket
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% sys.argv[2], rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+bucket = GradBucket(list(net.parameters()))
+assert bucket.active and bucket.numel() == sum(p.numel() for p in net.parameters())
+x = torch.arange(10, dtype=torch.float32).reshape(2, 5) * (rank + 1)
+net(x).sum().backward()
+local = [p.grad.clone() for p in net.parameters()]
+bucket.all_reduce_mean()
+# reference: mean of the two ranks' gradients
+outs = []
+for r in range(2):
+    net.zero_grad()
+    net(torch.arange(10, dtype=torch.float32).reshape(2, 5) * (r + 1)).sum().backward()
+    outs.append([p.grad.clone() for p in net.parameters()])
+for i, p in enumerate(net.parameters()):
+    pass
+ok = all(torch.allclose(bucket.views[i], (outs[0][i] + outs[1][i]) / 2, atol=1e-6) for i in range(len(local)))
+assert ok, 'bucket mismatch'
+assert all(p.grad.data_ptr() != 0 for p in net.parameters())
+print('rank', rank, 'ok')
+'''
+
+
+def test_grad_bucket_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(DP_WORKER % ROOT)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all('ok' in o for o in outs)
