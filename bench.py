@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DASR SRN hot path on B200 (contract in the task statement).
+
+Workload (BASELINE.json configs[1]): RRDBNet-23 x4 generator forward, batch 16 x 3 x 256 x 256 synthetic LR
+images per GPU (weak scaling), tcgen05 bf16 kernels (fp32 accumulate), random-init weights of the
+reference architecture.  metric = output megapixels / second over all GPUs.
+
+  value : device-timed steps, inputs resident in HBM (CUDA events, max over ranks)
+  e2e   : the same metric through the public API (SRModel.feed_data -> test -> get result) with PINNED HOST
+          input and output buffers, H2D + D2H inside the timed region
+  roofline      : the tcgen05 conv kernel (all conv_tc launches of a step bracketed by CUDA events)
+  cpu_baseline  : the oracle port of the reference forward on the host cores (bounded sample)
+  train         : DASR_Model train step (BASELINE configs[2]: B=32, HR crop 128) iterations / second, fp32 kernels
+
+`--impl reference` times the reference algorithm's CPU path (oracle port: the reference is pure Python and
+/root/reference does not exist on the GPU box) on the host cores with all threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB, NF, BATCH, LR = 23, 64, 16, 256
+FLOP_PER_LR_PIXEL = 35853696          # whole G forward, SURVEY.md §8(d): conv MACs x2, no recompute credit
+METRIC = 'x4 SR output megapixels/sec (RRDBNet-23 G forward)'
+
+
+def out_mp(batch, lr):
+    return batch * (4 * lr) * (4 * lr) / 1e6
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0)), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+    return 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        # median of the samples under load (upper half: the sampler also sees idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': load[len(load) // 2] if load else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def synth_weights(nb):
+    from oracle import srn_oracle as O           # deterministic synthetic weights only (bench legs may use oracle/)
+    return O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 1, 0.1)
+
+
+def cpu_reference_forward(n_images, lr, threads, steps, warmup):
+    """The reference algorithm on CPU (oracle port, fp32, torch CPU ops) — used by --impl reference and cpu_baseline."""
+    import torch
+    from oracle import srn_oracle as O
+    torch.set_num_threads(threads)
+    sd = synth_weights(NB)
+    x = O.synth_image((n_images, 3, lr, lr), 7)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.rrdbnet_forward(x, sd, NB)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.rrdbnet_forward(x, sd, NB)
+        dt = (time.perf_counter() - t0) / steps
+    return out_mp(n_images, lr) / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warm = max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0
+    mp_s, dt = cpu_reference_forward(1, LR, threads, steps, warm)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': mp_s, 'unit': 'MP/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'RRDBNet-23 x4 inference, batch 16 x 3x256x256 per GPU (configs[1]); CPU arm: one step = a '
+                               'bounded sample of 1 of the 16 images', 'inputs': 'host memory'},
+        'cpu_baseline': {'value': mp_s, 'unit': 'MP/s', 'cores': threads, 'kind': 'port',
+                         'sample': '1 x 3x256x256 image per step (1/16 of the batch), oracle/srn_oracle.py rrdbnet_forward, torch CPU fp32'},
+        'e2e': {'value': mp_s, 'unit': 'MP/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='dasr_b200')
+    ap.add_argument('--train-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from dasr_b200 import _lib, engine
+    from dasr_b200.srn.models import create_model
+    from dasr_b200.srn.options.options import dict_to_nonedict
+    from oracle import srn_oracle as O
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    opt = dict_to_nonedict({
+        'name': 'bench', 'model': 'sr', 'scale': 4, 'gpu_ids': [local_rank], 'is_train': False, 'chop': False, 'val_lpips': False,
+        'path': {'pretrain_model_G': None},
+        'network_G': {'which_model_G': 'RRDB_net', 'norm_type': None, 'mode': 'CNA', 'nf': NF, 'nb': NB, 'in_nc': 3,
+                      'out_nc': 3, 'gc': 32, 'scale': 4}})
+    model = create_model(opt)
+    netG = model.netG.module if hasattr(model.netG, 'module') else model.netG
+    netG.load_state_dict(synth_weights(NB))
+    netG.precision = 'bf16'
+    netG.eval()
+
+    x_host = O.synth_image((BATCH, 3, LR, LR), 100 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty((BATCH, 3, 4 * LR, 4 * LR), dtype=torch.float32).pin_memory()
+
+    # ---- profiling hook: CUDA events around the conv_tc launch sequence of every forward ----
+    marks = []
+    engine.PROFILE = lambda tag: marks.append((tag, _rec()))
+
+    def _rec():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    # ---------------------------------------------------------------- device-resident timing (value)
+    with torch.no_grad():
+        for _ in range(W):
+            netG(x_dev)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        marks.clear()
+        l0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            out = netG(x_dev)
+        e1.record()
+        barrier()
+        launches = _lib.LAUNCHES - l0
+        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        clocks = sampler.stop() if sampler else None
+        tc_ms = sum(marks[i][1].elapsed_time(marks[i + 1][1]) for i in range(0, len(marks), 2)) / K
+        n_tc = 1 + 5 * 3 * NB + 1 + 2 + 2
+        engine.PROFILE = None
+        del out
+
+        # ---------------------------------------------------------------- end-to-end through the public API
+        for _ in range(2):
+            model.feed_data({'LR': x_host})
+            model.test()
+            y_host.copy_(model.fake_H, non_blocking=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            model.feed_data({'LR': x_host})          # H2D of the step's input from pinned host memory
+            model.test()                             # netG forward (public API call of test.py)
+            y_host.copy_(model.fake_H, non_blocking=True)   # D2H of the result
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    model.fake_H = None
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- train step (configs[2]), fp32 kernels
+    train = None
+    if args.train_steps > 0:
+        train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    flops_step = FLOP_PER_LR_PIXEL * BATCH * LR * LR
+    ach = flops_step / (tc_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('dram_bytes_per_launch_avg')
+    line = {
+        'metric': METRIC, 'value': world * out_mp(BATCH, LR) / (ms * 1e-3), 'unit': 'MP/s', 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic',
+        'config': {'workload': 'RRDBNet-23 x4 inference, batch 16 x 3x256x256 per GPU, forward_chop off (BASELINE configs[1])',
+                   'weights': 'random init (deterministic synthetic), reference architecture nb=23 nf=64 gc=32',
+                   'parallelism': 'dp%d (independent replicas, no collective on the inference path)' % world,
+                   'l2': 'working set (3 x 403 MB concat buffers + 2.1 GB HR activations) >> 126 MB L2: no flush needed'},
+        'e2e': {'value': world * out_mp(BATCH, LR) / (e2e_ms * 1e-3), 'unit': 'MP/s', 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': y_host.numel() * 4,
+                'api': 'SRModel.feed_data(pinned host LR) -> SRModel.test() -> pinned host copy of fake_H'},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'dasr::conv_tc_kernel (tcgen05 implicit-GEMM 3x3 conv)',
+                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'peak_source': peak_src,
+                     'traffic': traffic, 'launches_per_step': n_tc, 'avg_launch_ms': tc_ms / n_tc,
+                     'algorithmic_flops_per_step': flops_step,
+                     'note': 'achieved = algorithmic conv FLOPs of one forward / CUDA-event time of its conv_tc launch sequence'},
+    }
+    if train:
+        line['train'] = train
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        mp_s, dt = cpu_reference_forward(1, LR, threads, 1, 0)
+        line['cpu_baseline'] = {'value': mp_s, 'unit': 'MP/s', 'cores': threads, 'kind': 'port', 'seconds': dt,
+                                'sample': '1 x 3x256x256 image (1/16 of the batch), oracle port of RRDBNet-23 forward, torch CPU fp32'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_train(args, dev, local_rank, world, barrier, max_over_ranks):
+    """DASR_Model.feed_data + optimize_parameters (G + D + VGG perceptual + weighted L1), B=32 per GPU, HR crop 128."""
+    import warnings
+    import torch
+    from dasr_b200 import _lib
+    from dasr_b200.srn.models import create_model
+    from dasr_b200.srn.options.options import dict_to_nonedict
+    from oracle import srn_oracle as O
+    B, h = 32, 32
+    opt = dict_to_nonedict({
+        'name': 'bench_train', 'model': 'DASR', 'scale': 4, 'gpu_ids': [local_rank], 'is_train': True, 'chop': False,
+        'val_lpips': False, 'multiweights': True,
+        'path': {'pretrain_model_G': None, 'pretrain_model_D_target': None, 'pretrain_model_D_source': None},
+        'network_G': {'which_model_G': 'RRDB_net', 'norm_type': None, 'mode': 'CNA', 'nf': NF, 'nb': NB, 'in_nc': 3,
+                      'out_nc': 3, 'gc': 32, 'scale': 4},
+        'network_D': {'which_model_D': 'discriminator_patch', 'nf': 64, 'in_nc': 9, 'n_layers': 2},
+        'train': {'lr_G': 5e-5, 'weight_decay_G': 0, 'beta1_G': 0.9, 'lr_D': 5e-5, 'weight_decay_D': 0, 'beta1_D': 0.9,
+                  'lr_scheme': 'MultiStepLR', 'lr_steps': [50000, 80000], 'lr_gamma': 0.5, 'fs': 'wavelet', 'norm': True,
+                  'sup_LL': True, 'pixel_criterion': 'l1', 'pixel_weight': 1, 'pixel_LL_weight': 1, 'feature_criterion': 'l1',
+                  'feature_weight': 1e-2, 'gan_type': 'vanilla', 'ragan': False, 'gan_H_target': 1e-4, 'gan_H_source': 0,
+                  'G_update_inter': 1, 'D_update_inter': 1, 'D_update_ratio': 1, 'D_init_iters': 0}})
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        model = create_model(opt)
+    rank = int(os.environ.get('RANK', 0))
+    data = {'LR_real': O.synth_image((B, 3, h, h), 200 + rank).pin_memory(), 'LR_fake': O.synth_image((B, 3, h, h), 300 + rank).pin_memory(),
+            'HR': O.synth_image((B, 3, 4 * h, 4 * h), 400 + rank).pin_memory(), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * h), 500 + rank).pin_memory(),
+            'fake_w': O.synth_image((B, 1, h, h), 600 + rank).pin_memory()}
+    step = 0
+    for _ in range(2):
+        step += 1
+        model.feed_data(data, True)
+        model.optimize_parameters(step)
+    barrier()
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        step += 1
+        model.feed_data(data, True)
+        model.optimize_parameters(step)
+    log = model.get_current_log()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.train_steps)
+    res = {'metric': 'DASR SRN train iterations/sec (G + patch-D + VGG19 perceptual + weighted L1, Adam x2)',
+           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps, 'dtype': 'f32',
+           'config': {'workload': 'BASELINE configs[2]: batch 32 (2B=64 LR 32x32 through G), HR crop 128, fs wavelet, per GPU',
+                      'global_batch': 32 * world, 'parallelism': 'dp%d, one flat-bucket NCCL all-reduce of G+D grads per step' % world},
+           'gpu_launches_per_step': (_lib.LAUNCHES - l0) // args.train_steps,
+           'loss_l_g_pix': log.get('loss/l_g_pix')}
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == '__main__':
+    main()

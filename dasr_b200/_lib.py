@@ -100,7 +100,12 @@ def load():
     return lib
 
 
-def check(rc, what):
+LAUNCHES = 0   # kernels launched through the C ABI since import (bench.py reports the delta)
+
+
+def check(rc, what, kernels=1):
+    global LAUNCHES
+    LAUNCHES += kernels
     if rc != 0:
         msg = load().dasr_last_error()
         raise DasrError('%s failed (rc=%d): %s' % (what, rc, msg.decode() if msg else ''))

@@ -18,6 +18,15 @@ import torch
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, DGRAD, FWD, TC_FPROP, TC_UPCONV, View
 
+# optional profiling hook: bench.py sets this to a callable(tag) that records a CUDA event on the current stream
+PROFILE = None
+
+
+def _mark(tag):
+    if PROFILE is not None:
+        PROFILE(tag)
+
+
 GC = 32  # growth channels: RRDBNet hard-codes gc=32 for every RRDB (architecture.py:183)
 
 
@@ -282,6 +291,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
     xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)       # Cin 3 -> one zero-padded 32-channel chunk
     ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
     fea = _empty((N, H, W, nf), x, bf)
+    _mark('tc_begin')
     ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
     n_rdb = L.n_rdb
     rot = [_empty((N, H, W, CS), x, bf) for _ in range(3)]
@@ -317,6 +327,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
     out_nc = Wt(L.i_hr1).shape[0]
     o16 = _empty((N, h, w, 16), x, bf)                                  # Cout 3 -> one 16-wide UMMA N tile
     ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), o16, nt=16)
+    _mark('tc_end')
     out = _empty((N, out_nc, h, w), x)
     ops.nhwc_to_nchw(View(o16, out_nc, 0), out)
     return out

@@ -104,7 +104,7 @@ def conv2d_wgrad_f32(inp, dout, dw, db, k, stride, pad, ups=1, accumulate=False)
     n = lib.dasr_conv2d_wgrad_f32_workspace(C.byref(p))
     ws = _workspace(n, inp.t.device)
     check(lib.dasr_conv2d_wgrad_f32(inp.ptr, dout.ptr, _p(dw), _p(db), C.byref(p), int(accumulate), _p(ws),
-                                    ws.numel(), _stream()), 'conv2d_wgrad_f32')
+                                    ws.numel(), _stream()), 'conv2d_wgrad_f32', 4 if db is not None else 2)
 
 
 def pack_filter_f32(w, for_dgrad=False):
@@ -137,7 +137,7 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     N, H, W, _ = inp.t.shape
     p = ConvTcParams()
     lib = _lib.load()
-    check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup')
+    check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup', 0)
     p.N, p.H, p.W = N, H, W
     p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
     p.cout, p.out_cs, p.out_coff = out.c, out.cs, out.coff
@@ -248,18 +248,18 @@ def _partials(device):
 def wl1_loss(a, b, w, loss, grad, gscale):
     N, Cc, H, W = a.shape
     check(_lib.load().dasr_wl1_loss(_p(a), _p(b), _p(w), _p(loss), _p(grad), gscale, N, Cc, H * W,
-                                    _p(_partials(a.device)), _stream()), 'wl1_loss')
+                                    _p(_partials(a.device)), _stream()), 'wl1_loss', 2)
 
 
 def mse_loss(a, b, loss, grad, gscale):
     check(_lib.load().dasr_mse_loss(_p(a), _p(b), _p(loss), _p(grad), gscale, a.numel(), _p(_partials(a.device)),
-                                    _stream()), 'mse_loss')
+                                    _stream()), 'mse_loss', 2)
 
 
 def bce_logits_loss(x, target, loss, grad, gscale):
     check(_lib.load().dasr_bce_logits_loss(_p(x), float(target), _p(loss), _p(grad), gscale, x.numel(),
-                                           _p(_partials(x.device)), _stream()), 'bce_logits_loss')
+                                           _p(_partials(x.device)), _stream()), 'bce_logits_loss', 2)
 
 
 def mean(x, out):
-    check(_lib.load().dasr_mean(_p(x), _p(out), x.numel(), _p(_partials(x.device)), _stream()), 'mean')
+    check(_lib.load().dasr_mean(_p(x), _p(out), x.numel(), _p(_partials(x.device)), _stream()), 'mean', 2)
