@@ -45,7 +45,8 @@ class ConvTcParams(C.Structure):
         ('beta2', C.c_float), ('res2_cs', C.c_int), ('res2_coff', C.c_int),
         ('mask_cs', C.c_int), ('mask_coff', C.c_int), ('mask_c0', C.c_int), ('mask_c1', C.c_int),
         ('mask_slope', C.c_float),
-        ('a_mode', C.c_int),
+        ('a_mode', C.c_int), ('epi_mode', C.c_int), ('act_cols', C.c_int),
+        ('pre_cs', C.c_int), ('pre_coff', C.c_int), ('out_nc', C.c_int),
     ]
 
 
@@ -58,7 +59,7 @@ SYMBOLS = {
     'dasr_conv2d_wgrad_f32_workspace': (_sz, [C.POINTER(ConvF32Params)]),
     'dasr_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),
     'dasr_pack_filter_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
+    'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
     'dasr_conv_tc_setup': (_i, [C.POINTER(ConvTcParams), _i]),
     'dasr_pack_filter_tc_bytes': (_sz, [_i, _i, _i]),
     'dasr_pack_filter_tc': (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -16,8 +16,9 @@
 //     lifetime of the persistent CTA ([tap][chunk][nt rows x 64 B], 64B-swizzled).
 //   * D: fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
 //     tile i+1.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/act/residual/mask -> bf16 NHWC stores).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + elected-lane MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> bias/pre/act/scale/residuals -> bf16 tile in swizzled shared
+// memory -> TMA store; pre-activation addend and residual tiles arrive by TMA as well).
 #include <cuda.h>
 #include "common.cuh"
 
@@ -29,7 +30,7 @@ constexpr int CHUNK = 32;                      // channels per K chunk (64 B row
 constexpr int ROW_B = CHUNK * 2;               // 64
 constexpr int A_HALO_BYTES = HALO_H * HALO_W * ROW_B;   // 11520
 constexpr int A_TAP_BYTES = TILE_H * TILE_W * ROW_B;    // 8192 (a_mode 1: one aligned tile per tap)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warpgroups)
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in max minus the kernel's 1 KB static allocation
 
@@ -166,7 +167,7 @@ struct TcKernelArgs {
   const __nv_bfloat16* res1;
   const __nv_bfloat16* res2;
   const __nv_bfloat16* mask_src;
-  __nv_bfloat16* out;
+  void* out;
   int nchunks;       // cin / 32
   int n_ntiles;      // cout / nt
   int tiles_x, tiles_y;
@@ -175,24 +176,62 @@ struct TcKernelArgs {
   int w_bytes;       // resident filter bytes of one CTA
   int a_stage_bytes; // bytes of one A stage
   int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
+  int epi_bytes;     // bytes of ONE staged epilogue tile: nt/32 blocks of 128 rows x 64 B
+  int has_pre, has_res1, has_res2;
 };
+
+// TMA store / bulk-group helpers (epilogue)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int EPI_BLK_BYTES = 128 * ROW_B;   // one 32-channel block of a staged tile: 128 pixels x 64 B, SWIZZLE_64B
+
+// 16 bf16 (two 16-byte chunks) of pixel row m, 16-column group g, inside a staged [blocks][128][64 B] tile
+__device__ __forceinline__ uint8_t* epi_addr(uint8_t* base, int m, int g, int half_chunk) {
+  const int blk = g >> 1;
+  const int c = ((g & 1) << 1) + half_chunk;
+  return base + blk * EPI_BLK_BYTES + m * ROW_B + ((c ^ ((m >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void fma_bf16x8(float* v, const uint4& u, float s) {
+  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float2 f = __bfloat1622float2(b2[j]);
+    v[2 * j] = fmaf(s, f.x, v[2 * j]);
+    v[2 * j + 1] = fmaf(s, f.y, v[2 * j + 1]);
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre,
+               const __grid_constant__ CUtensorMap tmap_res1, const __grid_constant__ CUtensorMap tmap_res2,
                const TcKernelArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [W resident][A stages][barriers]
+  // carve: [W resident][A stages][epilogue tiles: out/pre, res1, res2][barriers, bias]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + a.w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.stages * a.a_stage_bytes);
+  uint8_t* sR = sA + (size_t)a.stages * a.a_stage_bytes;          // output staging (and pre-activation addend, in place)
+  uint8_t* sR1 = sR + a.epi_bytes;
+  uint8_t* sR2 = sR1 + (a.has_res1 ? a.epi_bytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (a.has_res2 ? a.epi_bytes : 0));
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]
   uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;   // [2]
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
-  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 6);   // [nt] (16-byte aligned)
+  uint64_t* res_bar = bars + 2 * MAX_STAGES + 5;     // [1] pre / residual tiles landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 8);   // [nt] (16-byte aligned)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,19 +244,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
+    if (p.epi_mode == 0) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < a.stages; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(w_bar, 1);
+    mbar_init(res_bar, 1);
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, (uint32_t)a.tmem_cols);
-  for (int i = threadIdx.x; i < p.nt; i += TC_THREADS) sBias[i] = a.bias ? a.bias[(blockIdx.y % a.n_ntiles) * p.nt + i] : 0.f;
+  for (int i = threadIdx.x; i < nt; i += TC_THREADS) sBias[i] = a.bias ? a.bias[ntile * nt + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -263,7 +304,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the tcgen05.mma
     // instructions, so descriptors live in uniform registers and no per-lane serialisation is emitted.
     const uint32_t idesc = make_idesc_bf16(128, nt);
-    // descriptor pieces in 16-byte units (start-address field) + constant high words
     const uint32_t a_sbo = (p.a_mode == 0) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
     const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
     const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
@@ -314,12 +354,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       }
     }
   } else {
-    // =========================== epilogue warps (2..5) ===========================
+    // =========================== epilogue warps (2..9) ===========================
+    // Two warpgroups work on the SAME tile: warpgroup w takes the 16-column groups g with g % 2 == w.
+    // The epilogue is instruction-latency bound (one warp per scheduler), so: branch-free activation,
+    // the next TMEM load in flight while the current group is processed, staged tile -> one TMA store.
+    const int ew = warp - 2;                // 0..7
+    const int wg = ew >> 2;                 // warpgroup 0/1
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;            // accumulator row = tile pixel
     const int py = m >> 3, px = m & 7;
     const int co_base = ntile * nt;
     const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
+    const bool leader = (warp == 2) && (lane == 0);
+    const int nblk = nt >> 5;
+    const int ngroups = nt >> 4;
+    const bool has_loads = (p.epi_mode == 0) && (a.has_pre | a.has_res1 | a.has_res2);
+    const uint32_t load_bytes = (uint32_t)((a.has_pre + a.has_res1 + a.has_res2) * a.epi_bytes);
+    const int act = p.act;
+    const float slope = p.slope, alpha = p.alpha;
+    const bool scale = alpha != 1.f;
+    // swizzled offsets of this thread's row inside a staged 32-channel block: [g & 1][half]
+    const int sw = (m >> 1) & 3;
+    const int row_off = m * ROW_B;
+    uint32_t res_phase = 0;
     uint32_t it = 0;
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
@@ -328,87 +385,163 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       long r = tile / a.tiles_x;
       int ty = (int)(r % a.tiles_y);
       int n = (int)(r / a.tiles_y);
-      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      const int y = y0 + py, x = x0 + px;
       const bool valid = (y < p.H) && (x < p.W);
       const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
       const long opix = ((long)n * OH + oy) * OW + ox;
 
+      if (p.epi_mode == 0) {
+        // the staging tile may be overwritten only after the previous tile's TMA stores have read it
+        if (leader) bulk_wait_read0();
+        epi_bar_sync();
+        if (has_loads && leader) {
+          mbar_expect_tx(res_bar, load_bytes);
+          for (int b = 0; b < nblk; b++) {
+            const int cc = co_base + b * 32;
+            if (a.has_pre) tma_load_4d(sR + b * EPI_BLK_BYTES, &tmap_pre, res_bar, p.pre_coff + cc, x0, y0, n);
+            if (a.has_res1) tma_load_4d(sR1 + b * EPI_BLK_BYTES, &tmap_res1, res_bar, p.res1_coff + cc, x0, y0, n);
+            if (a.has_res2) tma_load_4d(sR2 + b * EPI_BLK_BYTES, &tmap_res2, res_bar, p.res2_coff + cc, x0, y0, n);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (has_loads) {
+        mbar_wait(res_bar, res_phase);
+        res_phase ^= 1;
+      }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-      for (int cg = 0; cg < nt; cg += 16) {
-        uint32_t rr[16];
-        tmem_ld16(t_addr + cg, rr);
+      uint32_t rr[16];
+      if (wg < ngroups) tmem_ld16(t_addr + wg * 16, rr);
+      for (int g = wg; g < ngroups; g += 2) {
+        const int cg = g << 4;
+        float v[16];
         tmem_ld_wait();
-        if (cg + 16 >= nt) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rr[j]);
+        if (g + 2 < ngroups) {
+          tmem_ld16(t_addr + cg + 32, rr);     // next group's accumulators fly while this one is processed
+        } else {
           // all TMEM reads of this warp for this tile are done: hand the accumulator back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (valid) {
-          const int co = co_base + cg;
-          float v[16];
+        const int co = co_base + cg;
+        const bool do_act = (act != DASR_ACT_NONE) && (co + 16 <= p.act_cols);
+        {
           const float4* bp = reinterpret_cast<const float4*>(sBias + cg);
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
             const float4 b4 = bp[j4];
-            v[4 * j4 + 0] = apply_act(__uint_as_float(rr[4 * j4 + 0]) + b4.x, p.act, p.slope) * p.alpha;
-            v[4 * j4 + 1] = apply_act(__uint_as_float(rr[4 * j4 + 1]) + b4.y, p.act, p.slope) * p.alpha;
-            v[4 * j4 + 2] = apply_act(__uint_as_float(rr[4 * j4 + 2]) + b4.z, p.act, p.slope) * p.alpha;
-            v[4 * j4 + 3] = apply_act(__uint_as_float(rr[4 * j4 + 3]) + b4.w, p.act, p.slope) * p.alpha;
+            v[4 * j4 + 0] += b4.x;
+            v[4 * j4 + 1] += b4.y;
+            v[4 * j4 + 2] += b4.z;
+            v[4 * j4 + 3] += b4.w;
           }
-          if (a.res1) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + opix * p.res1_cs + p.res1_coff + co);
-            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-            const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+        }
+        if (p.epi_mode == 0) {
+          const int blk_off = (g >> 1) * EPI_BLK_BYTES + row_off;
+          const int c0 = (g & 1) << 1;
+          const int o0 = blk_off + (((c0) ^ sw) << 4), o1 = blk_off + (((c0 + 1) ^ sw) << 4);
+          uint4* s0 = reinterpret_cast<uint4*>(sR + o0);
+          uint4* s1 = reinterpret_cast<uint4*>(sR + o1);
+          if (a.has_pre) {
+            fma_bf16x8(v, *s0, 1.f);
+            fma_bf16x8(v + 8, *s1, 1.f);
+          }
+          if (do_act) {
+            if (act == DASR_ACT_LRELU) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              float2 f = __bfloat1622float2(b0[j]);
-              v[2 * j] = fmaf(p.beta1, f.x, v[2 * j]);
-              v[2 * j + 1] = fmaf(p.beta1, f.y, v[2 * j + 1]);
-              float2 g = __bfloat1622float2(b1[j]);
-              v[8 + 2 * j] = fmaf(p.beta1, g.x, v[8 + 2 * j]);
-              v[8 + 2 * j + 1] = fmaf(p.beta1, g.y, v[8 + 2 * j + 1]);
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], v[j] * slope);     // 0 < slope < 1
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
             }
           }
-          if (a.res2) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + opix * p.res2_cs + p.res2_coff + co);
-            uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-            const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+          if (scale) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              float2 f = __bfloat1622float2(b0[j]);
-              v[2 * j] = fmaf(p.beta2, f.x, v[2 * j]);
-              v[2 * j + 1] = fmaf(p.beta2, f.y, v[2 * j + 1]);
-              float2 g = __bfloat1622float2(b1[j]);
-              v[8 + 2 * j] = fmaf(p.beta2, g.x, v[8 + 2 * j]);
-              v[8 + 2 * j + 1] = fmaf(p.beta2, g.y, v[8 + 2 * j + 1]);
-            }
+            for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
-          if (a.mask_src && co + 16 > p.mask_c0 && co < p.mask_c1) {
-            const __nv_bfloat16* mp = a.mask_src + opix * p.mask_cs + p.mask_coff + (co - p.mask_c0);
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              int cc = co + j;
-              if (cc >= p.mask_c0 && cc < p.mask_c1) {
-                float mv = __bfloat162float(mp[j]);
-                if (!(mv > 0.f)) v[j] *= p.mask_slope;
-              }
-            }
+          if (a.has_res1) {
+            fma_bf16x8(v, *reinterpret_cast<const uint4*>(sR1 + o0), p.beta1);
+            fma_bf16x8(v + 8, *reinterpret_cast<const uint4*>(sR1 + o1), p.beta1);
+          }
+          if (a.has_res2) {
+            fma_bf16x8(v, *reinterpret_cast<const uint4*>(sR2 + o0), p.beta2);
+            fma_bf16x8(v + 8, *reinterpret_cast<const uint4*>(sR2 + o1), p.beta2);
           }
           uint4 o[2];
           __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
           for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          uint4* op = reinterpret_cast<uint4*>(a.out + opix * p.out_cs + p.out_coff + co);
-          op[0] = o[0];
-          op[1] = o[1];
+          *s0 = o[0];
+          *s1 = o[1];
+        } else if (valid) {
+          if (do_act) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = (act == DASR_ACT_LRELU) ? fmaxf(v[j], v[j] * slope) : fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] *= alpha;
+          if (p.epi_mode == 2) {
+            // final layer: first out_nc channels straight to NCHW fp32 (the module boundary layout)
+            float* of = reinterpret_cast<float*>(a.out);
+            const long plane = (long)OH * OW;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (co + j < p.out_nc) of[((long)n * p.out_nc + co + j) * plane + (long)oy * OW + ox] = v[j];
+          } else {
+            __nv_bfloat16* ob16 = reinterpret_cast<__nv_bfloat16*>(a.out);
+            if (a.res1) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + opix * p.res1_cs + p.res1_coff + co);
+              fma_bf16x8(v, __ldg(rp), p.beta1);
+              fma_bf16x8(v + 8, __ldg(rp + 1), p.beta1);
+            }
+            if (a.res2) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + opix * p.res2_cs + p.res2_coff + co);
+              fma_bf16x8(v, __ldg(rp), p.beta2);
+              fma_bf16x8(v + 8, __ldg(rp + 1), p.beta2);
+            }
+            if (a.mask_src && co + 16 > p.mask_c0 && co < p.mask_c1) {
+              const __nv_bfloat16* mp = a.mask_src + opix * p.mask_cs + p.mask_coff + (co - p.mask_c0);
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                int cc = co + j;
+                if (cc >= p.mask_c0 && cc < p.mask_c1) {
+                  float mv = __bfloat162float(mp[j]);
+                  if (!(mv > 0.f)) v[j] *= p.mask_slope;
+                }
+              }
+            }
+            uint4 o[2];
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            uint4* op = reinterpret_cast<uint4*>(ob16 + opix * p.out_cs + p.out_coff + co);
+            op[0] = o[0];
+            op[1] = o[1];
+          }
+        }
+      }
+      if (wg >= ngroups) {
+        // this warpgroup had no column group in the tile (nt == 16): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (p.epi_mode == 0) {
+        fence_proxy_async();          // generic-proxy writes of the staged tile -> visible to the TMA engine
+        epi_bar_sync();
+        if (leader) {
+          for (int b = 0; b < nblk; b++)
+            tma_store_4d(&tmap_out, sR + b * EPI_BLK_BYTES, p.out_coff + co_base + b * 32, x0, y0, n);
+          bulk_commit();
         }
       }
     }
+    if (p.epi_mode == 0 && leader) bulk_wait0();   // all stores complete before the CTA (and its smem) goes away
   }
 
   tc_fence_before();
@@ -533,6 +666,50 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int sbo, int it
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA row-rate probe (selftest only): every CTA streams `iters` boxes of [rows x row_bytes] from / to a large
+// [npix x cs] bf16 tensor (pixel pitch cs*2 bytes), `depth` loads in flight.  Reports cycles per box.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64, 1) tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows_per_box,
+                                                         int box_bytes, int iters, int store, long npix, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar[4];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; i++) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nbox = (int)(npix / rows_per_box);
+    long long t0 = clock64();
+    if (!store) {
+      uint32_t ph[4] = {0, 0, 0, 0};
+      for (int i = 0; i < iters + 4; i++) {
+        int s = i & 3;
+        if (i >= 4) { mbar_wait(&bar[s], ph[s]); ph[s] ^= 1; }
+        if (i < iters) {
+          int b = (int)(((long)blockIdx.x * 7919 + (long)i * 104729) % nbox);
+          mbar_expect_tx(&bar[s], (uint32_t)box_bytes);
+          tma_load_2d(smem + s * 49152, &tm, &bar[s], 0, b * rows_per_box);
+        }
+      }
+    } else {
+      for (int i = 0; i < iters; i++) {
+        int b = (int)(((long)blockIdx.x * 7919 + (long)i * 104729) % nbox);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tm)), "r"(smem_u32(smem + (i & 3) * 49152)), "r"(0), "r"(b * rows_per_box)
+                     : "memory");
+        bulk_commit();
+        asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+      }
+      bulk_wait0();
+    }
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+}
+
 }  // namespace dasr
 
 using namespace dasr;
@@ -584,7 +761,23 @@ int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, vo
   return check_launch("pack_filter_tc");
 }
 
-int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* res1, const void* res2,
+static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int cs, int W, int H, int N,
+                          const char* what) {
+  cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+  cuuint32_t box[4] = {32, TILE_W, TILE_H, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+    return DASR_E_LAUNCH;
+  }
+  return DASR_OK;
+}
+
+int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
                  const void* mask_src, void* out, const DasrConvTcParams* p, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
@@ -592,11 +785,24 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc: input slice");
   DASR_REQUIRE(p->nt >= 16 && p->nt <= 256 && p->nt % 16 == 0 && p->cout % p->nt == 0, "conv_tc: nt=%d cout=%d",
                p->nt, p->cout);
-  DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc: output slice");
   DASR_REQUIRE(p->nvar >= 1 && p->nvar <= 4 && p->ntaps >= 1 && p->ntaps <= 9, "conv_tc: variants/taps");
   DASR_REQUIRE(p->out_mul == 1 || p->out_mul == 2, "conv_tc: out_mul");
+  DASR_REQUIRE(p->epi_mode >= 0 && p->epi_mode <= 2, "conv_tc: epi_mode");
+  DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc: act_cols must be a multiple of 16");
+  if (p->epi_mode == 2) {
+    DASR_REQUIRE(p->out_nc >= 1 && p->out_nc <= 16 && p->nt == p->cout && !res1 && !res2 && !pre && !mask_src,
+                 "conv_tc: NCHW-fp32 epilogue supports out_nc<=16, one Cout tile, no residuals");
+  } else {
+    DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc: output slice");
+  }
+  if (p->epi_mode == 0) {
+    DASR_REQUIRE(p->out_mul == 1 && p->nt % 32 == 0 && !mask_src, "conv_tc: staged epilogue needs out_mul=1, nt%%32==0, no mask");
+  } else {
+    DASR_REQUIRE(!pre, "conv_tc: the pre-activation addend is only supported by the staged epilogue (epi_mode 0)");
+  }
   if (res1) DASR_REQUIRE(p->res1_cs % 8 == 0 && p->res1_coff % 8 == 0, "conv_tc: res1 alignment");
   if (res2) DASR_REQUIRE(p->res2_cs % 8 == 0 && p->res2_coff % 8 == 0, "conv_tc: res2 alignment");
+  if (pre) DASR_REQUIRE(p->pre_cs % 8 == 0 && p->pre_coff % 8 == 0, "conv_tc: pre alignment");
   DASR_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                "conv_tc: pointers must be 16-byte aligned");
@@ -612,7 +818,7 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   a.res1 = (const __nv_bfloat16*)res1;
   a.res2 = (const __nv_bfloat16*)res2;
   a.mask_src = (const __nv_bfloat16*)mask_src;
-  a.out = (__nv_bfloat16*)out;
+  a.out = out;
   a.nchunks = p->cin / CHUNK;
   a.n_ntiles = p->cout / p->nt;
   a.tiles_x = cdiv(p->W, TILE_W);
@@ -621,20 +827,26 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   a.w_bytes = p->ntaps * a.nchunks * p->nt * ROW_B;
   a.a_stage_bytes = (p->a_mode == 0) ? ((A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
   a.tmem_cols = pow2_at_least(2 * p->nt);
-  const int bar_bytes = (2 * MAX_STAGES + 6) * 8 + 256 * 4 + 16;
-  int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - bar_bytes;
+  a.has_pre = (p->epi_mode == 0 && pre) ? 1 : 0;
+  a.has_res1 = (p->epi_mode == 0 && res1) ? 1 : 0;
+  a.has_res2 = (p->epi_mode == 0 && res2) ? 1 : 0;
+  a.epi_bytes = (p->epi_mode == 0) ? (p->nt / 32) * EPI_BLK_BYTES : 0;
+  const int epi_total = a.epi_bytes * (1 + a.has_res1 + a.has_res2);
+  const int bar_bytes = (2 * MAX_STAGES + 8) * 8 + 256 * 4 + 16;
+  int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
-    set_error("conv_tc: resident filters (%d B) + 2 A stages do not fit shared memory; use a smaller nt", a.w_bytes);
+    set_error("conv_tc: resident filters (%d B) + epilogue tiles (%d B) + 2 A stages do not fit shared memory; use a smaller nt",
+              a.w_bytes, epi_total);
     return DASR_E_SMEM;
   }
   a.stages = stages;
-  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + bar_bytes;
+  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + epi_total + bar_bytes;
   // one CTA per SM is assumed by the TMEM allocation (2 x nt columns): make sure two CTAs never co-reside
   if (smem < 120 * 1024) smem = 120 * 1024;
 
-  CUtensorMap tm_in, tm_w;
+  CUtensorMap tm_in, tm_w, tm_out, tm_pre, tm_r1, tm_r2;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2,
@@ -664,6 +876,14 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
       return DASR_E_LAUNCH;
     }
   }
+  tm_out = tm_in; tm_pre = tm_in; tm_r1 = tm_in; tm_r2 = tm_in;   // placeholders when unused
+  if (p->epi_mode == 0) {
+    int rc = encode_act_map(enc, &tm_out, out, p->out_cs, p->W, p->H, p->N, "output");
+    if (rc) return rc;
+    if (a.has_pre && (rc = encode_act_map(enc, &tm_pre, pre, p->pre_cs, p->W, p->H, p->N, "pre"))) return rc;
+    if (a.has_res1 && (rc = encode_act_map(enc, &tm_r1, res1, p->res1_cs, p->W, p->H, p->N, "res1"))) return rc;
+    if (a.has_res2 && (rc = encode_act_map(enc, &tm_r2, res2, p->res2_cs, p->W, p->H, p->N, "res2"))) return rc;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -679,10 +899,9 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* r
   if (gx < 1) gx = 1;
   if ((long)gx > a.ntiles) gx = (int)a.ntiles;
   dim3 grid(gx, gy);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, a);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, tm_pre, tm_r1, tm_r2, a);
   return check_launch("conv_tc");
 }
-
 
 // selftest-only probe (declared in selftest.cu, not in the public header)
 int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_per_mma) {
@@ -695,6 +914,37 @@ int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_pe
   cudaFree(d);
   if (e != cudaSuccess) { set_error("probe: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
   *cycles_per_mma = (double)h / ((double)iters * 18.0);
+  return DASR_OK;
+}
+
+
+int dasr_probe_tma_rate(int row_elems, int rows_per_box, int cs, int store, double* cycles_per_box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return DASR_E_NODRIVER;
+  const long npix = 1L << 20;
+  void* buf;
+  if (cudaMalloc(&buf, (size_t)npix * cs * 2) != cudaSuccess) return DASR_E_LAUNCH;
+  cudaMemset(buf, 0, (size_t)npix * cs * 2);
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {(cuuint64_t)cs, (cuuint64_t)npix};
+  cuuint64_t gstr[1] = {(cuuint64_t)cs * 2};
+  cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)rows_per_box};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = row_elems * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (row_elems * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cudaFree(buf); set_error("probe tma: encode %d", (int)r); return DASR_E_LAUNCH; }
+  long long* d;
+  cudaMalloc(&d, 8);
+  const int iters = 400;
+  cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  tma_rate_kernel<<<num_sms(), 64, 200 * 1024>>>(tm, rows_per_box, row_elems * 2 * rows_per_box, iters, store, npix, d);
+  long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaFree(buf);
+  if (e != cudaSuccess) { set_error("probe tma: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
+  *cycles_per_box = (double)h / iters;
   return DASR_OK;
 }
 

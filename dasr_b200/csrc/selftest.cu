@@ -22,6 +22,7 @@
   } while (0)
 
 extern "C" int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_per_mma);
+extern "C" int dasr_probe_tma_rate(int row_elems, int rows_per_box, int cs, int store, double* cycles_per_box);
 static unsigned long long rng_state = 0x1234567ULL;
 static inline unsigned rnd() {
   rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -169,7 +170,8 @@ static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
 }
 
 // tcgen05 conv vs CPU reference. kind 0 fprop, 1 dgrad, 2 upsample-fused
-static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, int a_mode, bool epi) {
+// epi: 0 none, 1 = act+res1+mask (direct-store epilogue), 2 = staged epilogue with pre + act_cols + res1 + res2, 3 = NCHW fp32 out
+static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, int a_mode, int epi) {
   char name[200];
   const int gk = (kind == 1) ? cout : cin;   // contraction channels
   const int gn = (kind == 1) ? cin : cout;   // produced channels
@@ -198,7 +200,9 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   for (auto& v : msk) v = rnd_q(8, 8.f);
   const float slope = 0.25f, alpha = 0.5f, beta1 = 2.f, mslope = 0.25f;
   const int mc0 = gn >= 32 ? gn - 24 : 0, mc1 = gn;
-  if (epi)
+  const int act_cols = (epi == 2) ? 16 * ((gn / 16 + 1) / 2) : gn;
+  const float beta2 = (gn > 96) ? 0.f : -0.5f;   // three staged tiles of a wide launch do not fit shared memory
+  if (epi == 1)
     for (size_t i = 0; i < ref.size(); i++) {
       double v = ref[i];
       v = v > 0 ? v : v * slope;
@@ -206,6 +210,13 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
       int c = (int)(i % gn);
       if (c >= mc0 && c < mc1 && !(msk[i] > 0.f)) v *= mslope;
       ref[i] = v;
+    }
+  if (epi == 2)
+    for (size_t i = 0; i < ref.size(); i++) {
+      int c = (int)(i % gn);
+      double v = ref[i] + msk[i];                 // msk doubles as the pre-activation addend
+      if (c < act_cols) v = v > 0 ? v : v * slope;
+      ref[i] = alpha * v + beta1 * res1[i] + beta2 * res1[(i + gn) % ref.size()];
     }
   auto in_b = to_bf16(in);
   auto res_b = to_bf16(res1);
@@ -223,30 +234,67 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   int rc = dasr_conv_tc_setup(&p, kind);
   p.N = N; p.H = H; p.W = W; p.cin = gk; p.in_cs = in_cs; p.in_coff = in_coff;
   p.cout = gn; p.out_cs = out_cs; p.out_coff = out_coff; p.nt = nt;
-  p.act = epi ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = epi ? alpha : 1.f;
+  p.act = (epi == 1 || epi == 2) ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = (epi == 1 || epi == 2) ? alpha : 1.f;
+  p.act_cols = act_cols;
   p.beta1 = beta1; p.res1_cs = gn; p.res1_coff = 0;
+  p.beta2 = beta2; p.res2_cs = gn; p.res2_coff = 0;
+  p.pre_cs = gn; p.pre_coff = 0;
   p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
   p.a_mode = a_mode;
+  p.epi_mode = (kind == 2 || epi == 1 || nt % 32) ? 1 : 0;
+  float* dnchw = nullptr;
+  if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
   rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
-  rc |= dasr_conv_tc(din, dwp, db, epi ? dres : nullptr, nullptr, epi ? dmsk : nullptr, dout, &p, 0);
+  // res2 for epi 2 = res1 shifted by one pixel (same buffer, pointer offset of gn elements, wraps at the end -> use a copy)
+  __nv_bfloat16* dres2 = nullptr;
+  if (epi == 2 && gn <= 96) {
+    std::vector<__nv_bfloat16> r2(res_b.size());
+    for (size_t i = 0; i < r2.size(); i++) r2[i] = res_b[(i + gn) % r2.size()];
+    dres2 = dalloc<__nv_bfloat16>(r2.size());
+    h2d(dres2, r2);
+  }
+  rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || epi == 2) ? dres : nullptr, dres2,
+                     epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
-  snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d", kind, a_mode, N, H, W, gk, gn, nt, (int)epi);
+  snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
+  if (rc == DASR_E_SMEM && e == cudaSuccess) {
+    printf("[SKIP] %s (does not fit shared memory in this A mode)\n", name);
+    return;
+  }
   if (rc || e != cudaSuccess) {
     printf("[FAIL] %s rc=%d err=%s cuda=%s\n", name, rc, dasr_last_error(), cudaGetErrorString(e));
     g_fail++;
     if (e != cudaSuccess) exit(3);
     return;
   }
-  auto got = d2h(dout, (size_t)N * OH * OW * out_cs);
   double me = 0, mref = 0;
-  for (size_t pix = 0; pix < (size_t)N * OH * OW; pix++)
-    for (int c = 0; c < gn; c++) {
-      double r = ref[pix * gn + c];
-      double g = __bfloat162float(got[pix * out_cs + out_coff + c]);
-      me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
-      mref = fmax(mref, fabs(r));
+  if (epi == 3) {
+    auto gotf = d2h(dnchw, (size_t)N * 3 * OH * OW);
+    for (int n = 0; n < N; n++)
+      for (int c = 0; c < 3; c++)
+        for (size_t pp = 0; pp < (size_t)OH * OW; pp++) {
+          double r = ref[((size_t)n * OH * OW + pp) * gn + c];
+          double g = gotf[((size_t)n * 3 + c) * OH * OW + pp];
+          me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
+        }
+    report(name, me, 1e-5);
+    cudaFree(dnchw);
+  } else {
+    auto got = d2h(dout, (size_t)N * OH * OW * out_cs);
+    // guard channels around the slice must be untouched (zero)
+    for (size_t pix = 0; pix < (size_t)N * OH * OW; pix++) {
+      for (int c = 0; c < out_coff; c++) me = fmax(me, fabs(__bfloat162float(got[pix * out_cs + c])));
+      for (int c = out_coff + gn; c < out_cs; c++) me = fmax(me, fabs(__bfloat162float(got[pix * out_cs + c])));
+      for (int c = 0; c < gn; c++) {
+        double r = ref[pix * gn + c];
+        double g = __bfloat162float(got[pix * out_cs + out_coff + c]);
+        me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
+        mref = fmax(mref, fabs(r));
+      }
     }
-  report(name, me, 8e-3);
+    report(name, me, 8e-3);
+  }
+  if (dres2) cudaFree(dres2);
   cudaFree(din); cudaFree(dres); cudaFree(dmsk); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
 }
 
@@ -266,11 +314,12 @@ static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, i
   dasr_conv_tc_setup(&p, kind);
   p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = in_cs; p.in_coff = 0;
   p.cout = cout; p.out_cs = in_cs; p.out_coff = (cout <= 128) ? 64 : 0; p.nt = nt;
-  p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.a_mode = a_mode;
+  p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.a_mode = a_mode; p.act_cols = cout;
+  p.epi_mode = (kind == 2 || nt % 32) ? 1 : 0;
   if (kind == 1) dasr_pack_filter_tc(dw, dwp, cin, cout, kind, 0);  // fwd conv had cout=K(cin here), cin=N(cout here)
   else dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
   int rc = 0;
-  for (int i = 0; i < 3; i++) rc |= dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
+  for (int i = 0; i < 3; i++) rc |= dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, nullptr, dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc || e != cudaSuccess) {
     printf("bench conv_tc cin%d cout%d nt%d kind%d amode%d: rc=%d %s cuda=%s\n", cin, cout, nt, kind, a_mode, rc,
@@ -281,7 +330,7 @@ static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, i
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; i++) dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
+  for (int i = 0; i < iters; i++) dasr_conv_tc(din, dwp, db, nullptr, nullptr, nullptr, nullptr, dout, &p, 0);
   cudaEventRecord(e1);
   CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -320,6 +369,18 @@ int main(int argc, char** argv) {
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "check")) do_check = true;
     if (!strcmp(argv[i], "bench")) do_bench = true;
+    if (!strcmp(argv[i], "tmarate")) {
+      for (int store = 0; store <= 1; store++)
+        for (int re : {32, 64, 128, 256})
+          for (int rows : {128, 16}) {
+            if ((long)re * 2 * rows > 49152) continue;
+            double c = 0;
+            int rc = dasr_probe_tma_rate(re, rows, 256, store, &c);
+            printf("tma_%s row=%4d B rows/box=%3d pitch=512 B : %8.1f cycles/box  %6.2f cycles/row  %6.2f B/clk/SM rc=%d\n",
+                   store ? "store" : "load ", re * 2, rows, c, c / rows, re * 2.0 * rows / c, rc);
+          }
+      return 0;
+    }
     if (!strcmp(argv[i], "mmarate")) {
       int ns[] = {16, 32, 48, 64, 96, 128, 160, 192, 256};
       for (int sbo : {512, 640})
@@ -353,15 +414,20 @@ int main(int argc, char** argv) {
     test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
     // tcgen05: validation path first (one aligned tile per tap), then shifted-descriptor halo path
     for (int am = 1; am >= 0; am--) {
-      test_tc(1, 16, 8, 32, 32, 32, 0, am, false);
-      test_tc(2, 32, 32, 64, 32, 32, 0, am, false);
-      test_tc(1, 20, 13, 96, 32, 32, 0, am, true);
-      test_tc(2, 32, 24, 192, 64, 32, 0, am, true);
-      test_tc(1, 32, 16, 64, 64, 64, 0, am, true);
-      test_tc(1, 24, 24, 160, 32, 160, 1, am, true);   // dgrad conv4-like: K=32 -> N=160
-      test_tc(1, 16, 16, 192, 64, 96, 1, am, false);   // dgrad conv5-like: K=64 -> N=192 split 2x96
-      test_tc(1, 16, 16, 64, 64, 64, 2, am, true);     // upsample-fused
-      test_tc(2, 19, 9, 64, 64, 32, 2, am, false);
+      test_tc(1, 16, 8, 32, 32, 32, 0, am, 0);
+      test_tc(2, 32, 32, 64, 32, 32, 0, am, 0);
+      test_tc(1, 20, 13, 96, 32, 32, 0, am, 1);
+      test_tc(2, 32, 24, 192, 64, 32, 0, am, 1);
+      test_tc(1, 32, 16, 64, 64, 64, 0, am, 1);
+      test_tc(1, 20, 13, 96, 32, 32, 0, am, 2);        // staged epilogue: pre + act_cols + res1 + res2, ragged tile
+      test_tc(2, 24, 16, 64, 64, 64, 0, am, 2);
+      test_tc(1, 40, 24, 32, 160, 160, 0, am, 2);      // fused dense-block launch shape: K=32 -> N=160
+      test_tc(1, 19, 11, 64, 192, 96, 0, am, 2);       // K=64 -> N=192 as 2 x 96
+      test_tc(1, 21, 10, 64, 16, 16, 0, am, 3);        // last layer: Cout padded to 16, NCHW fp32 out
+      test_tc(1, 24, 24, 160, 32, 160, 1, am, 1);      // dgrad conv4-like: K=32 -> N=160
+      test_tc(1, 16, 16, 192, 64, 96, 1, am, 0);       // dgrad conv5-like: K=64 -> N=192 split 2x96
+      test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
+      test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);
     }
   }
   if (do_bench) {

@@ -268,8 +268,40 @@ def _pad_vec(b, n):
     return o
 
 
-def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
-    """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between."""
+def _fused_rdb_filters(cache, params, L, r, nf):
+    """Dense-block N-fusion: launch j multiplies ONE input chunk (x for j=1, x_{j-1} otherwise) against the
+    filters of ALL convs k >= j that consume it, stacked along Cout.  Returns [(w_packed, bias)] for j=1..5."""
+    out = []
+    for j in range(1, 6):
+        lo, hi = (0, nf) if j == 1 else (nf + (j - 2) * GC, nf + (j - 1) * GC)
+        ks = list(range(j, 6))
+        wj = params[2 * L.rdb_conv(r, j)]
+
+        def make_w(lo=lo, hi=hi, ks=ks):
+            ws = [params[2 * L.rdb_conv(r, k)].detach()[:, lo:hi] for k in ks]
+            return ops.pack_filter_tc(torch.cat(ws, 0).float().contiguous(), TC_FPROP)
+
+        def make_b(j=j, ks=ks):
+            bj = params[2 * L.rdb_conv(r, j) + 1].detach().float()
+            n = sum(params[2 * L.rdb_conv(r, k)].shape[0] for k in ks)
+            b = torch.zeros(n, dtype=torch.float32, device=bj.device)
+            b[:bj.shape[0]] = bj          # the bias of conv j is added when conv j completes (this launch)
+            return b
+
+        out.append((cache.get(('fw', r, j), wj, make_w), cache.get(('fb', r, j), wj, make_b)))
+    return out
+
+
+def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
+    """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between.
+
+    fused=True : dense-block N-fusion.  Each RDB runs 5 launches; launch j reads one 32/64-channel chunk ONCE
+                 and produces conv j's output plus the partial sums of every later conv of the block
+                 (GEMM N = 192,160,128,96,64 instead of 32,32,32,32,64 — a tcgen05.mma of N<=96 costs the same
+                 ~72 cycles as N=32).  Partial sums live IN PLACE in the channel slots the finished activations
+                 will occupy (bf16), so the only extra state is a 64-channel slot for conv5.
+    fused=False: one launch per conv over the growing concat (the straightforward restatement).
+    """
     _need_cuda(x, 'RRDBNet')
     L = RRDBLayout(nb, params[0].shape[0], upscale)
     nf = L.nf
@@ -279,6 +311,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
     N, in_nc, H, W = x.shape
     bf = torch.bfloat16
     CS = nf + 4 * GC
+    BW = CS + (nf if fused else 0)        # fused: extra slot for conv5's partial sums
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -294,25 +327,36 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
     _mark('tc_begin')
     ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
     n_rdb = L.n_rdb
-    rot = [_empty((N, H, W, CS), x, bf) for _ in range(3)]
+    rot = [_empty((N, H, W, BW), x, bf) for _ in range(3)]
     bufs = [rot[i % 3] for i in range(n_rdb + 1)]
     ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
     for r in range(n_rdb):
         b = bufs[r]
-        for k in range(1, 5):
-            ci = L.rdb_conv(r, k)
-            ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
-        ci = L.rdb_conv(r, 5)
         dst = View(bufs[r + 1], nf, 0)
-        nt = _pick_nt(nf, CS)
-        if r % 3 == 2:
-            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=nt, alpha=0.04, res1=View(b, nf, 0), beta1=0.2,
-                        res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        if r % 3 == 2:      # (x5*0.2 + x)*0.2 + x_rrdb
+            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
         else:
-            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=nt, alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+            tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+        if fused:
+            fw = _fused_rdb_filters(cache, params, L, r, nf)
+            # launch 1: x -> x1 (complete) | partial conv2..5
+            ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2,
+                        act=ACT_LRELU, slope=0.2, act_cols=GC)
+            for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
+                o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
+                ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
+                            act_cols=GC, pre=o)
+            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+        else:
+            for k in range(1, 5):
+                ci = L.rdb_conv(r, k)
+                ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
+            ci = L.rdb_conv(r, 5)
+            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=_pick_nt(nf, CS), **tail)
     trunk = View(bufs[n_rdb], nf, 0)
     lr = _empty((N, H, W, nf), x, bf)
     ops.conv_tc(trunk, wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+    del rot, bufs
     cur, h, w = lr, H, W
     for u in range(L.n_up):
         h, w = 2 * h, 2 * w
@@ -325,11 +369,10 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None):
     ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2)
     del cur
     out_nc = Wt(L.i_hr1).shape[0]
-    o16 = _empty((N, h, w, 16), x, bf)                                  # Cout 3 -> one 16-wide UMMA N tile
-    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), o16, nt=16)
-    _mark('tc_end')
     out = _empty((N, out_nc, h, w), x)
-    ops.nhwc_to_nchw(View(o16, out_nc, 0), out)
+    # last layer: Cout 3 -> one 16-wide UMMA N tile, epilogue writes the 3 real channels straight to NCHW fp32
+    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), None, nchw_out=out, cout=16)
+    _mark('tc_end')
     return out
 
 

@@ -130,11 +130,17 @@ def pack_filter_tc(w, kind):
     return o
 
 
-def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0,
-            res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2, a_mode=0):
-    """tcgen05 3x3 conv on NHWC bf16 channel slices; `inp`/`out`/`res*`/`mask` are Views (or tensors)."""
-    inp, out = as_view(inp), as_view(out)
+def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0, act_cols=None,
+            pre=None, res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2,
+            a_mode=0, nchw_out=None, cout=None):
+    """tcgen05 3x3 conv on NHWC bf16 channel slices; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
+    v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
+    nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer)."""
+    inp = as_view(inp)
     N, H, W, _ = inp.t.shape
+    if nchw_out is not None:
+        return _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode)
+    out = as_view(out)
     p = ConvTcParams()
     lib = _lib.load()
     check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup', 0)
@@ -143,6 +149,11 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     p.cout, p.out_cs, p.out_coff = out.c, out.cs, out.coff
     p.nt = nt if nt else out.c
     p.act, p.slope, p.alpha = act, slope, alpha
+    p.act_cols = (out.c if act != ACT_NONE else 0) if act_cols is None else act_cols
+    p.epi_mode = 0 if (p.out_mul == 1 and p.nt % 32 == 0 and mask is None) else 1
+    if pre is not None:
+        pre = as_view(pre)
+        p.pre_cs, p.pre_coff = pre.cs, pre.coff
     if res1 is not None:
         res1 = as_view(res1)
         p.beta1, p.res1_cs, p.res1_coff = beta1, res1.cs, res1.coff
@@ -153,8 +164,22 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
         mask = as_view(mask)
         p.mask_cs, p.mask_coff, p.mask_c0, p.mask_c1, p.mask_slope = mask.cs, mask.coff, mask_c0, mask_c1, mask_slope
     p.a_mode = a_mode
-    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), res1.ptr if res1 else None, res2.ptr if res2 else None,
-                           mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
+    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
+                           res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
+
+
+def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):
+    N, H, W, _ = inp.t.shape
+    p = ConvTcParams()
+    lib = _lib.load()
+    check(lib.dasr_conv_tc_setup(C.byref(p), TC_FPROP), 'conv_tc_setup', 0)
+    p.N, p.H, p.W = N, H, W
+    p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
+    p.cout, p.out_cs, p.out_coff, p.nt = cout, cout, 0, cout
+    p.act, p.slope, p.alpha, p.act_cols = act, slope, alpha, (cout if act != ACT_NONE else 0)
+    p.epi_mode, p.out_nc, p.a_mode = 2, nchw_out.shape[1], a_mode
+    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), None, None, None, None, _p(nchw_out), C.byref(p), _stream()),
+          'conv_tc')
 
 
 # --------------------------------------------------------------------------------------------------

@@ -55,8 +55,9 @@ class RRDBNet(nn.Module):
         if need_grad:
             return engine.RRDBNetFunction.apply(x, self.nb, self.upscale, *params)
         prec = self.precision or _precision('bf16')
-        if prec == 'bf16':
-            return engine.rrdb_forward_bf16(x, params, self.nb, self.upscale, self._pack_cache)
+        if prec in ('bf16', 'bf16_layer'):
+            # 'bf16' = dense-block N-fused launches (default); 'bf16_layer' = one launch per conv
+            return engine.rrdb_forward_bf16(x, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
         out, _ = engine.rrdb_forward_f32(x, [p.detach() for p in params], self.nb, self.upscale, save=False)
         return out
 

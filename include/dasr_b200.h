@@ -92,7 +92,7 @@ int dasr_pack_filter_f32(const float* w_oihw, float* w_packed, int cout, int cin
  *       in chunks of 32 (cin % 32 == 0).
  * w   : packed by dasr_pack_filter_tc: [variant][tap][chunk][cout][32] bf16.
  * out : NHWC bf16; pixel (y,x) of variant v goes to (y*out_mul + py[v], x*out_mul + px[v]).
- * epilogue: v = alpha*act(acc + bias) + beta1*res1 + beta2*res2 ;
+ * epilogue: v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2 ;   (act on channels < act_cols only)
  *           channels [mask_c0,mask_c1) additionally multiplied by (mask_src>0 ? 1 : mask_slope)
  *           (LeakyReLU backward fused into the dgrad that completes a dense-block gradient slice).
  * One variant with the 9 taps of a 3x3 = plain conv.  Four variants with 2x2 taps and pre-summed
@@ -115,11 +115,18 @@ typedef struct {
   int mask_cs, mask_coff, mask_c0, mask_c1; float mask_slope;
   int a_mode;                  /* 0 = one halo tile per chunk + shifted UMMA descriptors (fast);
                                   1 = one aligned TMA tile per tap (validation path) */
+  int epi_mode;                /* 0 = staged: tile -> swizzled shared memory -> TMA store; pre/res tiles arrive by TMA
+                                  1 = direct bf16 NHWC stores (sub-pixel out_mul=2 variants, dgrad mask)
+                                  2 = direct NCHW fp32 store of the first out_nc channels (last layer) */
+  int act_cols;                /* only output channels [0, act_cols) of this launch get the activation
+                                  (dense-block fused launches finish one conv and extend partial sums of the others) */
+  int pre_cs, pre_coff;        /* pre-activation addend (bf16 NHWC): v = act(acc + bias + pre) */
+  int out_nc;                  /* epi_mode 2: real output channels */
 } DasrConvTcParams;
 
-int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias,
+int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
                  const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16,
-                 void* out_bf16, const DasrConvTcParams* p, void* stream);
+                 void* out /* bf16 NHWC, or fp32 NCHW in epi_mode 2 */, const DasrConvTcParams* p, void* stream);
 
 /* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
  *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)

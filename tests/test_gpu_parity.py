@@ -59,12 +59,13 @@ def test_rrdbnet_fp32_inference_vs_oracle(shape):
     assert rel_linf(out, ref) < FP32_TOL
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16_layer'])
 @pytest.mark.parametrize('shape', [(1, 3, 16, 8), (2, 3, 21, 13), (1, 3, 48, 40)])
-def test_rrdbnet_bf16_tcgen05_vs_oracle(shape):
+def test_rrdbnet_bf16_tcgen05_vs_oracle(shape, prec):
     nb = 2
     sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 103, 0.3)
     net = build_G(nb, sd).eval()
-    net.precision = 'bf16'
+    net.precision = prec
     x = O.synth_image(shape, 104)
     with torch.no_grad():
         out = net(x.cuda())
