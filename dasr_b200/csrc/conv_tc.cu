@@ -30,7 +30,7 @@ constexpr int CHUNK = 32;                      // channels per K chunk (64 B row
 constexpr int ROW_B = CHUNK * 2;               // 64
 constexpr int A_HALO_BYTES = HALO_H * HALO_W * ROW_B;   // 11520
 constexpr int A_TAP_BYTES = TILE_H * TILE_W * ROW_B;    // 8192 (a_mode 1: one aligned tile per tap)
-constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warpgroups)
+constexpr int TC_THREADS = 352;   // warp 0 A/B TMA, warp 1 MMA, warps 2..9 epilogue (two warpgroups), warp 10 epilogue TMA
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in max minus the kernel's 1 KB static allocation
 
@@ -161,6 +161,10 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+struct EpiMaps {          // TMA descriptors of the staged epilogue: [out, pre, res1, res2] x [64-channel box, 32-channel box]
+  CUtensorMap m[8];
+};
+
 struct TcKernelArgs {
   DasrConvTcParams p;
   const float* bias;
@@ -176,7 +180,7 @@ struct TcKernelArgs {
   int w_bytes;       // resident filter bytes of one CTA
   int a_stage_bytes; // bytes of one A stage
   int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
-  int epi_bytes;     // bytes of ONE staged epilogue tile: nt/32 blocks of 128 rows x 64 B
+  int epi_bytes;     // bytes of ONE staged epilogue tile: 128 pixels x nt channels bf16
   int has_pre, has_res1, has_res2;
 };
 
@@ -190,16 +194,25 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-constexpr int EPI_BLK_BYTES = 128 * ROW_B;   // one 32-channel block of a staged tile: 128 pixels x 64 B, SWIZZLE_64B
-
-// 16 bf16 (two 16-byte chunks) of pixel row m, 16-column group g, inside a staged [blocks][128][64 B] tile
-__device__ __forceinline__ uint8_t* epi_addr(uint8_t* base, int m, int g, int half_chunk) {
-  const int blk = g >> 1;
-  const int c = ((g & 1) << 1) + half_chunk;
-  return base + blk * EPI_BLK_BYTES + m * ROW_B + ((c ^ ((m >> 1) & 3)) << 4);
+// explicit shared-space 128-bit accesses with 32-bit addresses (generic pointers cost 64-bit address math + LD.E)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+constexpr int EPI_BLK64_BYTES = 128 * 128;   // 64-channel block of a staged tile: 128 pixels x 128 B, SWIZZLE_128B
+constexpr int EPI_BLK32_BYTES = 128 * 64;    // 32-channel tail block:            128 pixels x  64 B, SWIZZLE_64B
+
 __device__ __forceinline__ void fma_bf16x8(float* v, const uint4& u, float s) {
   const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -212,26 +225,26 @@ __device__ __forceinline__ void fma_bf16x8(float* v, const uint4& u, float s) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre,
-               const __grid_constant__ CUtensorMap tmap_res1, const __grid_constant__ CUtensorMap tmap_res2,
-               const TcKernelArgs a) {
+               const __grid_constant__ EpiMaps em, const TcKernelArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [W resident][A stages][epilogue tiles: out/pre, res1, res2][barriers, bias]
+  // carve: [W resident][A stages][staged tiles x2: out/pre][res1 x2][res2 x2][barriers, bias]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + a.w_bytes;
-  uint8_t* sR = sA + (size_t)a.stages * a.a_stage_bytes;          // output staging (and pre-activation addend, in place)
-  uint8_t* sR1 = sR + a.epi_bytes;
-  uint8_t* sR2 = sR1 + (a.has_res1 ? a.epi_bytes : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (a.has_res2 ? a.epi_bytes : 0));
-  uint64_t* full_bar = bars;                     // [stages]
-  uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]
-  uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]
-  uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;   // [2]
-  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;  // [2]
-  uint64_t* res_bar = bars + 2 * MAX_STAGES + 5;     // [1] pre / residual tiles landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
-  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 8);   // [nt] (16-byte aligned)
+  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;          // [2] output staging (and pre-activation addend, in place)
+  uint8_t* sR1 = sS + 2 * a.epi_bytes;                            // [2]
+  uint8_t* sR2 = sR1 + (a.has_res1 ? 2 * a.epi_bytes : 0);        // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (a.has_res2 ? 2 * a.epi_bytes : 0));
+  uint64_t* full_bar = bars;                     // [stages]  A chunk landed
+  uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]  A chunk consumed
+  uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]       resident filters landed
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;    // [2]  accumulator complete
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;   // [2]  accumulator drained
+  uint64_t* pre_bar = bars + 2 * MAX_STAGES + 5;      // [2]  pre / residual tiles landed in staging buffer b
+  uint64_t* sfull_bar = bars + 2 * MAX_STAGES + 7;    // [2]  staging buffer b holds a finished tile
+  uint64_t* sfree_bar = bars + 2 * MAX_STAGES + 9;    // [2]  staging buffer b has been read by its TMA stores
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 11);
+  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 12);   // [nt] (16-byte aligned)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,20 +253,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   const int nt = p.nt;
   const int ntaps = p.ntaps;
   const int acc_stride = a.tmem_cols >> 1;
+  const int nb64 = nt >> 6;                      // staged tile = nb64 blocks of 64 channels + (nt & 32) tail block
+  const bool tail32 = (nt & 32) != 0;
+  const bool has_loads = (p.epi_mode == 0) && (a.has_pre | a.has_res1 | a.has_res2);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
-    if (p.epi_mode == 0) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < a.stages; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(w_bar, 1);
-    mbar_init(res_bar, 1);
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
+      mbar_init(&pre_bar[b], 1);
+      mbar_init(&sfull_bar[b], 8);
+      mbar_init(&sfree_bar[b], 1);
     }
     fence_barrier_init();
   }
@@ -265,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (A halo tiles, resident filters) ===========================
     if (lane == 0) {
       // resident filters: rows [(var*ntaps + tap)*nchunks + c]*cout + ntile*nt .. +nt of the packed filter
       mbar_expect_tx(w_bar, (uint32_t)a.w_bytes);
@@ -353,11 +370,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp == 10) {
+    // =========================== epilogue TMA warp ===========================
+    // Feeds the staged epilogue: pre-activation / residual tiles in (two tiles ahead), finished tiles out.
+    if (p.epi_mode == 0 && lane == 0) {
+      const int co_base = p.out_coff + ntile * nt;
+      const uint32_t load_bytes = (uint32_t)((a.has_pre + a.has_res1 + a.has_res2) * a.epi_bytes);
+      auto tile_xyz = [&](long tile, int& x0, int& y0, int& n) {
+        int tx = (int)(tile % a.tiles_x);
+        long r = tile / a.tiles_x;
+        int ty = (int)(r % a.tiles_y);
+        n = (int)(r / a.tiles_y);
+        x0 = tx * TILE_W;
+        y0 = ty * TILE_H;
+      };
+      auto issue_loads = [&](long tile, int b) {
+        int x0, y0, n;
+        tile_xyz(tile, x0, y0, n);
+        mbar_expect_tx(&pre_bar[b], load_bytes);
+        const int cb = ntile * nt;
+        for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
+          const int wide = i < nb64;
+          const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
+          const int col = cb + (wide ? i * 64 : nb64 * 64);
+          if (a.has_pre) tma_load_4d(sS + b * a.epi_bytes + off, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
+          if (a.has_res1) tma_load_4d(sR1 + b * a.epi_bytes + off, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+          if (a.has_res2) tma_load_4d(sR2 + b * a.epi_bytes + off, &em.m[wide ? 6 : 7], &pre_bar[b], p.res2_coff + col, x0, y0, n);
+        }
+      };
+      const long G = gridDim.x;
+      if (has_loads) {
+        if ((long)blockIdx.x < a.ntiles) issue_loads(blockIdx.x, 0);
+        if ((long)blockIdx.x + G < a.ntiles) issue_loads(blockIdx.x + G, 1);
+      }
+      uint32_t it = 0;
+      for (long tile = blockIdx.x; tile < a.ntiles; tile += G, it++) {
+        const int b = it & 1;
+        int x0, y0, n;
+        tile_xyz(tile, x0, y0, n);
+        mbar_wait(&sfull_bar[b], (it >> 1) & 1);
+        for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
+          const int wide = i < nb64;
+          const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
+          tma_store_4d(&em.m[wide ? 0 : 1], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
+        }
+        bulk_commit();
+        bulk_wait_read0();                       // buffer b has been read by the stores
+        if (has_loads) {
+          if (tile + 2 * G < a.ntiles) issue_loads(tile + 2 * G, b);
+        } else {
+          mbar_arrive(&sfree_bar[b]);
+        }
+      }
+      bulk_wait0();                              // all stores complete before the CTA (and its smem) goes away
+    }
   } else {
     // =========================== epilogue warps (2..9) ===========================
     // Two warpgroups work on the SAME tile: warpgroup w takes the 16-column groups g with g % 2 == w.
     // The epilogue is instruction-latency bound (one warp per scheduler), so: branch-free activation,
-    // the next TMEM load in flight while the current group is processed, staged tile -> one TMA store.
+    // the next TMEM load in flight while the current group is processed, finished tile staged in swizzled
+    // shared memory and written by the TMA warp.
     const int ew = warp - 2;                // 0..7
     const int wg = ew >> 2;                 // warpgroup 0/1
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -365,18 +437,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int py = m >> 3, px = m & 7;
     const int co_base = ntile * nt;
     const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
-    const bool leader = (warp == 2) && (lane == 0);
-    const int nblk = nt >> 5;
     const int ngroups = nt >> 4;
-    const bool has_loads = (p.epi_mode == 0) && (a.has_pre | a.has_res1 | a.has_res2);
-    const uint32_t load_bytes = (uint32_t)((a.has_pre + a.has_res1 + a.has_res2) * a.epi_bytes);
     const int act = p.act;
     const float slope = p.slope, alpha = p.alpha;
     const bool scale = alpha != 1.f;
-    // swizzled offsets of this thread's row inside a staged 32-channel block: [g & 1][half]
-    const int sw = (m >> 1) & 3;
-    const int row_off = m * ROW_B;
-    uint32_t res_phase = 0;
+    const int sw64 = (m >> 1) & 3, sw128 = m & 7;
+    const uint32_t sS_u = smem_u32(sS), sR1_u = smem_u32(sR1), sR2_u = smem_u32(sR2), sBias_u = smem_u32(sBias);
+    const bool has_bias = a.bias != nullptr;
     uint32_t it = 0;
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
@@ -385,31 +452,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       long r = tile / a.tiles_x;
       int ty = (int)(r % a.tiles_y);
       int n = (int)(r / a.tiles_y);
-      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-      const int y = y0 + py, x = x0 + px;
+      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
       const bool valid = (y < p.H) && (x < p.W);
       const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
       const long opix = ((long)n * OH + oy) * OW + ox;
+      const uint32_t bS = sS_u + acc * a.epi_bytes, bR1 = sR1_u + acc * a.epi_bytes, bR2 = sR2_u + acc * a.epi_bytes;
 
-      if (p.epi_mode == 0) {
-        // the staging tile may be overwritten only after the previous tile's TMA stores have read it
-        if (leader) bulk_wait_read0();
-        epi_bar_sync();
-        if (has_loads && leader) {
-          mbar_expect_tx(res_bar, load_bytes);
-          for (int b = 0; b < nblk; b++) {
-            const int cc = co_base + b * 32;
-            if (a.has_pre) tma_load_4d(sR + b * EPI_BLK_BYTES, &tmap_pre, res_bar, p.pre_coff + cc, x0, y0, n);
-            if (a.has_res1) tma_load_4d(sR1 + b * EPI_BLK_BYTES, &tmap_res1, res_bar, p.res1_coff + cc, x0, y0, n);
-            if (a.has_res2) tma_load_4d(sR2 + b * EPI_BLK_BYTES, &tmap_res2, res_bar, p.res2_coff + cc, x0, y0, n);
-          }
-        }
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (has_loads) {
-        mbar_wait(res_bar, res_phase);
-        res_phase ^= 1;
+      if (p.epi_mode == 0) {
+        if (has_loads) mbar_wait(&pre_bar[acc], acc_phase);                  // pre / residual tiles of this tile landed
+        else if (it >= 2) mbar_wait(&sfree_bar[acc], ((it >> 1) - 1) & 1);   // stores of tile it-2 have read the buffer
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
       uint32_t rr[16];
@@ -430,11 +483,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         }
         const int co = co_base + cg;
         const bool do_act = (act != DASR_ACT_NONE) && (co + 16 <= p.act_cols);
-        {
-          const float4* bp = reinterpret_cast<const float4*>(sBias + cg);
+        if (has_bias) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
-            const float4 b4 = bp[j4];
+            const float4 b4 = lds128f(sBias_u + (cg + 4 * j4) * 4);
             v[4 * j4 + 0] += b4.x;
             v[4 * j4 + 1] += b4.y;
             v[4 * j4 + 2] += b4.z;
@@ -442,14 +494,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           }
         }
         if (p.epi_mode == 0) {
-          const int blk_off = (g >> 1) * EPI_BLK_BYTES + row_off;
-          const int c0 = (g & 1) << 1;
-          const int o0 = blk_off + (((c0) ^ sw) << 4), o1 = blk_off + (((c0 + 1) ^ sw) << 4);
-          uint4* s0 = reinterpret_cast<uint4*>(sR + o0);
-          uint4* s1 = reinterpret_cast<uint4*>(sR + o1);
+          int o0, o1;
+          if (cg < (nb64 << 6)) {             // inside a 64-channel block (128 B rows, SWIZZLE_128B)
+            const int base = (cg >> 6) * EPI_BLK64_BYTES + m * 128;
+            const int c0 = (cg & 63) >> 3;
+            o0 = base + ((c0 ^ sw128) << 4);
+            o1 = base + (((c0 + 1) ^ sw128) << 4);
+          } else {                            // 32-channel tail block (64 B rows, SWIZZLE_64B)
+            const int base = nb64 * EPI_BLK64_BYTES + m * 64;
+            const int c0 = (cg & 31) >> 3;
+            o0 = base + ((c0 ^ sw64) << 4);
+            o1 = base + (((c0 + 1) ^ sw64) << 4);
+          }
           if (a.has_pre) {
-            fma_bf16x8(v, *s0, 1.f);
-            fma_bf16x8(v + 8, *s1, 1.f);
+            fma_bf16x8(v, lds128(bS + o0), 1.f);
+            fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
           }
           if (do_act) {
             if (act == DASR_ACT_LRELU) {
@@ -465,19 +524,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
           if (a.has_res1) {
-            fma_bf16x8(v, *reinterpret_cast<const uint4*>(sR1 + o0), p.beta1);
-            fma_bf16x8(v + 8, *reinterpret_cast<const uint4*>(sR1 + o1), p.beta1);
+            fma_bf16x8(v, lds128(bR1 + o0), p.beta1);
+            fma_bf16x8(v + 8, lds128(bR1 + o1), p.beta1);
           }
           if (a.has_res2) {
-            fma_bf16x8(v, *reinterpret_cast<const uint4*>(sR2 + o0), p.beta2);
-            fma_bf16x8(v + 8, *reinterpret_cast<const uint4*>(sR2 + o1), p.beta2);
+            fma_bf16x8(v, lds128(bR2 + o0), p.beta2);
+            fma_bf16x8(v + 8, lds128(bR2 + o1), p.beta2);
           }
           uint4 o[2];
           __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
           for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          *s0 = o[0];
-          *s1 = o[1];
+          sts128(bS + o0, o[0]);
+          sts128(bS + o1, o[1]);
         } else if (valid) {
           if (do_act) {
 #pragma unroll
@@ -533,15 +592,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       }
       if (p.epi_mode == 0) {
         fence_proxy_async();          // generic-proxy writes of the staged tile -> visible to the TMA engine
-        epi_bar_sync();
-        if (leader) {
-          for (int b = 0; b < nblk; b++)
-            tma_store_4d(&tmap_out, sR + b * EPI_BLK_BYTES, p.out_coff + co_base + b * 32, x0, y0, n);
-          bulk_commit();
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull_bar[acc]);
       }
     }
-    if (p.epi_mode == 0 && leader) bulk_wait0();   // all stores complete before the CTA (and its smem) goes away
   }
 
   tc_fence_before();
@@ -762,14 +816,14 @@ int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, vo
 }
 
 static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int cs, int W, int H, int N,
-                          const char* what) {
+                          int width, const char* what) {
   cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstr[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
-  cuuint32_t box[4] = {32, TILE_W, TILE_H, 1};
+  cuuint32_t box[4] = {(cuuint32_t)width, TILE_W, TILE_H, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, width == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
     return DASR_E_LAUNCH;
@@ -830,9 +884,9 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   a.has_pre = (p->epi_mode == 0 && pre) ? 1 : 0;
   a.has_res1 = (p->epi_mode == 0 && res1) ? 1 : 0;
   a.has_res2 = (p->epi_mode == 0 && res2) ? 1 : 0;
-  a.epi_bytes = (p->epi_mode == 0) ? (p->nt / 32) * EPI_BLK_BYTES : 0;
-  const int epi_total = a.epi_bytes * (1 + a.has_res1 + a.has_res2);
-  const int bar_bytes = (2 * MAX_STAGES + 8) * 8 + 256 * 4 + 16;
+  a.epi_bytes = (p->epi_mode == 0) ? p->nt * 128 * 2 : 0;
+  const int epi_total = 2 * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
+  const int bar_bytes = (2 * MAX_STAGES + 12) * 8 + 256 * 4 + 16;
   int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -846,7 +900,8 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   // one CTA per SM is assumed by the TMEM allocation (2 x nt columns): make sure two CTAs never co-reside
   if (smem < 120 * 1024) smem = 120 * 1024;
 
-  CUtensorMap tm_in, tm_w, tm_out, tm_pre, tm_r1, tm_r2;
+  CUtensorMap tm_in, tm_w;
+  EpiMaps em;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2,
@@ -876,13 +931,18 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
       return DASR_E_LAUNCH;
     }
   }
-  tm_out = tm_in; tm_pre = tm_in; tm_r1 = tm_in; tm_r2 = tm_in;   // placeholders when unused
+  for (int i = 0; i < 8; i++) em.m[i] = tm_in;   // placeholders when unused
   if (p->epi_mode == 0) {
-    int rc = encode_act_map(enc, &tm_out, out, p->out_cs, p->W, p->H, p->N, "output");
-    if (rc) return rc;
-    if (a.has_pre && (rc = encode_act_map(enc, &tm_pre, pre, p->pre_cs, p->W, p->H, p->N, "pre"))) return rc;
-    if (a.has_res1 && (rc = encode_act_map(enc, &tm_r1, res1, p->res1_cs, p->W, p->H, p->N, "res1"))) return rc;
-    if (a.has_res2 && (rc = encode_act_map(enc, &tm_r2, res2, p->res2_cs, p->W, p->H, p->N, "res2"))) return rc;
+    const void* bases[4] = {out, pre, res1, res2};
+    const int css[4] = {p->out_cs, p->pre_cs, p->res1_cs, p->res2_cs};
+    const int used[4] = {1, a.has_pre, a.has_res1, a.has_res2};
+    const char* names[4] = {"output", "pre", "res1", "res2"};
+    for (int t = 0; t < 4; t++) {
+      if (!used[t]) continue;
+      int rc;
+      if (p->nt >= 64 && (rc = encode_act_map(enc, &em.m[2 * t], bases[t], css[t], p->W, p->H, p->N, 64, names[t]))) return rc;
+      if ((p->nt & 32) && (rc = encode_act_map(enc, &em.m[2 * t + 1], bases[t], css[t], p->W, p->H, p->N, 32, names[t]))) return rc;
+    }
   }
 
   static bool attr_set = false;
@@ -899,7 +959,7 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   if (gx < 1) gx = 1;
   if ((long)gx > a.ntiles) gx = (int)a.ntiles;
   dim3 grid(gx, gy);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, tm_pre, tm_r1, tm_r2, a);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, em, a);
   return check_launch("conv_tc");
 }
 

@@ -198,7 +198,8 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   std::vector<float> res1((size_t)N * OH * OW * gn), msk((size_t)N * OH * OW * gn);
   for (auto& v : res1) v = rnd_q(8, 8.f);
   for (auto& v : msk) v = rnd_q(8, 8.f);
-  const float slope = 0.25f, alpha = 0.5f, beta1 = 2.f, mslope = 0.25f;
+  const float slope = 0.25f, alpha = 0.5f, mslope = 0.25f;
+  const float beta1 = (epi == 2 && gn > 96) ? 0.f : 2.f;   // wide fused launches only carry the in-place pre addend
   const int mc0 = gn >= 32 ? gn - 24 : 0, mc1 = gn;
   const int act_cols = (epi == 2) ? 16 * ((gn / 16 + 1) / 2) : gn;
   const float beta2 = (gn > 96) ? 0.f : -0.5f;   // three staged tiles of a wide launch do not fit shared memory
@@ -253,7 +254,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     dres2 = dalloc<__nv_bfloat16>(r2.size());
     h2d(dres2, r2);
   }
-  rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || epi == 2) ? dres : nullptr, dres2,
+  rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
                      epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
@@ -342,6 +343,48 @@ static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, i
   cudaFree(din); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
 }
 
+// dense-block fused launch shape: one 32-channel chunk in, `cout` channels (finished conv + partial sums) out,
+// partial sums accumulated IN PLACE (pre == out), activation on the first 32 channels only.
+static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int with_pre, int iters) {
+  const int cs = 256;
+  size_t n = (size_t)N * H * W * cs;
+  __nv_bfloat16* buf = dalloc<__nv_bfloat16>(n);
+  std::vector<float> w((size_t)cout * cin * 9);
+  for (auto& v : w) v = rnd_q(4, 64.f);
+  float* dw = dalloc<float>(w.size());
+  h2d(dw, w);
+  void* dwp; CK(cudaMalloc(&dwp, dasr_pack_filter_tc_bytes(cout, cin, 0)));
+  DasrConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  dasr_conv_tc_setup(&p, 0);
+  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = cs; p.in_coff = 0;
+  p.cout = cout; p.out_cs = cs; p.out_coff = cs - cout; p.nt = nt;
+  p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.act_cols = 32; p.epi_mode = 0;
+  p.pre_cs = cs; p.pre_coff = cs - cout;
+  dasr_pack_filter_tc(dw, dwp, cout, cin, 0, 0);
+  void* pre = with_pre ? (void*)buf : nullptr;
+  int rc = 0;
+  for (int i = 0; i < 3; i++) rc |= dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, buf, &p, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc || e != cudaSuccess) {
+    printf("bench fused cin%d cout%d nt%d: rc=%d %s cuda=%s\n", cin, cout, nt, rc, dasr_last_error(), cudaGetErrorString(e));
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; i++) dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, buf, &p, 0);
+  cudaEventRecord(e1);
+  CK(cudaEventSynchronize(e1));
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  double tiles_per_sm = (double)N * (H / 16) * (W / 8) / 148.0 * (cout / nt);
+  printf("bench fused  %dx%dx%d K%-3d N%-3d nt%-3d pre%d : %8.3f ms  %7.1f TFLOP/s  %6.2f us/tile\n", N, H, W, cin, cout, nt,
+         with_pre, ms, 2.0 * N * H * W * cin * cout * 9 / ms * 1e-9, ms * 1e3 / tiles_per_sm);
+  cudaFree(buf); cudaFree(dw); cudaFree(dwp);
+}
+
 static void bench_f32(int N, int H, int W, int cin, int cout, int iters) {
   size_t in_n = (size_t)N * H * W * cin, out_n = (size_t)N * H * W * cout;
   float *din = dalloc<float>(in_n), *dout = dalloc<float>(out_n), *dw = dalloc<float>((size_t)9 * cin * cout), *db = dalloc<float>(cout);
@@ -389,6 +432,15 @@ int main(int argc, char** argv) {
           int rc = dasr_probe_mma_rate(n, sbo, 200, 64, &c);
           printf("mma_rate M128 N%-3d K16 sbo%d : %7.1f cycles/MMA  (ideal N/2=%d) rc=%d\n", n, sbo, c, n / 2, rc);
         }
+      return 0;
+    }
+    if (!strcmp(argv[i], "fused")) {
+      bench_tc_fused(16, 256, 256, 64, 192, 96, 0, 10);
+      bench_tc_fused(16, 256, 256, 32, 160, 160, 1, 10);
+      bench_tc_fused(16, 256, 256, 32, 160, 160, 0, 10);
+      bench_tc_fused(16, 256, 256, 32, 128, 128, 1, 10);
+      bench_tc_fused(16, 256, 256, 32, 96, 96, 1, 10);
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 1, 10);
       return 0;
     }
     if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes

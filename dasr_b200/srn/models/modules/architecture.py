@@ -21,6 +21,35 @@ def _precision(module_default):
     return os.environ.get('DASR_B200_PRECISION', module_default)
 
 
+class _GraphedForward:
+    """One inference forward captured into a CUDA graph (the tcgen05 path launches ~350-2800 small kernels per
+    forward; replaying a graph removes the per-launch host cost).  Inputs are copied into a static buffer; the
+    result is returned as a fresh tensor."""
+
+    def __init__(self, fn, x):
+        self.x = x.detach().clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn(self.x)                       # warm-up: builds the cached kernel-layout filters, sets func attributes
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from dasr_b200 import _lib
+        l0 = _lib.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(self.x)
+        self.launches = _lib.LAUNCHES - l0      # kernels of ours inside one replay
+
+    def __call__(self, x):
+        from dasr_b200 import _lib
+        self.x.copy_(x)
+        self.graph.replay()
+        _lib.LAUNCHES += self.launches
+        return self.out.clone()
+
+
 class RRDBNet(nn.Module):
     def __init__(self, in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None,
                  act_type='leakyrelu', mode='CNA', upsample_mode='upconv'):
@@ -48,6 +77,7 @@ class RRDBNet(nn.Module):
         self.nb, self.nf, self.upscale = nb, nf, upscale
         self.precision = None          # None: fp32 when grad is needed, DASR_B200_PRECISION / bf16 otherwise
         self._pack_cache = engine._PackCache()
+        self._graphs = {}
 
     def forward(self, x):
         params = list(self.parameters())
@@ -57,7 +87,16 @@ class RRDBNet(nn.Module):
         prec = self.precision or _precision('bf16')
         if prec in ('bf16', 'bf16_layer'):
             # 'bf16' = dense-block N-fused launches (default); 'bf16_layer' = one launch per conv
-            return engine.rrdb_forward_bf16(x, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
+            fn = lambda t: engine.rrdb_forward_bf16(t, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
+            if os.environ.get('DASR_B200_GRAPH', '1') == '0' or not x.is_cuda or engine.PROFILE is not None:
+                return fn(x)
+            key = (tuple(x.shape), x.dtype, x.device.index, prec, sum(p._version for p in params), id(params[0]))
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 2:        # each graph pins its activation pool: keep at most two shapes
+                    self._graphs.clear()
+                g = self._graphs[key] = _GraphedForward(fn, x.contiguous().float())
+            return g(x)
         out, _ = engine.rrdb_forward_f32(x, [p.detach() for p in params], self.nb, self.upscale, save=False)
         return out
 
