@@ -46,8 +46,13 @@ class ConvTcParams(C.Structure):
         ('mask_cs', C.c_int), ('mask_coff', C.c_int), ('mask_c0', C.c_int), ('mask_c1', C.c_int),
         ('mask_slope', C.c_float),
         ('a_mode', C.c_int), ('epi_mode', C.c_int), ('act_cols', C.c_int),
-        ('pre_cs', C.c_int), ('pre_coff', C.c_int), ('out_nc', C.c_int),
+        ('pre_cs', C.c_int), ('pre_coff', C.c_int), ('out_nc', C.c_int), ('tile_rev', C.c_int),
     ]
+
+
+class PipeArgs(C.Structure):
+    _fields_ = [('grid_x', C.c_int), ('dep0', C.c_void_p), ('dep0_g', C.c_int), ('dep1', C.c_void_p), ('dep1_g', C.c_int),
+                ('progress', C.c_void_p)]
 
 
 # every symbol include/dasr_b200.h declares: name -> (restype, argtypes)
@@ -60,6 +65,7 @@ SYMBOLS = {
     'dasr_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),
     'dasr_pack_filter_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
+    'dasr_conv_tc_pipe': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), C.POINTER(PipeArgs), _vp]),
     'dasr_conv_tc_setup': (_i, [C.POINTER(ConvTcParams), _i]),
     'dasr_pack_filter_tc_bytes': (_sz, [_i, _i, _i]),
     'dasr_pack_filter_tc': (_i, [_vp, _vp, _i, _i, _i, _vp]),

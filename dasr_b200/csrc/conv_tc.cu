@@ -182,6 +182,14 @@ struct TcKernelArgs {
   int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
   int epi_bytes;     // bytes of ONE staged epilogue tile: 128 pixels x nt channels bf16
   int has_pre, has_res1, has_res2;
+  // cross-launch spatial pipelining (dense-block stages run CONCURRENTLY on disjoint SM subsets):
+  //   dep{0,1}[k] = tiles finished by CTA k of a producer launch with dep_g CTAs (same tile order as this launch);
+  //   a tile (and its pre/residual tiles) may be loaded once every producer tile up to the end of the NEXT tile row
+  //   is finished; progress[blockIdx.x] = tiles of this launch whose stores are complete.
+  const int* dep0;
+  const int* dep1;
+  int dep0_g, dep1_g;
+  int* progress;
 };
 
 // TMA store / bulk-group helpers (epilogue)
@@ -194,6 +202,30 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Warp-wide: wait until every CTA k < g of a producer launch has finished all of its tiles with raster index <= tmax
+// (CTA k owns tiles k, k+g, k+2g, ...).  Progress is monotone, so a satisfied bound never has to be re-checked.
+__device__ __forceinline__ void wait_producer(const int* prog, int g, long tmax, int lane) {
+  if (prog == nullptr) return;
+  for (int base = 0; base < g; base += 32) {
+    const int k = base + lane;
+    const int need = (k < g && tmax >= k) ? (int)((tmax - k) / g) + 1 : 0;
+    while (true) {
+      const int v = (k < g) ? ld_acquire_gpu(prog + k) : 0x7fffffff;
+      if (__all_sync(0xffffffffu, v >= need)) break;
+      __nanosleep(100);
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> subsequent TMA (async proxy) reads
+}
 
 // explicit shared-space 128-bit accesses with 32-bit addresses (generic pointers cost 64-bit address math + LD.E)
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -223,6 +255,9 @@ __device__ __forceinline__ void fma_bf16x8(float* v, const uint4& u, float s) {
   }
 }
 
+// EPI_MODE / HAS_PRE / NRES are compile-time so that each instantiation carries only its own epilogue code
+// (the all-in-one kernel spread the per-group loop over ~32 KB of SASS and stalled on instruction fetch).
+template <int EPI_MODE, bool HAS_PRE, int NRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ EpiMaps em, const TcKernelArgs a) {
@@ -233,8 +268,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint8_t* sA = smem + a.w_bytes;
   uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;          // [2] output staging (and pre-activation addend, in place)
   uint8_t* sR1 = sS + 2 * a.epi_bytes;                            // [2]
-  uint8_t* sR2 = sR1 + (a.has_res1 ? 2 * a.epi_bytes : 0);        // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (a.has_res2 ? 2 * a.epi_bytes : 0));
+  uint8_t* sR2 = sR1 + (NRES >= 1 ? 2 * a.epi_bytes : 0);        // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (NRES >= 2 ? 2 * a.epi_bytes : 0));
   uint64_t* full_bar = bars;                     // [stages]  A chunk landed
   uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]  A chunk consumed
   uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]       resident filters landed
@@ -255,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   const int acc_stride = a.tmem_cols >> 1;
   const int nb64 = nt >> 6;                      // staged tile = nb64 blocks of 64 channels + (nt & 32) tail block
   const bool tail32 = (nt & 32) != 0;
-  const bool has_loads = (p.epi_mode == 0) && (a.has_pre | a.has_res1 | a.has_res2);
+  const bool has_loads = (EPI_MODE == 0) && (HAS_PRE || NRES > 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -292,14 +327,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           int row = ((var * ntaps + tap) * a.nchunks + c) * p.cout + ntile * nt;
           tma_load_2d(sW + (size_t)slot * nt * ROW_B, &tmap_w, w_bar, 0, row);
         }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        int tx = (int)(tile % a.tiles_x);
-        long r = tile / a.tiles_x;
-        int ty = (int)(r % a.tiles_y);
-        int n = (int)(r / a.tiles_y);
-        int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    long dep_ok = -1;                    // largest raster index already known to be finished by the producers
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
+      int tx = (int)(te % a.tiles_x);
+      long r = te / a.tiles_x;
+      int ty = (int)(r % a.tiles_y);
+      int n = (int)(r / a.tiles_y);
+      int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      if (a.dep0 != nullptr) {
+        long tmax = tile - tx + 2L * a.tiles_x - 1;          // halo: through the end of the next tile row
+        if (tmax > a.ntiles - 1) tmax = a.ntiles - 1;
+        if (tmax > dep_ok) {
+          wait_producer(a.dep0, a.dep0_g, tmax, lane);
+          wait_producer(a.dep1, a.dep1_g, tmax, lane);
+          dep_ok = tmax;
+        }
+      }
+      if (lane == 0) {
         for (int c = 0; c < a.nchunks; c++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* dst = sA + (size_t)stage * a.a_stage_bytes;
@@ -315,6 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -372,31 +421,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else if (warp == 10) {
     // =========================== epilogue TMA warp ===========================
-    // Feeds the staged epilogue: pre-activation / residual tiles in (two tiles ahead), finished tiles out.
-    if (p.epi_mode == 0 && lane == 0) {
+    // Feeds the staged epilogue: pre-activation / residual tiles in (two tiles ahead), finished tiles out;
+    // publishes per-CTA progress for consumer launches that run concurrently on other SMs.
+    if constexpr (EPI_MODE == 0) {
       const int co_base = p.out_coff + ntile * nt;
-      const uint32_t load_bytes = (uint32_t)((a.has_pre + a.has_res1 + a.has_res2) * a.epi_bytes);
+      const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * a.epi_bytes);
+      long dep_ok = -1;
       auto tile_xyz = [&](long tile, int& x0, int& y0, int& n) {
-        int tx = (int)(tile % a.tiles_x);
-        long r = tile / a.tiles_x;
+        const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
+        int tx = (int)(te % a.tiles_x);
+        long r = te / a.tiles_x;
         int ty = (int)(r % a.tiles_y);
         n = (int)(r / a.tiles_y);
         x0 = tx * TILE_W;
         y0 = ty * TILE_H;
       };
-      auto issue_loads = [&](long tile, int b) {
+      auto issue_loads = [&](long tile, int b) {      // whole warp: dependency wait, then lane 0 issues
         int x0, y0, n;
         tile_xyz(tile, x0, y0, n);
-        mbar_expect_tx(&pre_bar[b], load_bytes);
-        const int cb = ntile * nt;
-        for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
-          const int wide = i < nb64;
-          const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
-          const int col = cb + (wide ? i * 64 : nb64 * 64);
-          if (a.has_pre) tma_load_4d(sS + b * a.epi_bytes + off, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
-          if (a.has_res1) tma_load_4d(sR1 + b * a.epi_bytes + off, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
-          if (a.has_res2) tma_load_4d(sR2 + b * a.epi_bytes + off, &em.m[wide ? 6 : 7], &pre_bar[b], p.res2_coff + col, x0, y0, n);
+        if (a.dep0 != nullptr && tile > dep_ok) {     // pre/residual tiles have no halo: the tile itself suffices
+          wait_producer(a.dep0, a.dep0_g, tile, lane);
+          wait_producer(a.dep1, a.dep1_g, tile, lane);
+          dep_ok = tile;
         }
+        if (lane == 0) {
+          mbar_expect_tx(&pre_bar[b], load_bytes);
+          const int cb = ntile * nt;
+          for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
+            const int wide = i < nb64;
+            const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
+            const int col = cb + (wide ? i * 64 : nb64 * 64);
+            if constexpr (HAS_PRE) tma_load_4d(sS + b * a.epi_bytes + off, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
+            if constexpr (NRES >= 1) tma_load_4d(sR1 + b * a.epi_bytes + off, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+            if constexpr (NRES >= 2) tma_load_4d(sR2 + b * a.epi_bytes + off, &em.m[wide ? 6 : 7], &pre_bar[b], p.res2_coff + col, x0, y0, n);
+          }
+        }
+        __syncwarp();
       };
       const long G = gridDim.x;
       if (has_loads) {
@@ -406,23 +466,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       uint32_t it = 0;
       for (long tile = blockIdx.x; tile < a.ntiles; tile += G, it++) {
         const int b = it & 1;
-        int x0, y0, n;
-        tile_xyz(tile, x0, y0, n);
-        mbar_wait(&sfull_bar[b], (it >> 1) & 1);
-        for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
-          const int wide = i < nb64;
-          const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
-          tma_store_4d(&em.m[wide ? 0 : 1], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
+        if (lane == 0) {
+          int x0, y0, n;
+          tile_xyz(tile, x0, y0, n);
+          mbar_wait(&sfull_bar[b], (it >> 1) & 1);
+          for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
+            const int wide = i < nb64;
+            const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
+            tma_store_4d(&em.m[wide ? 0 : 1], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
+          }
+          bulk_commit();
+          bulk_wait_read0();                       // buffer b has been read by the stores
+          if (a.progress != nullptr && it > 0) {
+            // publish with one store group still in flight: everything up to the PREVIOUS tile is complete
+            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            __threadfence();
+            st_release_gpu(a.progress + blockIdx.x, (int)it);
+          }
+          if (!has_loads) mbar_arrive(&sfree_bar[b]);
         }
-        bulk_commit();
-        bulk_wait_read0();                       // buffer b has been read by the stores
-        if (has_loads) {
-          if (tile + 2 * G < a.ntiles) issue_loads(tile + 2 * G, b);
-        } else {
-          mbar_arrive(&sfree_bar[b]);
+        __syncwarp();
+        if (has_loads && tile + 2 * G < a.ntiles) issue_loads(tile + 2 * G, b);
+      }
+      if (lane == 0) {
+        bulk_wait0();                              // all stores complete before the CTA (and its smem) goes away
+        if (a.progress != nullptr && it > 0) {
+          __threadfence();
+          st_release_gpu(a.progress + blockIdx.x, (int)it);
         }
       }
-      bulk_wait0();                              // all stores complete before the CTA (and its smem) goes away
     }
   } else {
     // =========================== epilogue warps (2..9) ===========================
@@ -448,8 +520,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int tx = (int)(tile % a.tiles_x);
-      long r = tile / a.tiles_x;
+      const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
+      int tx = (int)(te % a.tiles_x);
+      long r = te / a.tiles_x;
       int ty = (int)(r % a.tiles_y);
       int n = (int)(r / a.tiles_y);
       const int y = ty * TILE_H + py, x = tx * TILE_W + px;
@@ -460,29 +533,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (p.epi_mode == 0) {
+      if constexpr (EPI_MODE == 0) {
         if (has_loads) mbar_wait(&pre_bar[acc], acc_phase);                  // pre / residual tiles of this tile landed
         else if (it >= 2) mbar_wait(&sfree_bar[acc], ((it >> 1) - 1) & 1);   // stores of tile it-2 have read the buffer
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-      uint32_t rr[16];
-      if (wg < ngroups) tmem_ld16(t_addr + wg * 16, rr);
-      for (int g = wg; g < ngroups; g += 2) {
+      // One 16-column group: registers -> (+bias, +pre) -> act -> scale -> (+residuals) -> bf16 -> staged tile / global.
+      auto process = [&](const uint32_t* rr, int g) {
         const int cg = g << 4;
-        float v[16];
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rr[j]);
-        if (g + 2 < ngroups) {
-          tmem_ld16(t_addr + cg + 32, rr);     // next group's accumulators fly while this one is processed
-        } else {
-          // all TMEM reads of this warp for this tile are done: hand the accumulator back early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
         const int co = co_base + cg;
         const bool do_act = (act != DASR_ACT_NONE) && (co + 16 <= p.act_cols);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rr[j]);
         if (has_bias) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; j4++) {
@@ -493,7 +556,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             v[4 * j4 + 3] += b4.w;
           }
         }
-        if (p.epi_mode == 0) {
+        if constexpr (EPI_MODE == 0) {
           int o0, o1;
           if (cg < (nb64 << 6)) {             // inside a 64-channel block (128 B rows, SWIZZLE_128B)
             const int base = (cg >> 6) * EPI_BLK64_BYTES + m * 128;
@@ -506,7 +569,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             o0 = base + ((c0 ^ sw64) << 4);
             o1 = base + (((c0 + 1) ^ sw64) << 4);
           }
-          if (a.has_pre) {
+          if constexpr (HAS_PRE) {
             fma_bf16x8(v, lds128(bS + o0), 1.f);
             fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
           }
@@ -523,11 +586,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
-          if (a.has_res1) {
+          if constexpr (NRES >= 1) {
             fma_bf16x8(v, lds128(bR1 + o0), p.beta1);
             fma_bf16x8(v + 8, lds128(bR1 + o1), p.beta1);
           }
-          if (a.has_res2) {
+          if constexpr (NRES >= 2) {
             fma_bf16x8(v, lds128(bR2 + o0), p.beta2);
             fma_bf16x8(v + 8, lds128(bR2 + o1), p.beta2);
           }
@@ -544,7 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           }
 #pragma unroll
           for (int j = 0; j < 16; j++) v[j] *= alpha;
-          if (p.epi_mode == 2) {
+          if constexpr (EPI_MODE == 2) {
             // final layer: first out_nc channels straight to NCHW fp32 (the module boundary layout)
             float* of = reinterpret_cast<float*>(a.out);
             const long plane = (long)OH * OW;
@@ -583,6 +646,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             op[1] = o[1];
           }
         }
+      };
+      auto release_acc = [&]() {
+        // all TMEM reads of this warp for this tile are done: hand the accumulator back early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      };
+      // two register sets: the next group's accumulators are in flight while the current group is processed
+      uint32_t ra[16], rb[16];
+      if (wg < ngroups) tmem_ld16(t_addr + wg * 16, ra);
+      for (int g = wg; g < ngroups; g += 4) {
+        tmem_ld_wait();
+        if (g + 2 < ngroups) tmem_ld16(t_addr + (g + 2) * 16, rb); else release_acc();
+        process(ra, g);
+        if (g + 2 < ngroups) {
+          tmem_ld_wait();
+          if (g + 4 < ngroups) tmem_ld16(t_addr + (g + 4) * 16, ra); else release_acc();
+          process(rb, g + 2);
+        }
       }
       if (wg >= ngroups) {
         // this warpgroup had no column group in the tile (nt == 16): still release the accumulator
@@ -590,7 +672,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      if (p.epi_mode == 0) {
+      if constexpr (EPI_MODE == 0) {
         fence_proxy_async();          // generic-proxy writes of the staged tile -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) mbar_arrive(&sfull_bar[acc]);
@@ -831,8 +913,18 @@ static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base
   return DASR_OK;
 }
 
+int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const void* pre, const void* res1,
+                      const void* res2, const void* mask_src, void* out, const DasrConvTcParams* p,
+                      const DasrPipeArgs* pipe, void* stream);
+
 int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
                  const void* mask_src, void* out, const DasrConvTcParams* p, void* stream) {
+  return dasr_conv_tc_pipe(in, w, bias, pre, res1, res2, mask_src, out, p, nullptr, stream);
+}
+
+int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const void* pre, const void* res1,
+                      const void* res2, const void* mask_src, void* out, const DasrConvTcParams* p,
+                      const DasrPipeArgs* pipe, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc: cin must be a multiple of 32 (got %d)", p->cin);
@@ -885,6 +977,16 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   a.has_res1 = (p->epi_mode == 0 && res1) ? 1 : 0;
   a.has_res2 = (p->epi_mode == 0 && res2) ? 1 : 0;
   a.epi_bytes = (p->epi_mode == 0) ? p->nt * 128 * 2 : 0;
+  a.dep0 = a.dep1 = nullptr;
+  a.dep0_g = a.dep1_g = 0;
+  a.progress = nullptr;
+  if (pipe) {
+    DASR_REQUIRE(p->epi_mode == 0 && p->nvar == 1 && p->nt == p->cout && !p->tile_rev, "conv_tc: pipelined launches need the staged epilogue, one Cout tile, forward tile order");
+    DASR_REQUIRE(pipe->grid_x >= 1 && pipe->dep0_g >= 0 && pipe->dep1_g >= 0 && (pipe->dep0 || !pipe->dep1), "conv_tc: pipe args");
+    a.dep0 = pipe->dep0; a.dep0_g = pipe->dep0_g;
+    a.dep1 = pipe->dep1; a.dep1_g = pipe->dep1_g;
+    a.progress = pipe->progress;
+  }
   const int epi_total = 2 * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
   const int bar_bytes = (2 * MAX_STAGES + 12) * 8 + 256 * 4 + 16;
   int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
@@ -945,21 +1047,28 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
     }
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const TcKernelArgs);
+  static const KernelFn kernels[8] = {
+      conv_tc_kernel<0, false, 0>, conv_tc_kernel<0, false, 1>, conv_tc_kernel<0, false, 2>,
+      conv_tc_kernel<0, true, 0>,  conv_tc_kernel<0, true, 1>,  conv_tc_kernel<0, true, 2>,
+      conv_tc_kernel<1, false, 0>, conv_tc_kernel<2, false, 0>};
+  const int ki = (p->epi_mode == 0) ? (a.has_pre * 3 + a.has_res1 + a.has_res2) : (p->epi_mode == 1 ? 6 : 7);
+  if (p->epi_mode == 0) DASR_REQUIRE(!(a.has_res2 && !a.has_res1), "conv_tc: res2 without res1");
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return DASR_E_LAUNCH;
     }
-    attr_set = true;
+    attr_set[ki] = true;
   }
   int gy = p->nvar * a.n_ntiles;
-  int gx = num_sms() / gy;
+  int gx = (pipe && pipe->grid_x > 0) ? pipe->grid_x : num_sms() / gy;
   if (gx < 1) gx = 1;
   if ((long)gx > a.ntiles) gx = (int)a.ntiles;
   dim3 grid(gx, gy);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, em, a);
+  kernels[ki]<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, em, a);
   return check_launch("conv_tc");
 }
 

@@ -12,6 +12,7 @@ precision:
   'bf16' — tcgen05 bf16 kernels, fp32 accumulate (inference performance mode)
 """
 import math
+import os
 
 import torch
 
@@ -226,7 +227,7 @@ def rrdb_backward_f32(ctx, params, dout, need_dx=False):
 # Dense-block working set per trunk pass.  Chunking the batch so that one pass fits the 126 MB L2 was measured
 # SLOWER on B200 (71 ms vs 62 ms per 16x256x256 forward: the shorter launches are latency-bound), so the default
 # keeps the whole batch in one pass; set e.g. 72 MiB to re-enable.
-TRUNK_L2_BYTES = float('inf')
+TRUNK_L2_BYTES = float(os.environ.get('DASR_B200_TRUNK_BYTES', 'inf'))
 _TC_W_BUDGET = 150 * 1024   # resident-filter bytes per CTA that still leaves >= 5 halo stages
 
 
@@ -281,9 +282,11 @@ def _fused_rdb_filters(cache, params, L, r, nf):
         ks = list(range(j, 6))
         wj = params[2 * L.rdb_conv(r, j)]
 
-        def make_w(lo=lo, hi=hi, ks=ks):
-            ws = [params[2 * L.rdb_conv(r, k)].detach()[:, lo:hi] for k in ks]
-            return ops.pack_filter_tc(torch.cat(ws, 0).float().contiguous(), TC_FPROP)
+        def stacked(lo=lo, hi=hi, ks=ks):
+            return torch.cat([params[2 * L.rdb_conv(r, k)].detach()[:, lo:hi] for k in ks], 0).float().contiguous()
+
+        def make_w(stacked=stacked):
+            return ops.pack_filter_tc(stacked(), TC_FPROP)
 
         def make_b(j=j, ks=ks):
             bj = params[2 * L.rdb_conv(r, j) + 1].detach().float()
@@ -292,11 +295,68 @@ def _fused_rdb_filters(cache, params, L, r, nf):
             b[:bj.shape[0]] = bj          # the bias of conv j is added when conv j completes (this launch)
             return b
 
-        out.append((cache.get(('fw', r, j), wj, make_w), cache.get(('fb', r, j), wj, make_b)))
+        ent = [cache.get(('fw', r, j), wj, make_w), cache.get(('fb', r, j), wj, make_b)]
+        if j == 1:   # the two Cout halves of launch 1 as separately packed filters (pipelined mode: two launches)
+            half = (nf + 4 * GC) // 2
+            ent.append(cache.get(('fw1a', r), wj, lambda: ops.pack_filter_tc(stacked()[:half].contiguous(), TC_FPROP)))
+            ent.append(cache.get(('fw1b', r), wj, lambda: ops.pack_filter_tc(stacked()[half:].contiguous(), TC_FPROP)))
+        out.append(tuple(ent))
     return out
 
 
-def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
+# CTAs per dense-block stage when the six stage launches of an RDB run concurrently (sum = 148 SMs); proportional to
+# the per-tile cost floor of each stage (MMA cycles for 1a/1b, TMA bytes for the partial-sum read-modify-write stages)
+PIPE_CTAS = (26, 26, 30, 24, 20, 22)
+
+
+def _rrdb_trunk_pipelined(L, params, cache, rot, fea, lr, wk, bk, nf, BW, CS):
+    """The 23 x 3 dense blocks with their stages SPATIALLY PIPELINED: the six stage launches of an RDB (1a, 1b, 2..5)
+    run concurrently on disjoint SM subsets, each on its own stream; a stage processes a tile as soon as its
+    producer stage(s) have finished the tiles around it (per-CTA progress counters in global memory, acquire/release).
+    The partial sums a stage re-reads were written microseconds earlier by a neighbouring SM, so the read-modify-write
+    traffic of the N-fused schedule stays in L2 instead of streaming through HBM once per launch."""
+    n_rdb = L.n_rdb
+    dev = fea.device
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(6)]
+    prog = torch.zeros((n_rdb, 6, 32), dtype=torch.int32, device=dev)      # progress[r][stage][cta]
+    bufs = [rot[i % 3] for i in range(n_rdb + 1)]
+    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
+    for s_ in streams:
+        s_.wait_stream(main)
+    G = PIPE_CTAS
+    half = (BW - nf) // 2
+    for r in range(n_rdb):
+        b = bufs[r]
+        fw = _fused_rdb_filters(cache, params, L, r, nf)
+        prev5 = [(prog[r - 1, 5], G[5])] if r > 0 else []
+        bias1 = fw[0][1]
+        with torch.cuda.stream(streams[0]):     # 1a: x -> x1 (complete) | partial conv2, conv3
+            ops.conv_tc(View(b, nf, 0), fw[0][2], bias1[:half].contiguous(), View(b, half, nf), act=ACT_LRELU, slope=0.2,
+                        act_cols=GC, pipe=dict(grid_x=G[0], deps=prev5, progress=prog[r, 0]))
+        with torch.cuda.stream(streams[1]):     # 1b: x -> partial conv4, conv5
+            ops.conv_tc(View(b, nf, 0), fw[0][3], None, View(b, half, nf + half),
+                        pipe=dict(grid_x=G[1], deps=prev5, progress=prog[r, 1]))
+        for j in (2, 3, 4):                     # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, in place
+            o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
+            deps = [(prog[r, 0], G[0]), (prog[r, 1], G[1])] if j == 2 else [(prog[r, j - 1], G[j - 1])]
+            with torch.cuda.stream(streams[j]):
+                ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
+                            act_cols=GC, pre=o, pipe=dict(grid_x=G[j], deps=deps, progress=prog[r, j]))
+        dst = View(bufs[r + 1], nf, 0)
+        if r % 3 == 2:
+            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        else:
+            tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+        with torch.cuda.stream(streams[5]):
+            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS),
+                        pipe=dict(grid_x=G[5], deps=[(prog[r, 4], G[4])], progress=prog[r, 5]), **tail)
+    for s_ in streams:
+        main.wait_stream(s_)
+    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+
+
+def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipelined=None):
     """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between.
 
     fused=True : dense-block N-fusion.  Each RDB runs 5 launches; launch j reads one 32/64-channel chunk ONCE
@@ -316,6 +376,9 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
     bf = torch.bfloat16
     CS = nf + 4 * GC
     BW = CS + (nf if fused else 0)        # fused: extra slot for conv5's partial sums
+    if pipelined is None:
+        pipelined = fused and os.environ.get('DASR_B200_PIPE', '0') == '1'   # experimental: measured slower
+    pipelined = bool(pipelined and fused and nf == 64)
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -335,9 +398,13 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
     # The trunk runs image-chunk by image-chunk so that the dense-block buffer of a chunk (partial sums that the
     # next launch re-reads) stays resident in the 126 MB L2 instead of round-tripping through HBM.
     per_img = H * W * BW * 2
-    cn = N if not fused else max(1, min(N, int(TRUNK_L2_BYTES // max(per_img, 1))))
+    cn = N if (not fused or TRUNK_L2_BYTES == float('inf')) else max(1, min(N, int(TRUNK_L2_BYTES // max(per_img, 1))))
     rot = [_empty((cn, H, W, BW), x, bf) for _ in range(3)]
-    for n0 in range(0, N, cn):
+    rev = False
+    if pipelined:
+        _rrdb_trunk_pipelined(L, params, cache, rot, fea, lr, wk, bk, nf, BW, CS)
+        cn = 0
+    for n0 in (range(0, N, cn) if cn else ()):
         n1 = min(N, n0 + cn)
         c = n1 - n0
         bufs = [rot[i % 3][:c] for i in range(n_rdb + 1)]
@@ -352,14 +419,19 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
                 tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
             if fused:
                 fw = _fused_rdb_filters(cache, params, L, r, nf)
+                # Consecutive launches walk the tile grid in opposite directions: a launch starts with the tiles its
+                # predecessor wrote last, i.e. with the part of the partial sums that is still resident in L2.
                 # launch 1: x -> x1 (complete) | partial conv2..5
                 ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2,
-                            act=ACT_LRELU, slope=0.2, act_cols=GC)
+                            act=ACT_LRELU, slope=0.2, act_cols=GC, tile_rev=rev)
+                rev = not rev
                 for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
                     o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
                     ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
-                                act_cols=GC, pre=o)
-                ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+                                act_cols=GC, pre=o, tile_rev=rev)
+                    rev = not rev
+                ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), tile_rev=rev, **tail)
+                rev = not rev
             else:
                 for k in range(1, 5):
                     ci = L.rdb_conv(r, k)
@@ -367,7 +439,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
                 ci = L.rdb_conv(r, 5)
                 ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=_pick_nt(nf, CS), **tail)
         ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr[n0:n1], nt=_pick_nt(nf, nf), res1=fea_c, beta1=1.0)
-    del rot, bufs
+    del rot
     cur, h, w = lr, H, W
     for u in range(L.n_up):
         h, w = 2 * h, 2 * w

@@ -132,7 +132,7 @@ def pack_filter_tc(w, kind):
 
 def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0, act_cols=None,
             pre=None, res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2,
-            a_mode=0, nchw_out=None, cout=None):
+            a_mode=0, nchw_out=None, cout=None, pipe=None, tile_rev=False):
     """tcgen05 3x3 conv on NHWC bf16 channel slices; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
     v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
     nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer)."""
@@ -164,8 +164,22 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
         mask = as_view(mask)
         p.mask_cs, p.mask_coff, p.mask_c0, p.mask_c1, p.mask_slope = mask.cs, mask.coff, mask_c0, mask_c1, mask_slope
     p.a_mode = a_mode
-    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
-                           res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
+    p.tile_rev = int(bool(tile_rev))
+    pa = None
+    if pipe is not None:
+        # pipe = dict(grid_x=int, deps=[(int32 tensor, producer CTAs), ...] (<= 2), progress=int32 tensor or None)
+        pa = _lib.PipeArgs()
+        pa.grid_x = pipe['grid_x']
+        deps = pipe.get('deps') or []
+        if len(deps) > 0:
+            pa.dep0, pa.dep0_g = deps[0][0].data_ptr(), deps[0][1]
+        if len(deps) > 1:
+            pa.dep1, pa.dep1_g = deps[1][0].data_ptr(), deps[1][1]
+        if pipe.get('progress') is not None:
+            pa.progress = pipe['progress'].data_ptr()
+    check(lib.dasr_conv_tc_pipe(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
+                                res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p),
+                                C.byref(pa) if pa is not None else None, _stream()), 'conv_tc')
 
 
 def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):

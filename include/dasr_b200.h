@@ -122,11 +122,29 @@ typedef struct {
                                   (dense-block fused launches finish one conv and extend partial sums of the others) */
   int pre_cs, pre_coff;        /* pre-activation addend (bf16 NHWC): v = act(acc + bias + pre) */
   int out_nc;                  /* epi_mode 2: real output channels */
+  int tile_rev;                /* 1 = walk the tile grid backwards: a launch that re-reads what the previous launch
+                                  just wrote (dense-block partial sums) starts with the tiles still resident in L2 */
 } DasrConvTcParams;
 
 int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
                  const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16,
                  void* out /* bf16 NHWC, or fp32 NCHW in epi_mode 2 */, const DasrConvTcParams* p, void* stream);
+
+/* Spatially pipelined launches (dense-block stages running concurrently on disjoint SM subsets, each on its own
+ * stream): this launch uses grid_x persistent CTAs; a tile is loaded only after every CTA of the producer launch(es)
+ * has finished its tiles up to the end of the next tile row (dep*[k] = tiles finished by producer CTA k, int32, zeroed
+ * before the producers start; producer and consumer must walk the same tile grid); progress[k] (>= grid_x ints) is
+ * published by this launch.  All pointers are device pointers; dep1/progress may be NULL. */
+typedef struct {
+  int grid_x;
+  const int* dep0; int dep0_g;
+  const int* dep1; int dep1_g;
+  int* progress;
+} DasrPipeArgs;
+
+int dasr_conv_tc_pipe(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
+                      const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16, void* out,
+                      const DasrConvTcParams* p, const DasrPipeArgs* pipe /* NULL = plain launch */, void* stream);
 
 /* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
  *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)

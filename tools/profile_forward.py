@@ -16,7 +16,7 @@ batch = int(os.environ.get('BATCH', 16))
 net = RRDBNet(3, 3, 64, nb)
 net.load_state_dict(O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 1, 0.1))
 net.cuda().eval()
-net.precision = 'bf16'
+net.precision = os.environ.get('PREC', 'bf16')
 x = O.synth_image((batch, 3, 256, 256), 100).cuda()
 with torch.no_grad():
     net(x)
