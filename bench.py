@@ -271,7 +271,8 @@ def main():
     # ---------------------------------------------------------------- train step (configs[2]), fp32 kernels
     train = None
     if args.train_steps > 0:
-        train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks)
+        train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'bf16')
+        train['fp32_mode'] = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'fp32')
 
     if rank != 0:
         if world > 1:
@@ -316,7 +317,7 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_train(args, dev, local_rank, world, barrier, max_over_ranks):
+def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision='fp32'):
     """DASR_Model.feed_data + optimize_parameters (G + D + VGG perceptual + weighted L1), B=32 per GPU, HR crop 128."""
     import warnings
     import torch
@@ -341,6 +342,8 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks):
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         model = create_model(opt)
+    g = model.netG.module if hasattr(model.netG, 'module') else model.netG
+    g.train_precision = precision
     rank = int(os.environ.get('RANK', 0))
     data = {'LR_real': O.synth_image((B, 3, h, h), 200 + rank).pin_memory(), 'LR_fake': O.synth_image((B, 3, h, h), 300 + rank).pin_memory(),
             'HR': O.synth_image((B, 3, 4 * h, 4 * h), 400 + rank).pin_memory(), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * h), 500 + rank).pin_memory(),
@@ -363,7 +366,8 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.train_steps)
     res = {'metric': 'DASR SRN train iterations/sec (G + patch-D + VGG19 perceptual + weighted L1, Adam x2)',
-           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps, 'dtype': 'f32',
+           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps,
+           'dtype': 'f32' if precision == 'fp32' else 'bf16 (G: tcgen05 fprop+dgrad, fp32-accumulated wgrad; D, VGG19, losses fp32)',
            'config': {'workload': 'BASELINE configs[2]: batch 32 (2B=64 LR 32x32 through G), HR crop 128, fs wavelet, per GPU',
                       'global_batch': 32 * world, 'parallelism': 'dp%d, one flat-bucket NCCL all-reduce of G+D grads per step' % world},
            'gpu_launches_per_step': (_lib.LAUNCHES - l0) // args.train_steps,

@@ -63,6 +63,11 @@ SYMBOLS = {
     'dasr_conv2d_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _vp]),
     'dasr_conv2d_wgrad_f32_workspace': (_sz, [C.POINTER(ConvF32Params)]),
     'dasr_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),
+    'dasr_conv2d_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),
+    'dasr_conv3x3_wgrad_tc_workspace': (_sz, [_i, _i, _i, _i, _i]),
+    'dasr_conv3x3_wgrad_tc': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'dasr_bias_grad': (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _vp]),
+    'dasr_upsample2x_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasr_pack_filter_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
     'dasr_conv_tc_pipe': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), C.POINTER(PipeArgs), _vp]),

@@ -175,10 +175,22 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
   }
 }
 
-// part[split][K x Cout] = gather(in)^T[K x Pslice] * dout[Pslice x Cout]
-template <bool VEC>
-__global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const float* __restrict__ in,
-                                                               const float* __restrict__ dout,
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const float2 a = __bfloat1622float2(b[0]), c = __bfloat1622float2(b[1]);
+  return make_float4(a.x, a.y, c.x, c.y);
+}
+template <typename T> __device__ __forceinline__ float load1(const T* p);
+template <> __device__ __forceinline__ float load1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// part[split][K x Cout] = gather(in)^T[K x Pslice] * dout[Pslice x Cout]      (T = fp32 or bf16 inputs, fp32 accumulate)
+template <bool VEC, typename T>
+__global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restrict__ in,
+                                                               const T* __restrict__ dout,
                                                                float* __restrict__ part,
                                                                DasrConvF32Params p, long pix_per_split) {
   __shared__ __align__(16) float As[BK][BMP];  // [pixel][k]
@@ -229,8 +241,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const float* __re
           if (ktap[0] >= 0) {
             int dy = ktap[0] / p.kw, dx = ktap[0] - dy * p.kw, iy, ix;
             if (gather_coord(p, oy, ox, dy, dx, iy, ix)) {
-              const float4 q = *reinterpret_cast<const float4*>(
-                  in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[0]);
+              const float4 q = load4<T>(in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[0]);
               v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
             }
           }
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const float* __re
             if (ktap[j] >= 0) {
               int dy = ktap[j] / p.kw, dx = ktap[j] - dy * p.kw, iy, ix;
               if (gather_coord(p, oy, ox, dy, dx, iy, ix))
-                v[j] = in[((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[j]];
+                v[j] = load1<T>(in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + kci[j]);
             }
           }
         }
@@ -251,14 +262,14 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const float* __re
       float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
       int c = co0 + l_q * 4;
       if (ok) {
-        const float* dp = dout + pix * p.out_cs + p.out_coff + c;
+        const T* dp = dout + pix * p.out_cs + p.out_coff + c;
         if (VEC) {
-          if (c < p.cout) q = *reinterpret_cast<const float4*>(dp);
+          if (c < p.cout) q = load4<T>(dp);
         } else {
-          if (c + 0 < p.cout) q.x = dp[0];
-          if (c + 1 < p.cout) q.y = dp[1];
-          if (c + 2 < p.cout) q.z = dp[2];
-          if (c + 3 < p.cout) q.w = dp[3];
+          if (c + 0 < p.cout) q.x = load1<T>(dp + 0);
+          if (c + 1 < p.cout) q.y = load1<T>(dp + 1);
+          if (c + 2 < p.cout) q.z = load1<T>(dp + 2);
+          if (c + 3 < p.cout) q.w = load1<T>(dp + 3);
         }
       }
       *reinterpret_cast<float4*>(&Bs[l_p][l_q * 4]) = q;
@@ -305,12 +316,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 }
 
 // bias gradient: column sums of dout, two-stage deterministic
-__global__ void bgrad_partial_kernel(const float* __restrict__ dout, float* __restrict__ part, long P, int cout,
+template <typename T>
+__global__ void bgrad_partial_kernel(const T* __restrict__ dout, float* __restrict__ part, long P, int cout,
                                      int cs, int coff, long pix_per_block) {
   long pbeg = (long)blockIdx.x * pix_per_block, pend = min(P, pbeg + pix_per_block);
   for (int c = threadIdx.x; c < cout; c += blockDim.x) {
     float s = 0.f;
-    for (long pp = pbeg; pp < pend; pp++) s += dout[pp * cs + coff + c];
+    for (long pp = pbeg; pp < pend; pp++) s += load1<T>(dout + pp * cs + coff + c);
     part[(long)blockIdx.x * cout + c] = s;
   }
 }
@@ -367,6 +379,43 @@ static int check_conv_params(const DasrConvF32Params* p) {
 
 using namespace dasr;
 
+extern "C" size_t dasr_conv2d_wgrad_f32_workspace(const DasrConvF32Params* p);
+
+template <typename T>
+static int wgrad_impl(const T* in, const T* dout, float* dw, float* db, const DasrConvF32Params* p, int accumulate,
+                      void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  DASR_REQUIRE(p->mode == DASR_CONV_FWD, "wgrad: params must describe the FWD conv");
+  DASR_REQUIRE(ws_bytes >= dasr_conv2d_wgrad_f32_workspace(p), "wgrad: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  long P = (long)p->N * p->OH * p->OW;
+  int K = p->kh * p->kw * p->cin;
+  int splits = wgrad_splits(p);
+  long pps = ((P + splits - 1) / splits + BK - 1) / BK * BK;
+  float* part = (float*)ws;
+  dim3 grid(cdiv(K, BM), cdiv(p->cout, BN), splits);
+  const uintptr_t amask = sizeof(T) == 4 ? 15 : 7;
+  bool vec = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
+             (p->out_cs % 4 == 0) && (p->out_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & amask) == 0) &&
+             ((reinterpret_cast<uintptr_t>(dout) & amask) == 0);
+  if (vec)
+    conv2d_wgrad_f32_kernel<true, T><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
+  else
+    conv2d_wgrad_f32_kernel<false, T><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
+  long total = (long)K * p->cout;
+  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(part, dw, splits, K, p->cin, p->cout, p->kh * p->kw,
+                                                         accumulate);
+  if (db) {
+    float* bpart = part + (size_t)splits * total;
+    int nb = bgrad_blocks(P);
+    long ppb = (P + nb - 1) / nb;
+    bgrad_partial_kernel<T><<<nb, 128, 0, st>>>(dout, bpart, P, p->cout, p->out_cs, p->out_coff, ppb);
+    bgrad_reduce_kernel<<<cdiv(p->cout, 128), 128, 0, st>>>(bpart, db, nb, p->cout, accumulate);
+  }
+  return check_launch("conv2d_wgrad");
+}
+
 extern "C" {
 
 const char* dasr_last_error(void) { return g_err; }
@@ -396,35 +445,13 @@ size_t dasr_conv2d_wgrad_f32_workspace(const DasrConvF32Params* p) {
 
 int dasr_conv2d_wgrad_f32(const float* in, const float* dout, float* dw, float* db, const DasrConvF32Params* p,
                           int accumulate, void* ws, size_t ws_bytes, void* stream) {
-  int rc = check_conv_params(p);
-  if (rc) return rc;
-  DASR_REQUIRE(p->mode == DASR_CONV_FWD, "wgrad_f32: params must describe the FWD conv");
-  DASR_REQUIRE(ws_bytes >= dasr_conv2d_wgrad_f32_workspace(p), "wgrad_f32: workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  long P = (long)p->N * p->OH * p->OW;
-  int K = p->kh * p->kw * p->cin;
-  int splits = wgrad_splits(p);
-  long pps = ((P + splits - 1) / splits + BK - 1) / BK * BK;
-  float* part = (float*)ws;
-  dim3 grid(cdiv(K, BM), cdiv(p->cout, BN), splits);
-  bool vec = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
-             (p->out_cs % 4 == 0) && (p->out_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
-             ((reinterpret_cast<uintptr_t>(dout) & 15) == 0);
-  if (vec)
-    conv2d_wgrad_f32_kernel<true><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
-  else
-    conv2d_wgrad_f32_kernel<false><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
-  long total = (long)K * p->cout;
-  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(part, dw, splits, K, p->cin, p->cout, p->kh * p->kw,
-                                                         accumulate);
-  if (db) {
-    float* bpart = part + (size_t)splits * total;
-    int nb = bgrad_blocks(P);
-    long ppb = (P + nb - 1) / nb;
-    bgrad_partial_kernel<<<nb, 128, 0, st>>>(dout, bpart, P, p->cout, p->out_cs, p->out_coff, ppb);
-    bgrad_reduce_kernel<<<cdiv(p->cout, 128), 128, 0, st>>>(bpart, db, nb, p->cout, accumulate);
-  }
-  return check_launch("conv2d_wgrad_f32");
+  return wgrad_impl<float>(in, dout, dw, db, p, accumulate, ws, ws_bytes, stream);
+}
+
+int dasr_conv2d_wgrad_bf16(const void* in, const void* dout, float* dw, float* db, const DasrConvF32Params* p,
+                           int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  return wgrad_impl<__nv_bfloat16>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, dw, db, p, accumulate, ws,
+                                   ws_bytes, stream);
 }
 
 int dasr_pack_filter_f32(const float* w, float* o, int cout, int cin, int kh, int kw, int for_dgrad, void* stream) {

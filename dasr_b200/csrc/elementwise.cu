@@ -98,6 +98,22 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ src, T* __restrict__
 }
 
 template <typename T>
+__global__ void upsample2x_fwd_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C,
+                                      int src_cs, int src_coff, int dst_cs, int dst_coff) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * 2 * H * 2 * W * C;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long pp = i / C;
+  int x = (int)(pp % (2 * W));
+  long r = pp / (2 * W);
+  int y = (int)(r % (2 * H));
+  int n = (int)(r / (2 * H));
+  long sp = ((long)n * H + (y >> 1)) * W + (x >> 1);
+  st<T>(dst + pp * dst_cs + dst_coff + c, ld<T>(src + sp * src_cs + src_coff + c));
+}
+
+template <typename T>
 __global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ d, long npix, int C,
                              int x_cs, int x_coff, int y_cs, int y_coff, int d_cs, int d_coff, float a, float b) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,6 +240,33 @@ __global__ void instnorm_lrelu_bwd_kernel(const float* __restrict__ y, const flo
       dx[base + (long)pp * C + c] = rstd * (g - mg - xh * mgx);
     }
   }
+}
+
+// ---- bias gradient: db[c] (+)= sum over pixels of dout[p][c]; NHWC channel slice, fp32 or bf16 -------------------
+// stage 1: grid (cdiv(C,32), nblk), block (32 channels, 8 pixel lanes): coalesced 32-channel rows
+template <typename T>
+__global__ void bias_grad_partial_kernel(const T* __restrict__ d, float* __restrict__ part, long npix, int C, int cs,
+                                         int coff, long pix_per_block) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long p0 = (long)blockIdx.y * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (long pp = p0 + threadIdx.y; pp < p1; pp += 8) s += ld<T>(d + pp * cs + coff + c);
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int k = 0; k < 8; k++) t += sh[k][threadIdx.x];
+    part[(long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void bias_grad_reduce_kernel(const float* __restrict__ part, float* __restrict__ db, int nblk, int C, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; b++) s += part[(long)b * C + c];
+  db[c] = accumulate ? db[c] + s : s;
 }
 
 // ---- Haar J=1 split (pytorch_wavelets DWTForward 'haar', even H,W) ------------------------------
@@ -474,6 +517,19 @@ int dasr_upsample2x_bwd(const void* src, void* dst, int N, int H, int W, int C, 
   return check_launch("upsample2x_bwd");
 }
 
+int dasr_upsample2x_fwd(const void* src, void* dst, int N, int H, int W, int C, int src_cs, int src_coff, int dst_cs,
+                        int dst_coff, int is_bf16, void* stream) {
+  DASR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "upsample2x_fwd: bad dims");
+  long total = (long)N * 4 * H * W * C;
+  if (is_bf16)
+    upsample2x_fwd_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, H, W, C, src_cs, src_coff, dst_cs, dst_coff);
+  else
+    upsample2x_fwd_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)src, (float*)dst, N, H, W, C, src_cs, src_coff, dst_cs, dst_coff);
+  return check_launch("upsample2x_fwd");
+}
+
 int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff, int y_cs, int y_coff,
                int d_cs, int d_coff, float a, float b, int is_bf16, void* stream) {
   DASR_REQUIRE(npix > 0 && C > 0 && x && dst, "axpby: bad arguments");
@@ -486,6 +542,22 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
     axpby_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const float*)x, (const float*)y, (float*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs, d_coff, a, b);
   return check_launch("axpby");
+}
+
+int dasr_bias_grad(const void* dout, float* db, long npix, int C, int cs, int coff, int is_bf16, int accumulate,
+                   float* partials, void* stream) {
+  DASR_REQUIRE(npix > 0 && C > 0 && cs >= coff + C && partials, "bias_grad: bad arguments");
+  long nblk = (npix + 2047) / 2048;
+  if (nblk > 64) nblk = 64;                       // partials: >= 64 * C floats
+  long ppb = (npix + nblk - 1) / nblk;
+  dim3 grid(cdiv(C, 32), (unsigned)nblk), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (is_bf16)
+    bias_grad_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dout, partials, npix, C, cs, coff, ppb);
+  else
+    bias_grad_partial_kernel<float><<<grid, block, 0, st>>>((const float*)dout, partials, npix, C, cs, coff, ppb);
+  bias_grad_reduce_kernel<<<cdiv(C, 128), 128, 0, st>>>(partials, db, (int)nblk, C, accumulate);
+  return check_launch("bias_grad");
 }
 
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream) {

@@ -299,6 +299,49 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   cudaFree(din); cudaFree(dres); cudaFree(dmsk); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
 }
 
+static void test_wgrad_tc(int N, int H, int W, int cin, int cout) {
+  char name[160];
+  const int x_cs = cin + 32, x_coff = 8, dy_cs = cout + 16, dy_coff = 8;
+  std::vector<float> x((size_t)N * H * W * x_cs), dy((size_t)N * H * W * dy_cs);
+  for (auto& v : x) v = rnd_q(8, 8.f);
+  for (auto& v : dy) v = rnd_q(8, 8.f);
+  std::vector<double> ref((size_t)cout * cin * 9, 0.0);
+  for (int n = 0; n < N; n++)
+    for (int oy = 0; oy < H; oy++)
+      for (int ox = 0; ox < W; ox++)
+        for (int t = 0; t < 9; t++) {
+          int iy = oy - 1 + t / 3, ix = ox - 1 + t % 3;
+          if (iy < 0 || ix < 0 || iy >= H || ix >= W) continue;
+          const float* xp = &x[((size_t)(n * H + iy) * W + ix) * x_cs + x_coff];
+          const float* gp = &dy[((size_t)(n * H + oy) * W + ox) * dy_cs + dy_coff];
+          for (int co = 0; co < cout; co++) {
+            double g = gp[co];
+            if (g == 0.0) continue;
+            for (int ci = 0; ci < cin; ci++) ref[((size_t)co * cin + ci) * 9 + t] += g * xp[ci];
+          }
+        }
+  auto xb = to_bf16(x), dyb = to_bf16(dy);
+  __nv_bfloat16 *dx = dalloc<__nv_bfloat16>(xb.size()), *ddy = dalloc<__nv_bfloat16>(dyb.size());
+  h2d(dx, xb); h2d(ddy, dyb);
+  float* dw = dalloc<float>(ref.size());
+  size_t wsb = dasr_conv3x3_wgrad_tc_workspace(N, H, W, cin, cout);
+  void* ws; CK(cudaMalloc(&ws, wsb));
+  int rc = dasr_conv3x3_wgrad_tc(dx, x_cs, x_coff, ddy, dy_cs, dy_coff, dw, N, H, W, cin, cout, 0, ws, wsb, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  snprintf(name, sizeof(name), "wgrad_tc N%d %dx%d cin%d cout%d", N, H, W, cin, cout);
+  if (rc || e != cudaSuccess) {
+    printf("[FAIL] %s rc=%d err=%s cuda=%s\n", name, rc, dasr_last_error(), cudaGetErrorString(e));
+    g_fail++;
+    if (e != cudaSuccess) exit(3);
+    return;
+  }
+  auto got = d2h(dw, ref.size());
+  double me = 0;
+  for (size_t i = 0; i < ref.size(); i++) me = fmax(me, fabs(got[i] - ref[i]));
+  report(name, me, 1e-3);      // inputs are small dyadic rationals: products and fp32 sums are exact
+  cudaFree(dx); cudaFree(ddy); cudaFree(dw); cudaFree(ws);
+}
+
 static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, int a_mode, int iters) {
   const int in_cs = 192;
   const int mul = (kind == 2) ? 2 : 1;
@@ -464,6 +507,12 @@ int main(int argc, char** argv) {
     test_f32(1, 6, 7, 16, 16, 3, 1, 1, 2);
     test_f32(1, 8, 8, 8, 1, 4, 1, 1, 1);
     test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
+    test_wgrad_tc(1, 16, 8, 32, 32);
+    test_wgrad_tc(1, 16, 8, 64, 32);
+    test_wgrad_tc(2, 20, 13, 96, 32);
+    test_wgrad_tc(3, 32, 24, 160, 32);
+    test_wgrad_tc(2, 32, 16, 192, 64);
+    test_wgrad_tc(1, 48, 40, 64, 64);
     // tcgen05: validation path first (one aligned tile per tap), then shifted-descriptor halo path
     for (int am = 1; am >= 0; am--) {
       test_tc(1, 16, 8, 32, 32, 32, 0, am, 0);

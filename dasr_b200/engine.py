@@ -459,6 +459,189 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
     return out
 
 
+# ---- bf16 tcgen05 training (mixed precision: bf16 activations/gradients, fp32 accumulation, fp32 filter grads) ----
+
+def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
+    """Forward of the mixed-precision training mode: the dense-block N-fused tcgen05 schedule of the inference path,
+    but every RDB keeps its own buffer (the backward needs x, x1..x4)."""
+    _need_cuda(x, 'RRDBNet')
+    L = RRDBLayout(nb, params[0].shape[0], upscale)
+    nf = L.nf
+    cache = cache if cache is not None else _PackCache()
+    N, in_nc, H, W = x.shape
+    bf = torch.bfloat16
+    CS = nf + 4 * GC
+    BW = CS + nf
+    Wt = lambda i: params[2 * i]
+
+    def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
+        return cache.get(('w', i, kind), Wt(i), lambda: ops.pack_filter_tc(_pad_filter(Wt(i), cout_to, cin_to).float(), kind))
+
+    def bk(i, n=None):
+        p = params[2 * i + 1]
+        return cache.get(('b', i), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
+
+    xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)
+    ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
+    fea = _empty((N, H, W, nf), x, bf)
+    ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
+    n_rdb = L.n_rdb
+    bufs = [_empty((N, H, W, BW), x, bf) for _ in range(n_rdb)] + [_empty((N, H, W, nf), x, bf)]
+    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
+    for r in range(n_rdb):
+        b = bufs[r]
+        dst = View(bufs[r + 1], nf, 0)
+        if r % 3 == 2:
+            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        else:
+            tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+        fw = _fused_rdb_filters(cache, params, L, r, nf)
+        ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2, act=ACT_LRELU, slope=0.2,
+                    act_cols=GC)
+        for j in (2, 3, 4):
+            o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
+            ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o)
+        ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+    lr = _empty((N, H, W, nf), x, bf)
+    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+    ups = [lr]
+    cur, h, w = lr, H, W
+    for u in range(L.n_up):
+        h, w = 2 * h, 2 * w
+        nxt = _empty((N, h, w, nf), x, bf)
+        ops.conv_tc(cur, wk(L.i_up0 + u, TC_UPCONV), bk(L.i_up0 + u), nxt, kind=TC_UPCONV, nt=_pick_nt(nf, nf, 4),
+                    act=ACT_LRELU, slope=0.2)
+        ups.append(nxt)
+        cur = nxt
+    h0 = _empty((N, h, w, nf), x, bf)
+    ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2)
+    out_nc = Wt(L.i_hr1).shape[0]
+    out = _empty((N, out_nc, h, w), x)
+    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), None, nchw_out=out, cout=16)
+    ctx = dict(L=L, xin=xin, fea=fea, bufs=bufs, ups=ups, h0=h0, shape=(N, in_nc, H, W))
+    return out, ctx
+
+
+def rrdb_backward_bf16(ctx, params, dout, cache=None):
+    """Backward of the mixed-precision mode: input gradients (dgrad) on the tcgen05 kernel (3x3 conv with flipped,
+    transposed filters; gradient contributions of a dense block accumulate in place in one bf16 buffer), filter
+    gradients on the tcgen05 wgrad kernel (MN-major operands straight from the NHWC tiles, fp32 TMEM accumulation).  Returns fp32 grads."""
+    from .ops import TC_DGRAD
+    L = ctx['L']
+    nf = L.nf
+    N, in_nc, H, W = ctx['shape']
+    bf = torch.bfloat16
+    Wt = lambda i: params[2 * i]
+    CS = nf + 4 * GC
+    grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+    gW = lambda i: grads[2 * i]
+    gB = lambda i: grads[2 * i + 1]
+    cache = cache if cache is not None else _PackCache()
+
+    def wd(i, cout_to=None):
+        return cache.get(('wd', i), Wt(i), lambda: ops.pack_filter_tc(_pad_filter(Wt(i), cout_to, None).float(), TC_DGRAD))
+
+    bufs, ups, h0, fea, xin = ctx['bufs'], ctx['ups'], ctx['h0'], ctx['fea'], ctx['xin']
+    dev = dout
+
+    def wgrad(xv, gv, i, cin_real=None, cout_real=None):
+        """filter + bias gradient of conv i on the tcgen05 wgrad kernel (zero-padded channel chunks are cut off)"""
+        xv, gv = ops.as_view(xv), ops.as_view(gv)
+        if cin_real is None and cout_real is None:
+            ops.conv3x3_wgrad_tc(xv, gv, gW(i))
+        else:
+            tmp = torch.empty((gv.c, xv.c, 3, 3), dtype=torch.float32, device=dout.device)
+            ops.conv3x3_wgrad_tc(xv, gv, tmp)
+            gW(i).copy_(tmp[:cout_real or gv.c, :cin_real or xv.c])
+        ops.bias_grad(View(gv.t, cout_real or gv.c, gv.coff), gB(i))
+    out_nc = Wt(L.i_hr1).shape[0]
+    hh, ww = dout.shape[2], dout.shape[3]
+
+    g_o = torch.zeros((N, hh, ww, 32), dtype=bf, device=dout.device)      # Cout 3 -> one zero-padded 32-channel K chunk
+    ops.nchw_to_nhwc(dout.contiguous().float(), View(g_o, out_nc, 0))
+    wgrad(h0, g_o, L.i_hr1, cout_real=out_nc)
+    g_h0 = _empty((N, hh, ww, nf), dev, bf)
+    ops.conv_tc(g_o, wd(L.i_hr1, cout_to=32), None, g_h0, kind=TC_DGRAD, nt=_pick_nt(nf, 32))
+    ops.act_bwd(g_h0, h0, 0.2)
+    top = ups[-1]
+    wgrad(top, g_h0, L.i_hr0)
+    g_cur = _empty((N, hh, ww, nf), dev, bf)
+    ops.conv_tc(g_h0, wd(L.i_hr0), None, g_cur, kind=TC_DGRAD, nt=_pick_nt(nf, nf))
+    del g_h0, g_o
+    for u in reversed(range(L.n_up)):
+        y, xin_u = ups[u + 1], ups[u]
+        ops.act_bwd(g_cur, y, 0.2)
+        x_up = _empty(tuple(y.shape), dev, bf)                 # nearest-x2 input materialised for the filter gradient only
+        ops.upsample2x_fwd(xin_u, x_up)
+        wgrad(x_up, g_cur, L.i_up0 + u)
+        del x_up
+        g_upin = _empty(tuple(y.shape), dev, bf)
+        ops.conv_tc(g_cur, wd(L.i_up0 + u), None, g_upin, kind=TC_DGRAD, nt=_pick_nt(nf, nf))
+        g_nxt = _empty(tuple(xin_u.shape), dev, bf)
+        ops.upsample2x_bwd(g_upin, g_nxt)
+        del g_upin
+        g_cur = g_nxt
+    g_lr = g_cur
+    n_rdb = L.n_rdb
+    trunk = View(bufs[n_rdb], nf, 0)
+    wgrad(trunk, g_lr, L.i_lr)
+    g_y = _empty((N, H, W, nf), dev, bf)
+    ops.conv_tc(g_lr, wd(L.i_lr), None, g_y, kind=TC_DGRAD, nt=_pick_nt(nf, nf))
+
+    GB = _empty((N, H, W, CS), dev, bf)
+    g_x5 = _empty((N, H, W, nf), dev, bf)
+    g_rrdb = None
+    for r in reversed(range(n_rdb)):
+        b = bufs[r]
+        if r % 3 == 2:
+            a5, b1 = 0.04, 0.2
+            g_rrdb = g_y
+        else:
+            a5, b1 = 0.2, 1.0
+        ops.axpby(g_y, a5, None, 0.0, g_x5)
+        ci = L.rdb_conv(r, 5)
+        wgrad(View(b, CS, 0), g_x5, ci)
+        ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)        # K=64 -> N=192 as 2 x 96
+        ops.axpby(View(GB, nf, 0), 1.0, g_y, b1, View(GB, nf, 0))
+        for k in (4, 3, 2, 1):
+            ci = L.rdb_conv(r, k)
+            cin = _rdb_cin(nf, k)
+            gk = View(GB, GC, nf + (k - 1) * GC)
+            ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
+            wgrad(View(b, cin, 0), gk, ci)
+            o = View(GB, cin, 0)
+            ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                          # accumulate in place
+        g_new = _empty((N, H, W, nf), dev, bf)
+        if r % 3 == 0 and g_rrdb is not None:
+            ops.axpby(View(GB, nf, 0), 1.0, g_rrdb, 1.0, g_new)
+            g_rrdb = None
+        else:
+            ops.axpby(View(GB, nf, 0), 1.0, None, 0.0, g_new)
+        g_y = g_new
+    g_fea = _empty((N, H, W, nf), dev, bf)
+    ops.axpby(g_y, 1.0, g_lr, 1.0, g_fea)
+    wgrad(xin, g_fea, L.i_fea, cin_real=in_nc)
+    return None, grads
+
+
+class RRDBNetFunctionBF16(torch.autograd.Function):
+    """Mixed-precision training node (tcgen05 fprop + dgrad, fp32-accumulated filter gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, nb, upscale, cache, *params):
+        out, saved = rrdb_forward_bf16_train(x, [p.detach() for p in params], nb, upscale, cache)
+        ctx.saved, ctx.params, ctx.cache = saved, params, cache
+        if x.requires_grad:
+            raise ops._lib.DasrError('bf16 training mode does not return the input-image gradient; use precision fp32')
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        _, grads = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
+        ctx.saved = None
+        return (None, None, None, None) + tuple(g.to(p.dtype) for g, p in zip(grads, ctx.params))
+
+
 class RRDBNetFunction(torch.autograd.Function):
     """fp32 training node: forward/backward entirely on the C-ABI kernels."""
 

@@ -103,8 +103,44 @@ def conv2d_wgrad_f32(inp, dout, dw, db, k, stride, pad, ups=1, accumulate=False)
     lib = _lib.load()
     n = lib.dasr_conv2d_wgrad_f32_workspace(C.byref(p))
     ws = _workspace(n, inp.t.device)
-    check(lib.dasr_conv2d_wgrad_f32(inp.ptr, dout.ptr, _p(dw), _p(db), C.byref(p), int(accumulate), _p(ws),
-                                    ws.numel(), _stream()), 'conv2d_wgrad_f32', 4 if db is not None else 2)
+    fn = lib.dasr_conv2d_wgrad_bf16 if inp.t.dtype == torch.bfloat16 else lib.dasr_conv2d_wgrad_f32
+    if inp.t.dtype != dout.t.dtype:
+        raise _lib.DasrError('conv2d_wgrad: input and output-gradient dtypes differ')
+    check(fn(inp.ptr, dout.ptr, _p(dw), None, C.byref(p), int(accumulate), _p(ws), ws.numel(), _stream()), 'conv2d_wgrad', 2)
+    if db is not None:
+        bias_grad(dout, db, accumulate)
+
+
+def conv3x3_wgrad_tc(x, dy, dw, accumulate=False):
+    """tcgen05 filter gradient of a 3x3 s1 p1 conv: x, dy = Views of bf16 NHWC buffers (channels % 32 == 0), dw fp32 OIHW."""
+    x, dy = as_view(x), as_view(dy)
+    N, H, W, _ = x.t.shape
+    lib = _lib.load()
+    n = lib.dasr_conv3x3_wgrad_tc_workspace(N, H, W, x.c, dy.c)
+    ws = _workspace(n, x.t.device)
+    check(lib.dasr_conv3x3_wgrad_tc(x.ptr, x.cs, x.coff, dy.ptr, dy.cs, dy.coff, _p(dw), N, H, W, x.c, dy.c, int(accumulate),
+                                    _p(ws), ws.numel(), _stream()), 'conv3x3_wgrad_tc', 2)
+
+
+_bg_cache = {}
+
+
+def bias_grad(dy, db, accumulate=False):
+    dy = as_view(dy)
+    npix = dy.t.numel() // dy.cs
+    key = str(dy.t.device)
+    part = _bg_cache.get(key)
+    if part is None or part.numel() < 64 * dy.c:
+        part = _bg_cache[key] = torch.empty(64 * max(dy.c, 512), dtype=torch.float32, device=dy.t.device)
+    check(_lib.load().dasr_bias_grad(dy.ptr, _p(db), npix, dy.c, dy.cs, dy.coff, int(dy.t.dtype == torch.bfloat16),
+                                     int(accumulate), _p(part), _stream()), 'bias_grad', 2)
+
+
+def upsample2x_fwd(src, dst):
+    src, dst = as_view(src), as_view(dst)
+    N, H, W, _ = src.t.shape
+    check(_lib.load().dasr_upsample2x_fwd(src.ptr, dst.ptr, N, H, W, dst.c, src.cs, src.coff, dst.cs, dst.coff,
+                                          int(dst.t.dtype == torch.bfloat16), _stream()), 'upsample2x_fwd')
 
 
 def pack_filter_f32(w, for_dgrad=False):

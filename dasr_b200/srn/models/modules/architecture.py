@@ -75,7 +75,8 @@ class RRDBNet(nn.Module):
         ups = upsampler if isinstance(upsampler, list) else [upsampler]
         self.model = B.sequential(fea_conv, B.ShortcutBlock(B.sequential(*rb_blocks, LR_conv)), *ups, HR_conv0, HR_conv1)
         self.nb, self.nf, self.upscale = nb, nf, upscale
-        self.precision = None          # None: fp32 when grad is needed, DASR_B200_PRECISION / bf16 otherwise
+        self.precision = None          # inference: None -> DASR_B200_PRECISION or 'bf16' ('bf16' | 'bf16_layer' | 'fp32')
+        self.train_precision = None    # training:  None -> DASR_B200_TRAIN_PRECISION or 'fp32' ('fp32' | 'bf16')
         self._pack_cache = engine._PackCache()
         self._graphs = {}
 
@@ -83,6 +84,9 @@ class RRDBNet(nn.Module):
         params = list(self.parameters())
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if need_grad:
+            tp = self.train_precision or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')
+            if tp == 'bf16':      # mixed precision: tcgen05 fprop/dgrad, fp32-accumulated filter gradients
+                return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, *params)
             return engine.RRDBNetFunction.apply(x, self.nb, self.upscale, *params)
         prec = self.precision or _precision('bf16')
         if prec in ('bf16', 'bf16_layer'):

@@ -78,6 +78,23 @@ int dasr_conv2d_wgrad_f32(const float* in, const float* dout, float* dw_oihw, fl
                           const DasrConvF32Params* p, int accumulate, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Same filter gradient with bf16 NHWC activations / output gradients (mixed-precision training): fp32 accumulation,
+ * fp32 OIHW result.  Same params struct (strides in elements) and workspace query. */
+int dasr_conv2d_wgrad_bf16(const void* in_bf16, const void* dout_bf16, float* dw_oihw, float* dbias /*nullable*/,
+                           const DasrConvF32Params* p, int accumulate, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* tcgen05 filter gradient of a 3x3 s1 p1 conv on bf16 NHWC channel slices (cin, cout multiples of 32):
+ * dW[co][ci][dy][dx] (fp32 OIHW) = sum_pixels x[p + tap][ci] * dy[p][co], fp32 accumulation in TMEM, deterministic
+ * split-K reduction.  Replaces autograd's weight gradient of the RRDB convs (block.py:142-143, 262-278). */
+size_t dasr_conv3x3_wgrad_tc_workspace(int N, int H, int W, int cin, int cout);
+int dasr_conv3x3_wgrad_tc(const void* x_bf16, int x_cs, int x_coff, const void* dy_bf16, int dy_cs, int dy_coff,
+                          float* dw_oihw, int N, int H, int W, int cin, int cout, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* db[c] (+)= sum over pixels of dout[p][c] on an NHWC channel slice (fp32 or bf16); partials >= 64*C floats */
+int dasr_bias_grad(const void* dout, float* db, long npix, int C, int cs, int coff, int is_bf16, int accumulate,
+                   float* partials, void* stream);
+
 /* OIHW fp32 nn.Parameter -> packed [tap][cin][cout] fp32 (FWD) or the transposed/flipped-free
  * [tap][cout][cin] layout DGRAD mode consumes. */
 int dasr_pack_filter_f32(const float* w_oihw, float* w_packed, int cout, int cin, int kh, int kw,
@@ -171,6 +188,10 @@ int dasr_act_bwd(void* g, const void* y, long npix, int C, int g_cs, int g_coff,
 /* dst[n,y,x,c] = sum of the 2x2 block of src (backward of nn.Upsample(2,'nearest'), block.py:858) */
 int dasr_upsample2x_bwd(const void* src, void* dst, int N, int H, int W, int C, int src_cs,
                         int src_coff, int dst_cs, int dst_coff, int is_bf16, void* stream);
+/* dst[n,y,x,c] = src[n,y/2,x/2,c]: nn.Upsample(2,'nearest') materialised (only for the filter gradient of the
+ * upconv layers in mixed-precision training; the forward never materialises it) */
+int dasr_upsample2x_fwd(const void* src, void* dst, int N, int H, int W, int C, int src_cs, int src_coff, int dst_cs,
+                        int dst_coff, int is_bf16, void* stream);
 /* dst = a*x + b*y on channel slices (gradient accumulation across concat consumers) */
 int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff,
                int y_cs, int y_coff, int d_cs, int d_coff, float a, float b, int is_bf16, void* stream);
