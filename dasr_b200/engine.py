@@ -624,22 +624,64 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
     return None, grads
 
 
+class _TrainGraphs:
+    """CUDA graphs of the mixed-precision forward and backward of one RRDBNet for one input shape.  A training step
+    launches ~4000 small kernels for G alone (filter re-packing, 345 fused convs, dgrad/wgrad/bias-grad per conv);
+    replaying two graphs removes that host cost.  Filters are re-packed INSIDE the forward graph (the parameters
+    change every step, their addresses do not); activations live in the graphs' private pool."""
+
+    def __init__(self, x, params, nb, upscale):
+        self.params = params
+        self.x = x.detach().clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        plist = [p.detach() for p in params]
+        with torch.cuda.stream(side):            # eager warm-up: workspaces, function attributes, allocator
+            out, ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, _PackCache())
+            rrdb_backward_bf16(ctx, plist, torch.zeros_like(out), _PackCache())
+            del out, ctx
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd, pool=self.pool):
+            self.out, self.ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, _PackCache())
+        self.dout = torch.zeros_like(self.out)
+        self.bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd, pool=self.pool):
+            _, self.grads = rrdb_backward_bf16(self.ctx, plist, self.dout, _PackCache())
+        from . import _lib
+        self.launches = 0
+
+
 class RRDBNetFunctionBF16(torch.autograd.Function):
-    """Mixed-precision training node (tcgen05 fprop + dgrad, fp32-accumulated filter gradients)."""
+    """Mixed-precision training node (tcgen05 fprop + dgrad + wgrad); graphs = None runs eagerly."""
 
     @staticmethod
-    def forward(ctx, x, nb, upscale, cache, *params):
-        out, saved = rrdb_forward_bf16_train(x, [p.detach() for p in params], nb, upscale, cache)
-        ctx.saved, ctx.params, ctx.cache = saved, params, cache
+    def forward(ctx, x, nb, upscale, cache, graphs, *params):
         if x.requires_grad:
             raise ops._lib.DasrError('bf16 training mode does not return the input-image gradient; use precision fp32')
+        ctx.params, ctx.cache, ctx.graphs = params, cache, graphs
+        if graphs is not None:
+            graphs.x.copy_(x)
+            graphs.fwd.replay()
+            return graphs.out.clone()
+        out, saved = rrdb_forward_bf16_train(x, [p.detach() for p in params], nb, upscale, cache)
+        ctx.saved = saved
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        _, grads = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
-        ctx.saved = None
-        return (None, None, None, None) + tuple(g.to(p.dtype) for g, p in zip(grads, ctx.params))
+        g = ctx.graphs
+        if g is not None:
+            g.dout.copy_(dout)
+            g.bwd.replay()
+            grads = [t.clone() for t in g.grads]
+        else:
+            _, grads = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
+            ctx.saved = None
+        return (None, None, None, None, None) + tuple(gr.to(p.dtype) for gr, p in zip(grads, ctx.params))
 
 
 class RRDBNetFunction(torch.autograd.Function):

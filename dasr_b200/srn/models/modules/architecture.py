@@ -79,14 +79,22 @@ class RRDBNet(nn.Module):
         self.train_precision = None    # training:  None -> DASR_B200_TRAIN_PRECISION or 'fp32' ('fp32' | 'bf16')
         self._pack_cache = engine._PackCache()
         self._graphs = {}
+        self._train_graphs = {}
 
     def forward(self, x):
         params = list(self.parameters())
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if need_grad:
             tp = self.train_precision or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')
-            if tp == 'bf16':      # mixed precision: tcgen05 fprop/dgrad, fp32-accumulated filter gradients
-                return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, *params)
+            if tp == 'bf16':      # mixed precision: tcgen05 fprop / dgrad / wgrad, fp32 accumulation, fp32 filter gradients
+                graphs = None
+                if os.environ.get('DASR_B200_GRAPH', '1') != '0' and x.is_cuda and not x.requires_grad:
+                    key = (tuple(x.shape), x.device.index, id(params[0]))
+                    graphs = self._train_graphs.get(key)
+                    if graphs is None:
+                        self._train_graphs.clear()
+                        graphs = self._train_graphs[key] = engine._TrainGraphs(x.contiguous().float(), params, self.nb, self.upscale)
+                return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, graphs, *params)
             return engine.RRDBNetFunction.apply(x, self.nb, self.upscale, *params)
         prec = self.precision or _precision('bf16')
         if prec in ('bf16', 'bf16_layer'):
