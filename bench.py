@@ -236,6 +236,14 @@ def main():
         fea = torch.empty((BATCH, LR, LR, NF), dtype=bf, device=dev)
         buf = torch.empty((BATCH, LR, LR, 256), dtype=bf, device=dev)
         big = torch.empty((BATCH, 3, 4 * LR, 4 * LR), dtype=torch.float32, device=dev)
+        def _non_conv():
+            xin.zero_()
+            ops.nchw_to_nhwc(x_dev, ops.View(xin, 3, 0))
+            ops.axpby(fea, 1.0, None, 0.0, ops.View(buf, NF, 0))
+            big.clone()
+            x_dev.clone()
+        for _ in range(2):
+            _non_conv()                          # allocator warm-up
         torch.cuda.synchronize()
         n0 = _rec()
         for _ in range(K):
@@ -344,6 +352,9 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision
         model = create_model(opt)
     g = model.netG.module if hasattr(model.netG, 'module') else model.netG
     g.train_precision = precision
+    f = getattr(model, 'netF', None)
+    if f is not None:
+        (f.module if hasattr(f, 'module') else f).precision = precision
     rank = int(os.environ.get('RANK', 0))
     data = {'LR_real': O.synth_image((B, 3, h, h), 200 + rank).pin_memory(), 'LR_fake': O.synth_image((B, 3, h, h), 300 + rank).pin_memory(),
             'HR': O.synth_image((B, 3, 4 * h, 4 * h), 400 + rank).pin_memory(), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * h), 500 + rank).pin_memory(),

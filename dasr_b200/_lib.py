@@ -81,6 +81,8 @@ SYMBOLS = {
     'dasr_axpby': (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
     'dasr_maxpool2_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'dasr_maxpool2_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasr_maxpool2_fwd_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasr_maxpool2_bwd_bf16': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dasr_instnorm_lrelu_fwd': (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
     'dasr_instnorm_lrelu_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'dasr_haar_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

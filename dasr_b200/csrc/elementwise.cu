@@ -166,6 +166,65 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ in, const float* _
   }
 }
 
+// bf16 NHWC variants, 8 channels (16 B) per thread; first-max tie rule as above
+__global__ void maxpool2_fwd_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int C8) {
+  const int OH = H / 2, OW = W / 2;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  long total = (long)N * OH * OW * C8;
+  if (i >= total) return;
+  int c = (int)(i % C8);
+  long pp = i / C8;
+  int ox = (int)(pp % OW);
+  long r = pp / OW;
+  int oy = (int)(r % OH);
+  int n = (int)(r / OH);
+  long b = (((long)n * H + 2 * oy) * W + 2 * ox) * C8 + c;
+  uint4 v0 = in[b], v1 = in[b + C8], v2 = in[b + (long)W * C8], v3 = in[b + (long)W * C8 + C8];
+  const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&v0);
+  const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&v1);
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&v2);
+  const __nv_bfloat162* a3 = reinterpret_cast<const __nv_bfloat162*>(&v3);
+  uint4 o;
+  __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; k++) op[k] = __hmax2(__hmax2(a0[k], a1[k]), __hmax2(a2[k], a3[k]));
+  out[i] = o;
+}
+__global__ void maxpool2_bwd_bf16_kernel(const uint4* __restrict__ in, const uint4* __restrict__ out,
+                                         const uint4* __restrict__ dout, uint4* __restrict__ din, int N, int H, int W, int C8) {
+  const int OH = H / 2, OW = W / 2;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  long total = (long)N * OH * OW * C8;
+  if (i >= total) return;
+  int c = (int)(i % C8);
+  long pp = i / C8;
+  int ox = (int)(pp % OW);
+  long r = pp / OW;
+  int oy = (int)(r % OH);
+  int n = (int)(r / OH);
+  long b = (((long)n * H + 2 * oy) * W + 2 * ox) * C8 + c;
+  const long offs[4] = {0, (long)C8, (long)W * C8, (long)W * C8 + C8};
+  uint4 mv = out[i], gv = dout[i];
+  const unsigned short* m = reinterpret_cast<const unsigned short*>(&mv);
+  const unsigned short* g = reinterpret_cast<const unsigned short*>(&gv);
+  unsigned done = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint4 xv = in[b + offs[k]];
+    const unsigned short* x = reinterpret_cast<const unsigned short*>(&xv);
+    uint4 o;
+    unsigned short* op = reinterpret_cast<unsigned short*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      // values are finite relu outputs (>= 0), so bit equality is value equality except +-0 (both give gradient to one slot)
+      bool hit = !((done >> j) & 1u) && (__bfloat162float(__ushort_as_bfloat16(x[j])) == __bfloat162float(__ushort_as_bfloat16(m[j])));
+      op[j] = hit ? g[j] : (unsigned short)0;
+      done |= (hit ? 1u : 0u) << j;
+    }
+    din[b + offs[k]] = o;
+  }
+}
+
 // ---- InstanceNorm (biased var, eps, no affine) + LeakyReLU, NHWC fp32 ---------------------------
 // grid (C/32 , N), block (32 channels, 8 pixel lanes)
 __global__ void instnorm_lrelu_fwd_kernel(float* __restrict__ x, float* __restrict__ stats, int HW, int C, float eps,
@@ -573,6 +632,21 @@ int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, floa
   maxpool2_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, dout, din, N, H, W, C);
   return check_launch("maxpool2_bwd");
 }
+int dasr_maxpool2_fwd_bf16(const void* in, void* out, int N, int H, int W, int C, void* stream) {
+  DASR_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool2_bf16: H,W even, C%%8==0");
+  long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_fwd_bf16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  return check_launch("maxpool2_fwd_bf16");
+}
+int dasr_maxpool2_bwd_bf16(const void* in, const void* out, const void* dout, void* din, int N, int H, int W, int C,
+                           void* stream) {
+  DASR_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool2_bf16: H,W even, C%%8==0");
+  long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bwd_bf16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (const uint4*)out,
+                                                                              (const uint4*)dout, (uint4*)din, N, H, W, C / 8);
+  return check_launch("maxpool2_bwd_bf16");
+}
+
 
 int dasr_instnorm_lrelu_fwd(float* x, float* stats, int N, int HW, int C, float eps, float slope, void* stream) {
   DASR_REQUIRE(N > 0 && HW > 0 && C > 0, "instnorm: bad dims");

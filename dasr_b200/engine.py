@@ -17,7 +17,7 @@ import os
 import torch
 
 from . import ops
-from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, DGRAD, FWD, TC_FPROP, TC_UPCONV, View
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, DGRAD, FWD, TC_DGRAD, TC_FPROP, TC_UPCONV, View
 
 # optional profiling hook: bench.py sets this to a callable(tag) that records a CUDA event on the current stream
 PROFILE = None
@@ -235,6 +235,17 @@ def _pick_nt(cout, cin, ntaps=9):
     nt = cout
     while nt >= 16:
         if cout % nt == 0 and nt % 16 == 0 and ntaps * (cin // 32) * nt * 64 <= _TC_W_BUDGET:
+            return nt
+        nt //= 2
+    raise ops._lib.DasrError('conv_tc: no Cout tile fits shared memory for cin=%d cout=%d' % (cin, cout))
+
+
+def _pick_nt_staged(cout, cin, ntaps=9, min_stages=4):
+    """Largest Cout tile whose resident filters + staged-epilogue tiles (nt % 32 == 0) + min_stages halo stages fit."""
+    nt = min(cout, 256)
+    while nt >= 16:
+        epi = 2 * nt * 256 if nt % 32 == 0 else 0
+        if cout % nt == 0 and ntaps * (cin // 32) * nt * 64 + epi + min_stages * 12288 <= 220 * 1024:
             return nt
         nt //= 2
     raise ops._lib.DasrError('conv_tc: no Cout tile fits shared memory for cin=%d cout=%d' % (cin, cout))
@@ -882,6 +893,83 @@ def vgg_backward(ctx, params, std, dout, cache=None):
     inv_std = (1.0 / std.float()).contiguous() if std is not None else None
     ops.nhwc_to_nchw(g, dx, inv_std)                                    # d/dx of (x-mean)/std
     return dx
+
+
+def vgg_forward_bf16(x, params, mean, std, feature_layer=34, save=False, cache=None):
+    """VGG19 features on the tcgen05 conv (bf16 activations/filters, fp32 accumulate).  Filters of the 256/512-channel
+    layers do not fit shared memory whole, so those layers run as Cout/nt column tiles (grid.y) of 16..64 channels."""
+    _need_cuda(x, 'VGGFeatureExtractor')
+    plan = vgg_plan(feature_layer)
+    N, C0, H, W = x.shape
+    a = torch.zeros((N, H, W, 32), dtype=torch.bfloat16, device=x.device)
+    ops.nchw_to_nhwc(x.contiguous().float(), View(a, C0, 0), mean, std)
+    acts = [a]
+    pi = 0
+    h, w = H, W
+    for step in plan:
+        cur = acts[-1]
+        if step[0] == 'pool':
+            o = torch.empty((N, h // 2, w // 2, cur.shape[3]), dtype=torch.bfloat16, device=x.device)
+            ops.maxpool2_fwd(cur, o)
+            h, w = h // 2, w // 2
+        else:
+            wt, bs = params[pi], params[pi + 1]
+            key = pi
+            pi += 2
+            cin = cur.shape[3]
+            mk = lambda wt=wt, cin=cin: ops.pack_filter_tc(_pad_filter(wt, cin_to=cin), TC_FPROP)
+            pk = cache.get(('vtf', key), wt, mk) if cache is not None else mk()
+            o = torch.empty((N, h, w, wt.shape[0]), dtype=torch.bfloat16, device=x.device)
+            ops.conv_tc(cur, pk, bs, o, kind=TC_FPROP, nt=_pick_nt_staged(wt.shape[0], cin),
+                        act=ACT_RELU if step[1] else ACT_NONE)
+        acts.append(o)
+    Cf = acts[-1].shape[3]
+    out = _empty((N, Cf, h, w), x)
+    ops.nhwc_to_nchw(acts[-1], out)
+    ctx = dict(acts=acts, plan=plan, shape=(N, C0, H, W), bf16=True) if save else None
+    return out, ctx
+
+
+def vgg_backward_bf16(ctx, params, std, dout, cache=None):
+    acts, plan = ctx['acts'], ctx['plan']
+    N, C0, H, W = ctx['shape']
+    g = torch.empty_like(acts[-1])
+    ops.nchw_to_nhwc(dout.contiguous().float(), g)
+    pi = 2 * sum(1 for s in plan if s[0] == 'conv')
+    for li in reversed(range(len(plan))):
+        step = plan[li]
+        if step[0] == 'pool':
+            gin = torch.empty_like(acts[li])
+            ops.maxpool2_bwd(acts[li], acts[li + 1], g, gin)
+        else:
+            pi -= 2
+            wt = params[pi]
+            if step[1]:
+                ops.act_bwd(g, acts[li + 1], 0.0)
+            cin = acts[li].shape[3]
+            mk = lambda wt=wt, cin=cin: ops.pack_filter_tc(_pad_filter(wt, cin_to=cin), TC_DGRAD)
+            pk = cache.get(('vtd', pi), wt, mk) if cache is not None else mk()
+            gin = torch.empty_like(acts[li])
+            ops.conv_tc(g, pk, None, gin, kind=TC_DGRAD, nt=_pick_nt_staged(cin, wt.shape[0]))
+        g = gin
+    dx = _empty((N, C0, H, W), dout)
+    inv_std = (1.0 / std.float()).contiguous() if std is not None else None
+    ops.nhwc_to_nchw(View(g, C0, 0), dx, inv_std)
+    return dx
+
+
+class VGGFunctionBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, feature_layer, mean, std, cache, *params):
+        out, saved = vgg_forward_bf16(x, [p.detach() for p in params], mean, std, feature_layer, save=x.requires_grad, cache=cache)
+        ctx.saved, ctx.params, ctx.std, ctx.cache = saved, params, std, cache
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = vgg_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], ctx.std, dout, ctx.cache)
+        ctx.saved = None
+        return (dx, None, None, None, None) + (None,) * len(ctx.params)
 
 
 class VGGFunction(torch.autograd.Function):

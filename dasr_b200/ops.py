@@ -276,11 +276,16 @@ def axpby(x, a, y, b, dst):
 
 def maxpool2_fwd(x, out):
     N, H, W, Cc = x.shape
+    if x.dtype == torch.bfloat16:
+        return check(_lib.load().dasr_maxpool2_fwd_bf16(_p(x), _p(out), N, H, W, Cc, _stream()), 'maxpool2_fwd_bf16')
     check(_lib.load().dasr_maxpool2_fwd(_p(x), _p(out), N, H, W, Cc, _stream()), 'maxpool2_fwd')
 
 
 def maxpool2_bwd(x, out, dout, din):
     N, H, W, Cc = x.shape
+    if x.dtype == torch.bfloat16:
+        return check(_lib.load().dasr_maxpool2_bwd_bf16(_p(x), _p(out), _p(dout), _p(din), N, H, W, Cc, _stream()),
+                     'maxpool2_bwd_bf16')
     check(_lib.load().dasr_maxpool2_bwd(_p(x), _p(out), _p(dout), _p(din), N, H, W, Cc, _stream()), 'maxpool2_bwd')
 
 

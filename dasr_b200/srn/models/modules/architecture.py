@@ -174,6 +174,7 @@ class VGGFeatureExtractor(nn.Module):
         for _, v in self.features.named_parameters():
             v.requires_grad = False
         self._pack_cache = engine._PackCache()
+        self.precision = None          # None -> DASR_B200_TRAIN_PRECISION or 'fp32'; 'bf16' = tcgen05 convs
 
     def _load_pretrained(self, weights):
         sd = None
@@ -196,7 +197,9 @@ class VGGFeatureExtractor(nn.Module):
         params = list(self.features.parameters())
         mean = self.mean.view(-1).contiguous() if self.use_input_norm else None
         std = self.std.view(-1).contiguous() if self.use_input_norm else None
-        return engine.VGGFunction.apply(x, self.feature_layer, mean, std, self._pack_cache, *params)
+        prec = self.precision or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')
+        fn = engine.VGGFunctionBF16 if prec == 'bf16' else engine.VGGFunction
+        return fn.apply(x, self.feature_layer, mean, std, self._pack_cache, *params)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -199,6 +199,10 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
 int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H,
                       int W, int C, void* stream);
+/* the same on NHWC bf16 (C % 8 == 0) for the tensor-core VGG path */
+int dasr_maxpool2_fwd_bf16(const void* in, void* out, int N, int H, int W, int C, void* stream);
+int dasr_maxpool2_bwd_bf16(const void* in, const void* out, const void* dout, void* din, int N, int H,
+                           int W, int C, void* stream);
 
 /* InstanceNorm2d(affine=False, eps) + LeakyReLU(slope), NHWC fp32, in place on x.
  * Replaces architecture.py:1005-1007,1013-1015.  stats[n][c][2] = (mean, rstd). */

@@ -178,6 +178,59 @@ def test_vgg19_vs_golden(golden):
     assert rel_linf(x.grad, g['dx']) < FP32_TOL
 
 
+def test_vgg19_bf16_tensor_core_path_vs_golden(golden):
+    """Mixed-precision perceptual-loss network (tcgen05 convs, bf16 activations): features and input gradient
+    against the fp32 reference within bf16 tolerances (rel-L2; 16 stacked bf16 layers)."""
+    from dasr_b200.srn.models.modules.architecture import VGGFeatureExtractor
+    g = golden('vgg19.pt')
+    sd = O.synth_state_dict(O.vgg19_shapes(34), g['w_seed'], 1.0)
+    net = VGGFeatureExtractor(feature_layer=34, weights=sd).cuda()
+    net.precision = 'bf16'
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert out.shape == g['out'].shape
+
+    def rel_l2(a, b):
+        return float((a.detach().float().cpu() - b).norm() / b.norm())
+    e_f = rel_l2(out, g['out'])
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    e_g = rel_l2(x.grad, g['dx'])
+    cos = float(torch.nn.functional.cosine_similarity(x.grad.cpu().flatten(), g['dx'].flatten(), dim=0))
+    print('vgg bf16: feature rel-L2 %.3e  dx rel-L2 %.3e  cos %.4f' % (e_f, e_g, cos))
+    # The input gradient of a ReLU/max-pool stack is piecewise constant: every pre-activation within bf16 rounding of
+    # zero flips its mask (~0.3 % of the elements per layer -> ~4 % rel-L2 per layer, 16 layers + 4 pools in
+    # quadrature ~ 0.3).  It is the exact gradient of the bf16 network; the kernels themselves are checked
+    # tightly in test_conv_tc_wide_channel_tiles.
+    assert e_f < 3e-2 and e_g < 0.45 and cos > 0.9
+
+
+@pytest.mark.parametrize('cin,cout,h,w', [(64, 128, 20, 12), (256, 256, 9, 17), (512, 512, 8, 8), (32, 64, 16, 8)])
+def test_conv_tc_wide_channel_tiles(cin, cout, h, w):
+    """tcgen05 fprop / dgrad with the filters split in Cout tiles (VGG19 widths) against torch fp32 convs on the
+    same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from dasr_b200 import engine, ops
+    N = 3
+    x = O.synth((N, cin, h, w), 11, 1.0).bfloat16().float()
+    wt = O.synth((cout, cin, 3, 3), 12, 1.0 / (3.0 * cin ** 0.5)).bfloat16().float()
+    b = O.synth((cout,), 13, 0.1)
+    ref = F.relu(F.conv2d(x, wt, b, padding=1))
+    xd = x.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    od = torch.empty((N, h, w, cout), dtype=torch.bfloat16, device='cuda')
+    ops.conv_tc(xd, ops.pack_filter_tc(wt.cuda(), ops.TC_FPROP), b.cuda(), od, kind=ops.TC_FPROP,
+                nt=engine._pick_nt_staged(cout, cin), act=ops.ACT_RELU)
+    got = od.float().permute(0, 3, 1, 2).cpu()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-2
+    gy = O.synth((N, cout, h, w), 14, 1.0).bfloat16().float()
+    gref = F.conv_transpose2d(gy, wt, padding=1)
+    gd = gy.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    gi = torch.empty((N, h, w, cin), dtype=torch.bfloat16, device='cuda')
+    ops.conv_tc(gd, ops.pack_filter_tc(wt.cuda(), ops.TC_DGRAD), None, gi, kind=ops.TC_DGRAD,
+                nt=engine._pick_nt_staged(cin, cout))
+    got = gi.float().permute(0, 3, 1, 2).cpu()
+    assert float((got - gref).abs().max() / gref.abs().max()) < 1e-2
+
+
 # ------------------------------------------------------------------------ filters / haar / losses
 def test_filters_haar_bilinear_losses(golden):
     from dasr_b200 import ops
