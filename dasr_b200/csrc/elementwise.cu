@@ -78,6 +78,91 @@ __global__ void act_bwd_kernel(T* __restrict__ g, const T* __restrict__ y, long 
   }
 }
 
+// bf16 slices with C, cs, coff all multiples of 8: one 16-byte vector (8 channels) per thread
+__device__ __forceinline__ void bf8_to_f(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_bf8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; k++) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return v;
+}
+__global__ void act_bwd_bf16x8_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, long npix, int C8,
+                                      int g_cs, int g_coff, int y_cs, int y_coff, float slope) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C8) return;
+  long pp = i / C8;
+  int c = (int)(i - pp * C8) * 8;
+  const uint4 yv = *reinterpret_cast<const uint4*>(y + pp * y_cs + y_coff + c);
+  uint4* gp = reinterpret_cast<uint4*>(g + pp * g_cs + g_coff + c);
+  float yf[8], gf[8];
+  bf8_to_f(yv, yf);
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 8; k++) any |= !(yf[k] > 0.f);
+  if (!any) return;
+  bf8_to_f(*gp, gf);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    // same arithmetic as the scalar kernel: untouched lanes keep their bits, masked lanes are g*slope rounded once
+    if (!(yf[k] > 0.f)) gf[k] *= slope;
+  }
+  *gp = f_to_bf8(gf);
+}
+__global__ void axpby_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                                    __nv_bfloat16* __restrict__ d, long npix, int C8, int x_cs, int x_coff, int y_cs,
+                                    int y_coff, int d_cs, int d_coff, float a, float b) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C8) return;
+  long pp = i / C8;
+  int c = (int)(i - pp * C8) * 8;
+  float xf[8], yf[8];
+  bf8_to_f(*reinterpret_cast<const uint4*>(x + pp * x_cs + x_coff + c), xf);
+  if (y) {
+    bf8_to_f(*reinterpret_cast<const uint4*>(y + pp * y_cs + y_coff + c), yf);
+#pragma unroll
+    for (int k = 0; k < 8; k++) xf[k] = a * xf[k] + b * yf[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) xf[k] = a * xf[k];
+  }
+  *reinterpret_cast<uint4*>(d + pp * d_cs + d_coff + c) = f_to_bf8(xf);
+}
+// bias gradient partials, bf16 vector form: block = (C/8 channel lanes) x (256/(C/8) pixel lanes), grid = nblk
+__global__ void bias_grad_partial_bf16x8_kernel(const __nv_bfloat16* __restrict__ d, float* __restrict__ part, long npix,
+                                                int C, int cs, int coff, long pix_per_block) {
+  extern __shared__ float sh[];                 // [plane][C]
+  const int C8 = C / 8;
+  const int lane = threadIdx.x % C8, plane = threadIdx.x / C8, nplane = blockDim.x / C8;
+  const long p0 = (long)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (plane < nplane) {
+#pragma unroll 4
+    for (long pp = p0 + plane; pp < p1; pp += nplane) {
+      float f[8];
+      bf8_to_f(*reinterpret_cast<const uint4*>(d + pp * cs + coff + lane * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sh[plane * C + lane * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < nplane; k++) t += sh[k * C + c];
+    part[(long)blockIdx.x * C + c] = t;
+  }
+}
+
 template <typename T>
 __global__ void upsample2x_bwd_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C,
                                       int src_cs, int src_coff, int dst_cs, int dst_coff) {
@@ -554,7 +639,11 @@ int dasr_act_bwd(void* g, const void* y, long npix, int C, int g_cs, int g_coff,
                  int is_bf16, void* stream) {
   DASR_REQUIRE(npix > 0 && C > 0, "act_bwd: bad dims");
   long total = npix * C;
-  if (is_bf16)
+  if (is_bf16 && C % 8 == 0 && g_cs % 8 == 0 && g_coff % 8 == 0 && y_cs % 8 == 0 && y_coff % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
+    act_bwd_bf16x8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)g, (const __nv_bfloat16*)y, npix, C / 8, g_cs, g_coff, y_cs, y_coff, slope);
+  else if (is_bf16)
     act_bwd_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)g, (const __nv_bfloat16*)y, npix, C, g_cs, g_coff, y_cs, y_coff, slope);
   else
@@ -593,7 +682,14 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
                int d_cs, int d_coff, float a, float b, int is_bf16, void* stream) {
   DASR_REQUIRE(npix > 0 && C > 0 && x && dst, "axpby: bad arguments");
   long total = npix * C;
-  if (is_bf16)
+  const bool vec = is_bf16 && C % 8 == 0 && x_cs % 8 == 0 && x_coff % 8 == 0 && d_cs % 8 == 0 && d_coff % 8 == 0 &&
+                   (!y || (y_cs % 8 == 0 && y_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)) &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (vec)
+    axpby_bf16x8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C / 8, x_cs, x_coff, y_cs, y_coff, d_cs,
+        d_coff, a, b);
+  else if (is_bf16)
     axpby_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs,
         d_coff, a, b);
@@ -611,7 +707,15 @@ int dasr_bias_grad(const void* dout, float* db, long npix, int C, int cs, int co
   long ppb = (npix + nblk - 1) / nblk;
   dim3 grid(cdiv(C, 32), (unsigned)nblk), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (is_bf16)
+  if (is_bf16 && C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && cs % 8 == 0 && coff % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
+    nblk = (npix + 255) / 256;
+    if (nblk > 64) nblk = 64;
+    ppb = (npix + nblk - 1) / nblk;
+    const int nplane = 256 / (C / 8);
+    bias_grad_partial_bf16x8_kernel<<<(unsigned)nblk, 256, (size_t)nplane * C * sizeof(float), st>>>(
+        (const __nv_bfloat16*)dout, partials, npix, C, cs, coff, ppb);
+  } else if (is_bf16)
     bias_grad_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dout, partials, npix, C, cs, coff, ppb);
   else
     bias_grad_partial_kernel<float><<<grid, block, 0, st>>>((const float*)dout, partials, npix, C, cs, coff, ppb);

@@ -23,6 +23,9 @@ class DWTForward(nn.Module):
         hh = (a - b - c + d) * 0.5
         return ll, [torch.stack((lh, hl, hh), dim=2)]
 
+    def cuda(self, device=None):      # DSN/loss.py:103 calls .cuda() unconditionally; the stand-in has no state
+        return self
+
 
 class DWTInverse(nn.Module):
     def __init__(self, wave='haar', mode='zero'):
