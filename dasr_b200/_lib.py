@@ -94,6 +94,11 @@ SYMBOLS = {
     'dasr_mse_loss': (_i, [_vp, _vp, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_bce_logits_loss': (_i, [_vp, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_mean': (_i, [_vp, _vp, _l, _vp, _vp]),
+    'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
+    'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
+    'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),
+    'dasr_sigmoid_fwd': (_i, [_vp, _vp, _l, _vp]),
+    'dasr_sigmoid_bwd': (_i, [_vp, _vp, _vp, _l, _vp]),
 }
 
 

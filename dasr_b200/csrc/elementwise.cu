@@ -532,6 +532,25 @@ __global__ void bilinear_kernel(const float* __restrict__ src, float* __restrict
   dst[i] = v;
 }
 
+// ---- PReLU (one learnable slope, nn.PReLU() default) and sigmoid, fp32 elementwise (DSN/model.py:28-29,55) -------
+__global__ void prelu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope, float* __restrict__ y, long n) {
+  const float a = *slope;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = z[i];
+    y[i] = v > 0.f ? v : a * v;
+  }
+}
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = 1.f / (1.f + expf(-x[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = y[i];
+    dx[i] = dy[i] * v * (1.f - v);
+  }
+}
+
 // ---- losses ---------------------------------------------------------------------------------------
 constexpr int RED_BLOCKS = 512, RED_THREADS = 256;
 
@@ -554,7 +573,31 @@ __global__ void final_sum_kernel(const float* __restrict__ part, float* __restri
   v = block_sum(v);
   if (threadIdx.x == 0) *out = v * scale;
 }
+__global__ void final_acc_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int accumulate) {
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = block_sum(v);
+  if (threadIdx.x == 0) *out = accumulate ? *out + v : v;
+}
+// dz = dy * (z > 0 ? 1 : a);  part[block] = sum_{z <= 0} dy * z   (ATen prelu backward)
+__global__ void prelu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dy, const float* __restrict__ slope,
+                                 float* __restrict__ dz, float* __restrict__ part, long n) {
+  const float a = *slope;
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = z[i], g = dy[i];
+    if (v > 0.f) {
+      dz[i] = g;
+    } else {
+      dz[i] = a * g;
+      acc += g * v;
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
 // kind 0: w*|a-b| (w nullable)   1: (a-b)^2   2: bce_with_logits(a, target)   3: a
+//      4: -log(a + eps)   5: -log(1 - a + eps)   (eps passed in `target`; DSN/loss.py:11-41)
 __global__ void loss_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                     const float* __restrict__ w, float* __restrict__ part, float* __restrict__ grad,
                                     float gscale, long n, int C, long HW, int kind, float target) {
@@ -580,6 +623,12 @@ __global__ void loss_partial_kernel(const float* __restrict__ a, const float* __
       // max(x,0) - x*t + log1p(exp(-|x|))   (ATen binary_cross_entropy_with_logits)
       val = fmaxf(av, 0.f) - av * target + log1pf(expf(-fabsf(av)));
       g = 1.f / (1.f + expf(-av)) - target;
+    } else if (kind == 4) {
+      val = -logf(av + target);
+      g = -1.f / (av + target);
+    } else if (kind == 5) {
+      val = -logf(1.f - av + target);
+      g = 1.f / (1.f - av + target);
     } else {
       val = av;
     }
@@ -817,6 +866,41 @@ int dasr_mse_loss(const float* a, const float* b, float* loss, float* grad_a, fl
 int dasr_bce_logits_loss(const float* x, float target, float* loss, float* grad_x, float gscale, long n,
                          float* partials, void* stream) {
   return run_loss(x, nullptr, nullptr, loss, grad_x, gscale / (float)n, n, 1, 1, 2, target, partials, stream);
+}
+int dasr_log_loss(const float* x, int one_minus, float eps, float* loss, float* grad_x, float gscale, long n,
+                  float* partials, void* stream) {
+  return run_loss(x, nullptr, nullptr, loss, grad_x, gscale / (float)n, n, 1, 1, one_minus ? 5 : 4, eps, partials, stream);
+}
+int dasr_prelu_fwd(const float* z, const float* slope, float* y, long n, void* stream) {
+  DASR_REQUIRE(z && slope && y && n > 0, "prelu_fwd: bad arguments");
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  prelu_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, slope, y, n);
+  return check_launch("prelu_fwd");
+}
+int dasr_prelu_bwd(const float* z, const float* dy, const float* slope, float* dz, float* dslope, int accumulate, long n,
+                   float* partials, void* stream) {
+  DASR_REQUIRE(z && dy && slope && dz && dslope && partials && n > 0, "prelu_bwd: bad arguments");
+  int blocks = (int)((n + RED_THREADS - 1) / RED_THREADS);
+  if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+  cudaStream_t st = (cudaStream_t)stream;
+  prelu_bwd_kernel<<<blocks, RED_THREADS, 0, st>>>(z, dy, slope, dz, partials, n);
+  final_acc_kernel<<<1, 256, 0, st>>>(partials, dslope, blocks, accumulate);
+  return check_launch("prelu_bwd");
+}
+int dasr_sigmoid_fwd(const float* x, float* y, long n, void* stream) {
+  DASR_REQUIRE(x && y && n > 0, "sigmoid_fwd: bad arguments");
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  sigmoid_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  return check_launch("sigmoid_fwd");
+}
+int dasr_sigmoid_bwd(const float* y, const float* dy, float* dx, long n, void* stream) {
+  DASR_REQUIRE(y && dy && dx && n > 0, "sigmoid_bwd: bad arguments");
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  sigmoid_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+  return check_launch("sigmoid_bwd");
 }
 int dasr_mean(const float* x, float* out, long n, float* partials, void* stream) {
   return run_loss(x, nullptr, nullptr, out, nullptr, 0.f, n, 1, 1, 3, 0.f, partials, stream);

@@ -823,10 +823,18 @@ class NLayerDFunction(torch.autograd.Function):
 VGG19_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512, 'M']
 
 
+VGG16_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M']
+VGG_CFGS = {'vgg19': VGG19_CFG, 'vgg16': VGG16_CFG}
+
+
 def vgg_plan(feature_layer):
-    """[('conv', relu?) | ('pool',)] for torchvision vgg19.features[:feature_layer+1]."""
+    """[('conv', relu?) | ('pool',)] for torchvision vgg19.features[:feature_layer+1]; feature_layer may also be
+    ('vgg16' | 'vgg19', last index) — DSN's perceptual loss uses vgg16.features[:31] (DSN/loss.py:121)."""
+    arch = 'vgg19'
+    if isinstance(feature_layer, tuple):
+        arch, feature_layer = feature_layer
     plan, idx = [], 0
-    for v in VGG19_CFG:
+    for v in VGG_CFGS[arch]:
         if idx > feature_layer:
             break
         if v == 'M':

@@ -343,3 +343,29 @@ def bce_logits_loss(x, target, loss, grad, gscale):
 
 def mean(x, out):
     check(_lib.load().dasr_mean(_p(x), _p(out), x.numel(), _p(_partials(x.device)), _stream()), 'mean', 2)
+
+
+def log_loss(x, one_minus, eps, loss, grad, gscale):
+    check(_lib.load().dasr_log_loss(_p(x), int(one_minus), float(eps), _p(loss), _p(grad), gscale, x.numel(),
+                                    _p(_partials(x.device)), _stream()), 'log_loss', 2)
+
+
+# --------------------------------------------------------------------------------------------------
+# DSN elementwise (PReLU with one slope, sigmoid)
+# --------------------------------------------------------------------------------------------------
+
+def prelu_fwd(z, slope, y):
+    check(_lib.load().dasr_prelu_fwd(_p(z), _p(slope), _p(y), z.numel(), _stream()), 'prelu_fwd')
+
+
+def prelu_bwd(z, dy, slope, dz, dslope, accumulate=False):
+    check(_lib.load().dasr_prelu_bwd(_p(z), _p(dy), _p(slope), _p(dz), _p(dslope), int(accumulate), z.numel(),
+                                     _p(_partials(z.device)), _stream()), 'prelu_bwd', 2)
+
+
+def sigmoid_fwd(x, y):
+    check(_lib.load().dasr_sigmoid_fwd(_p(x), _p(y), x.numel(), _stream()), 'sigmoid_fwd')
+
+
+def sigmoid_bwd(y, dy, dx):
+    check(_lib.load().dasr_sigmoid_bwd(_p(y), _p(dy), _p(dx), y.numel(), _stream()), 'sigmoid_bwd')

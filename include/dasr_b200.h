@@ -246,6 +246,19 @@ int dasr_mse_loss(const float* a, const float* b, float* loss, float* grad_a, fl
 int dasr_bce_logits_loss(const float* x, float target, float* loss, float* grad_x, float gscale, long n,
                          float* partials, void* stream);
 int dasr_mean(const float* x, float* out, long n, float* partials, void* stream);
+/* DSN adversarial log losses on sigmoid scores (DSN/loss.py:11-41): mean(-log(x + eps)) or, one_minus != 0,
+ * mean(-log(1 - x + eps)); gradient as above. */
+int dasr_log_loss(const float* x, int one_minus, float eps, float* loss, float* grad_x, float gscale, long n,
+                  float* partials, void* stream);
+
+/* nn.PReLU() with ONE learnable slope read from device memory (DSN/model.py:28-29,38-41,217-223): y = z > 0 ? z : a*z.
+ * bwd: dz = dy * (z > 0 ? 1 : a); *dslope (+)= sum_{z <= 0} dy * z (two-stage, `partials` >= 1024 floats). */
+int dasr_prelu_fwd(const float* z, const float* slope, float* y, long n, void* stream);
+int dasr_prelu_bwd(const float* z, const float* dy, const float* slope, float* dz, float* dslope, int accumulate,
+                   long n, float* partials, void* stream);
+/* torch.sigmoid fwd / bwd (dx = dy * y * (1 - y)), fp32 (DSN/model.py:55,103) */
+int dasr_sigmoid_fwd(const float* x, float* y, long n, void* stream);
+int dasr_sigmoid_bwd(const float* y, const float* dy, float* dx, long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -139,3 +139,20 @@ def test_grad_bucket_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all('ok' in o for o in outs)
+
+
+def test_dsn_modules_match_reference_state_dict_layout():
+    """De_resnet / Discriminator(FSD) expose the reference's state_dict keys and shapes (DSN/model.py), and a CPU
+    tensor is refused loudly (no CPU fallback on the product path)."""
+    import pytest
+    import torch
+    from oracle import dsn_oracle as D
+    from dasr_b200._lib import DasrError
+    from dasr_b200.dsn.model import De_resnet, Discriminator
+    net = De_resnet(n_res_blocks=8, scale=4)
+    shapes = D.de_resnet_shapes(8, 4)
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == list(shapes.items())
+    d = Discriminator(kernel_size=5, D_arch='FSD', norm_layer='Instance', filter_type='wavelet', cs='cat')
+    assert [(k, tuple(v.shape)) for k, v in d.state_dict().items()] == list(D.fsd_shapes(9).items())
+    with pytest.raises(DasrError):
+        net(torch.zeros(1, 3, 16, 16))
