@@ -277,10 +277,11 @@ def main():
     torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- train step (configs[2]), fp32 kernels
-    train = None
+    train = dsn = None
     if args.train_steps > 0:
         train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'bf16')
         train['fp32_mode'] = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'fp32')
+        dsn = bench_dsn(args, dev, rank, world, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -315,6 +316,8 @@ def main():
     }
     if train:
         line['train'] = train
+    if dsn:
+        line['dsn'] = dsn
     if not args.no_cpu_baseline and world == 1:
         threads = pick_threads()
         mp_s, dt = cpu_reference_forward(1, LR, threads, 1, 0)
@@ -378,12 +381,68 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision
     ms = max_over_ranks(e0.elapsed_time(e1) / args.train_steps)
     res = {'metric': 'DASR SRN train iterations/sec (G + patch-D + VGG19 perceptual + weighted L1, Adam x2)',
            'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps,
-           'dtype': 'f32' if precision == 'fp32' else 'bf16 (G: tcgen05 fprop+dgrad, fp32-accumulated wgrad; D, VGG19, losses fp32)',
+           'dtype': 'f32' if precision == 'fp32' else 'bf16 (G and VGG19: tcgen05 fprop+dgrad, G wgrad tcgen05 with fp32 accumulation; D, losses, Adam fp32)',
            'config': {'workload': 'BASELINE configs[2]: batch 32 (2B=64 LR 32x32 through G), HR crop 128, fs wavelet, per GPU',
                       'global_batch': 32 * world, 'parallelism': 'dp%d, one flat-bucket NCCL all-reduce of G+D grads per step' % world},
            'gpu_launches_per_step': (_lib.LAUNCHES - l0) // args.train_steps,
            'loss_l_g_pix': log.get('loss/l_g_pix')}
     del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, dp_sync=None):
+    """BASELINE configs[4]: DSN DeResnet + wavelet-cat FS discriminator GAN iteration, batch 8, crop 256, per GPU."""
+    import warnings
+    import torch
+    from dasr_b200 import _lib
+    from dasr_b200.dsn.loss import GeneratorLoss
+    from dasr_b200.dsn.model import De_resnet, Discriminator
+    from dasr_b200.dsn.train import train_iteration
+    from oracle import srn_oracle as O
+    import contextlib
+    import io
+    torch.manual_seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter('ignore')
+        mg = De_resnet(n_res_blocks=8, scale=4).to(dev)
+        md = Discriminator(kernel_size=5, D_arch='FSD', norm_layer='Instance', filter_type='wavelet', cs='cat').to(dev)
+        gl = GeneratorLoss(per_type='VGG', filter='wavelet', kernel_size=5, w_col=1, w_tex=0.005, w_per=0.01, wgan=False).to(dev)
+    og = torch.optim.Adam(mg.parameters(), lr=1e-4, betas=[0.5, 0.999])
+    od = torch.optim.Adam(md.parameters(), lr=1e-4, betas=[0.5, 0.999])
+    B = 8
+    inp = O.synth_image((B, 3, 256, 256), 700 + rank).to(dev)
+    bic = O.synth_image((B, 3, 64, 64), 800 + rank).to(dev)
+    dis = O.synth_image((B, 3, 64, 64), 900 + rank).to(dev)
+    sync = None
+    if world > 1:
+        import torch.distributed as dist
+        plist = [p for p in list(mg.parameters()) + list(md.parameters()) if p.requires_grad]
+
+        def sync():
+            flat = torch.cat([p.grad.reshape(-1) for p in plist])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for p in plist:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+    for _ in range(2):
+        train_iteration(mg, md, gl, og, od, inp, bic, dis, grad_sync=sync, log=False)
+    barrier()
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        train_iteration(mg, md, gl, og, od, inp, bic, dis, grad_sync=sync, log=False)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.train_steps)
+    res = {'metric': 'DSN train iterations/sec (De_resnet + FS discriminator + VGG16 perceptual + LL colour loss, Adam x2)',
+           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps, 'dtype': 'f32',
+           'config': {'workload': 'BASELINE configs[4]: batch 8, crop 256 -> 64, wavelet cat, per GPU', 'global_batch': B * world},
+           'gpu_launches_per_step': (_lib.LAUNCHES - l0) // args.train_steps}
+    del mg, md, gl
     torch.cuda.empty_cache()
     return res
 

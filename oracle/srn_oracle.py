@@ -252,7 +252,7 @@ def filter_low(x, k=5, gaussian=True, include_pad=True):
     """FilterLow.forward, architecture.py:1208-1224 (recursions=1, stride 1, pad (k-1)//2)."""
     pad = int((k - 1) / 2)
     if gaussian:
-        w = gaussian_taps(k).view(1, 1, k, k).repeat(x.shape[1], 1, 1, 1)
+        w = gaussian_taps(k).view(1, 1, k, k).repeat(x.shape[1], 1, 1, 1).to(x.dtype)
         return F.conv2d(x, w, None, stride=1, padding=pad, groups=x.shape[1])
     return F.avg_pool2d(x, k, 1, pad, count_include_pad=include_pad)
 
