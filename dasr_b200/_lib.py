@@ -50,6 +50,13 @@ class ConvTcParams(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """DasrPackJob (include/dasr_b200.h)"""
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('cout', C.c_int), ('cin', C.c_int), ('kind', C.c_int),
+                ('ci_lo', C.c_int), ('ci_n', C.c_int), ('cout_rows', C.c_int), ('k_pad', C.c_int), ('dst_rows', C.c_int),
+                ('dst_row_off', C.c_int), ('reserved', C.c_int)]
+
+
 class PipeArgs(C.Structure):
     _fields_ = [('grid_x', C.c_int), ('dep0', C.c_void_p), ('dep0_g', C.c_int), ('dep1', C.c_void_p), ('dep1_g', C.c_int),
                 ('progress', C.c_void_p)]
@@ -94,6 +101,7 @@ SYMBOLS = {
     'dasr_mse_loss': (_i, [_vp, _vp, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_bce_logits_loss': (_i, [_vp, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_mean': (_i, [_vp, _vp, _l, _vp, _vp]),
+    'dasr_pack_filter_tc_batch': (_i, [_vp, _i, _i, _vp]),
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
     'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),

@@ -728,6 +728,50 @@ __global__ void pack_filter_tc_kernel(const float* __restrict__ w, __nv_bfloat16
   o[i] = __float2bfloat16(v);
 }
 
+// Batched form: one launch re-packs every filter of a network from a device-resident job table (training re-packs
+// all filters every step; ~850 tiny launches per generator step otherwise).  A job reads input channels
+// [ci_lo, ci_lo + ci_n) of an OIHW fp32 filter (zero beyond its real extents) and writes rows
+// [dst_row_off, dst_row_off + rows) of a packed tensor whose Cout dimension is dst_rows (stacked filters of the
+// dense-block N-fused launches).  kind 3 copies `cout` fp32 values (bias prefix of a zero-initialised vector).
+__global__ void pack_filter_tc_batch_kernel(const DasrPackJob* __restrict__ jobs) {
+  const DasrPackJob j = jobs[blockIdx.y];
+  if (j.kind == 3) {
+    float* d = reinterpret_cast<float*>(j.dst);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < j.cout; i += (long)gridDim.x * blockDim.x) d[i] = j.src[i];
+    return;
+  }
+  const int rows = (j.kind == 1) ? j.ci_n : j.cout_rows;      // GEMM-N rows this job writes
+  const int gk = (j.kind == 1) ? j.k_pad : j.ci_n;            // GEMM-K channels (multiple of 32)
+  const int nvar = (j.kind == 2) ? 4 : 1, ntaps = (j.kind == 2) ? 4 : 9, nchunks = gk / CHUNK;
+  const long total = (long)nvar * ntaps * nchunks * rows * CHUNK;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(j.dst);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int kc = (int)(i % CHUNK);
+    long r = i / CHUNK;
+    int nn = (int)(r % rows); r /= rows;
+    int c = (int)(r % nchunks); r /= nchunks;
+    int tap = (int)(r % ntaps);
+    int var = (int)(r / ntaps);
+    int kk = c * CHUNK + kc;
+    float v = 0.f;
+    if (j.kind == 0) {
+      if (nn < j.cout && j.ci_lo + kk < j.cin) v = j.src[((long)nn * j.cin + j.ci_lo + kk) * 9 + tap];
+    } else if (j.kind == 1) {
+      int dy = tap / 3, dx = tap % 3;
+      if (kk < j.cout && j.ci_lo + nn < j.cin) v = j.src[((long)kk * j.cin + j.ci_lo + nn) * 9 + (2 - dy) * 3 + (2 - dx)];
+    } else {
+      int py = var >> 1, px = var & 1, ta = tap >> 1, tb = tap & 1;
+      int r0, r1, c0, c1;
+      if (py == 0) { r0 = ta ? 1 : 0; r1 = ta ? 2 : 0; } else { r0 = ta ? 2 : 0; r1 = ta ? 2 : 1; }
+      if (px == 0) { c0 = tb ? 1 : 0; c1 = tb ? 2 : 0; } else { c0 = tb ? 2 : 0; c1 = tb ? 2 : 1; }
+      if (nn < j.cout && j.ci_lo + kk < j.cin)
+        for (int rr = r0; rr <= r1; rr++)
+          for (int cc = c0; cc <= c1; cc++) v += j.src[((long)nn * j.cin + j.ci_lo + kk) * 9 + rr * 3 + cc];
+    }
+    o[(((long)var * ntaps + tap) * nchunks + c) * j.dst_rows * CHUNK + (long)(j.dst_row_off + nn) * CHUNK + kc] = __float2bfloat16(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -895,6 +939,13 @@ int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, vo
   long total = (long)dasr_pack_filter_tc_bytes(cout, cin, kind) / 2;
   pack_filter_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)o, cout, cin, kind);
   return check_launch("pack_filter_tc");
+}
+
+int dasr_pack_filter_tc_batch(const DasrPackJob* jobs_dev, int njobs, int blocks_per_job, void* stream) {
+  DASR_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && blocks_per_job > 0, "pack_filter_tc_batch: bad arguments");
+  dim3 grid(blocks_per_job, njobs);
+  pack_filter_tc_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  return check_launch("pack_filter_tc_batch");
 }
 
 static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int cs, int W, int H, int N,

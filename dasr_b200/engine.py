@@ -284,7 +284,7 @@ def _pad_vec(b, n):
     return o
 
 
-def _fused_rdb_filters(cache, params, L, r, nf):
+def _fused_rdb_filters(cache, params, L, r, nf, halves=False):
     """Dense-block N-fusion: launch j multiplies ONE input chunk (x for j=1, x_{j-1} otherwise) against the
     filters of ALL convs k >= j that consume it, stacked along Cout.  Returns [(w_packed, bias)] for j=1..5."""
     out = []
@@ -307,12 +307,95 @@ def _fused_rdb_filters(cache, params, L, r, nf):
             return b
 
         ent = [cache.get(('fw', r, j), wj, make_w), cache.get(('fb', r, j), wj, make_b)]
-        if j == 1:   # the two Cout halves of launch 1 as separately packed filters (pipelined mode: two launches)
+        if j == 1 and halves:   # the two Cout halves of launch 1 as separately packed filters (pipelined mode: two launches)
             half = (nf + 4 * GC) // 2
             ent.append(cache.get(('fw1a', r), wj, lambda: ops.pack_filter_tc(stacked()[:half].contiguous(), TC_FPROP)))
             ent.append(cache.get(('fw1b', r), wj, lambda: ops.pack_filter_tc(stacked()[half:].contiguous(), TC_FPROP)))
         out.append(tuple(ent))
     return out
+
+
+class _BatchPacker:
+    """All kernel-layout filter copies of one RRDBNet training step (N-fused fprop stacks, dgrad packs, padded
+    first/last layers) as ONE dasr_pack_filter_tc_batch launch over a device-resident job table.  `cache` is a
+    _PackCache pre-filled with the destination tensors under the keys rrdb_forward_bf16_train / rrdb_backward_bf16
+    use, so code running against it finds every filter already packed (valid while the parameter versions are the
+    ones seen at construction — i.e. for graph capture right after; replays call launch() from inside the graph)."""
+
+    def __init__(self, params, L, nf):
+        import ctypes as C
+        from ._lib import PackJob
+        dev = params[0].device
+        self.cache = _PackCache()
+        jobs, keep = [], []
+        W = lambda i: params[2 * i]
+        Bv = lambda i: params[2 * i + 1]
+
+        def ver(p):
+            return (p.data_ptr(), p._version)
+
+        def add(key, param, kind, rows_total, k_ch, parts, nvar_taps):
+            # parts: [(src param, ci_lo, ci_n, cout_rows, k_pad, row_off)]
+            dst = torch.zeros(nvar_taps * (k_ch // 32) * rows_total * 32, dtype=torch.bfloat16, device=dev)
+            for (src, ci_lo, ci_n, cout_rows, k_pad, row_off) in parts:
+                j = PackJob()
+                j.src, j.dst = src.data_ptr(), dst.data_ptr()
+                j.cout, j.cin, j.kind = src.shape[0], src.shape[1], kind
+                j.ci_lo, j.ci_n, j.cout_rows, j.k_pad = ci_lo, ci_n, cout_rows, k_pad
+                j.dst_rows, j.dst_row_off = rows_total, row_off
+                jobs.append(j)
+            self.cache.d[key] = (ver(param), dst)
+            keep.append(dst)
+
+        def fprop(i, kind=TC_FPROP, cout_to=None, cin_to=None):
+            w = W(i)
+            co, ci = cout_to or w.shape[0], cin_to or w.shape[1]
+            add(('w', i, kind), w, kind, co, ci, [(w, 0, ci, co, 0, 0)], 16 if kind == TC_UPCONV else 9)
+
+        def dgrad(i, cout_to=None):
+            w = W(i)
+            kp = cout_to or w.shape[0]
+            add(('wd', i), w, TC_DGRAD, w.shape[1], kp, [(w, 0, w.shape[1], 0, kp, 0)], 9)
+
+        def bias_alias(i):
+            self.cache.d[('b', i)] = (ver(Bv(i)), Bv(i))
+
+        def bias_copy(key, param, src, n):
+            dst = torch.zeros(n, dtype=torch.float32, device=dev)
+            j = PackJob()
+            j.src, j.dst, j.cout, j.kind = src.data_ptr(), dst.data_ptr(), src.shape[0], 3
+            jobs.append(j)
+            self.cache.d[key] = (ver(param), dst)
+            keep.append(dst)
+
+        fprop(L.i_fea, cin_to=32); bias_alias(L.i_fea)
+        fprop(L.i_lr); bias_alias(L.i_lr); dgrad(L.i_lr)
+        for u in range(L.n_up):
+            fprop(L.i_up0 + u, TC_UPCONV); bias_alias(L.i_up0 + u); dgrad(L.i_up0 + u)
+        fprop(L.i_hr0); bias_alias(L.i_hr0); dgrad(L.i_hr0)
+        fprop(L.i_hr1, cout_to=16); bias_copy(('b', L.i_hr1), Bv(L.i_hr1), Bv(L.i_hr1), 16); dgrad(L.i_hr1, cout_to=32)
+        for r in range(L.n_rdb):
+            for j in range(1, 6):
+                lo, hi = (0, nf) if j == 1 else (nf + (j - 2) * GC, nf + (j - 1) * GC)
+                ks = list(range(j, 6))
+                couts = [W(L.rdb_conv(r, k)).shape[0] for k in ks]
+                parts, off = [], 0
+                for k, co in zip(ks, couts):
+                    parts.append((W(L.rdb_conv(r, k)), lo, hi - lo, co, 0, off))
+                    off += co
+                wj = W(L.rdb_conv(r, j))
+                add(('fw', r, j), wj, TC_FPROP, off, hi - lo, parts, 9)
+                bias_copy(('fb', r, j), wj, Bv(L.rdb_conv(r, j)), off)
+                dgrad(L.rdb_conv(r, j))
+        arr = (PackJob * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(dev)
+        self.njobs = len(jobs)
+        self.keep = keep
+
+    def launch(self):
+        ops.check(ops._lib.load().dasr_pack_filter_tc_batch(ops._p(self.table), self.njobs, 16, ops._stream()),
+                  'pack_filter_tc_batch')
 
 
 # CTAs per dense-block stage when the six stage launches of an RDB run concurrently (sum = 148 SMs); proportional to
@@ -339,7 +422,7 @@ def _rrdb_trunk_pipelined(L, params, cache, rot, fea, lr, wk, bk, nf, BW, CS):
     half = (BW - nf) // 2
     for r in range(n_rdb):
         b = bufs[r]
-        fw = _fused_rdb_filters(cache, params, L, r, nf)
+        fw = _fused_rdb_filters(cache, params, L, r, nf, halves=True)
         prev5 = [(prog[r - 1, 5], G[5])] if r > 0 else []
         bias1 = fw[0][1]
         with torch.cuda.stream(streams[0]):     # 1a: x -> x1 (complete) | partial conv2, conv3
@@ -648,20 +731,24 @@ class _TrainGraphs:
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         plist = [p.detach() for p in params]
+        L = RRDBLayout(nb, params[0].shape[0], upscale)
+        self.packer = _BatchPacker(plist, L, L.nf)          # every filter copy of the step from ONE launch
         with torch.cuda.stream(side):            # eager warm-up: workspaces, function attributes, allocator
-            out, ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, _PackCache())
-            rrdb_backward_bf16(ctx, plist, torch.zeros_like(out), _PackCache())
+            self.packer.launch()
+            out, ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, self.packer.cache)
+            rrdb_backward_bf16(ctx, plist, torch.zeros_like(out), self.packer.cache)
             del out, ctx
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.pool = torch.cuda.graph_pool_handle()
         self.fwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.fwd, pool=self.pool):
-            self.out, self.ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, _PackCache())
+            self.packer.launch()
+            self.out, self.ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, self.packer.cache)
         self.dout = torch.zeros_like(self.out)
         self.bwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.bwd, pool=self.pool):
-            _, self.grads = rrdb_backward_bf16(self.ctx, plist, self.dout, _PackCache())
+            _, self.grads = rrdb_backward_bf16(self.ctx, plist, self.dout, self.packer.cache)
         from . import _lib
         self.launches = 0
 

@@ -172,6 +172,24 @@ size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind);
 int dasr_pack_filter_tc(const float* w_oihw, void* w_packed_bf16, int cout, int cin, int kind,
                         void* stream);
 
+/* One launch for many filters (training re-packs every filter each step).  `jobs` lives in DEVICE memory.
+ *   kind 0/2: rows [dst_row_off, dst_row_off + cout_rows) of a packed tensor with dst_rows Cout rows receive
+ *             input channels [ci_lo, ci_lo + ci_n) of src (OIHW [cout][cin][3][3]); reads beyond cout/cin give 0.
+ *   kind 1  : dgrad pack; GEMM-N rows = input channels [ci_lo, ci_lo + ci_n), GEMM-K = k_pad >= cout channels.
+ *   kind 3  : copy `cout` fp32 values src -> dst (bias prefix). */
+typedef struct {
+  const float* src;
+  void* dst;
+  int cout, cin;          /* real extents of src */
+  int kind;
+  int ci_lo, ci_n;        /* input-channel slice (kind 0/2: GEMM-K, multiple of 32; kind 1: GEMM-N rows) */
+  int cout_rows;          /* kind 0/2: rows written (>= cout pads with zeros) */
+  int k_pad;              /* kind 1: GEMM-K channels (multiple of 32, >= cout) */
+  int dst_rows, dst_row_off;
+  int reserved;
+} DasrPackJob;
+int dasr_pack_filter_tc_batch(const DasrPackJob* jobs, int njobs, int blocks_per_job, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Layout / elementwise / reductions (all HBM-bound).
  * ---------------------------------------------------------------------------------------------- */

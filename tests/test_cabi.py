@@ -34,7 +34,7 @@ def test_param_structs_match_header_layout():
     behaviour is GPU-only; here: field order/count against the header text)."""
     from dasr_b200 import _lib
     txt = open(os.path.join(ROOT, 'include', 'dasr_b200.h')).read()
-    for name, struct in (('DasrConvF32Params', _lib.ConvF32Params), ('DasrConvTcParams', _lib.ConvTcParams)):
+    for name, struct in (('DasrConvF32Params', _lib.ConvF32Params), ('DasrConvTcParams', _lib.ConvTcParams), ('DasrPackJob', _lib.PackJob)):
         end = txt.index('} %s;' % name)
         body = txt[txt.rindex('typedef struct {', 0, end) + len('typedef struct {'):end]
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
@@ -43,9 +43,8 @@ def test_param_structs_match_header_layout():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r'^(int8_t|int|float)\s+', '', decl)
             for f in decl.split(','):
-                fields.append(re.sub(r'\[.*', '', f.strip()))
+                fields.append(re.split(r'[\s\*]+', re.sub(r'\[.*', '', f.strip()))[-1])
         assert fields == [f[0] for f in struct._fields_], name
 
 

@@ -231,6 +231,30 @@ def test_conv_tc_wide_channel_tiles(cin, cout, h, w):
     assert float((got - gref).abs().max() / gref.abs().max()) < 1e-2
 
 
+def test_batch_packer_matches_per_filter_packs():
+    """dasr_pack_filter_tc_batch (one launch, device job table) writes bit-identical kernel-layout filters to the
+    per-filter path for every key the mixed-precision forward/backward asks for."""
+    from dasr_b200 import engine
+    nb = 1
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 5, 0.3)
+    params = [v.cuda() for v in sd.values()]
+    x = O.synth_image((1, 3, 16, 24), 6).cuda()
+    ref = engine._PackCache()
+    out, ctx = engine.rrdb_forward_bf16_train(x, params, nb, 4, ref)
+    engine.rrdb_backward_bf16(ctx, params, torch.ones_like(out), ref)
+    L = engine.RRDBLayout(nb, params[0].shape[0], 4)
+    bp = engine._BatchPacker(params, L, L.nf)
+    bp.launch()
+    torch.cuda.synchronize()
+    assert set(ref.d.keys()) == set(bp.cache.d.keys())
+    for k, (_, t) in ref.d.items():
+        got = bp.cache.d[k][1]
+        assert got.shape == t.shape and got.dtype == t.dtype, k
+        assert torch.equal(got, t), k
+    out2, ctx2 = engine.rrdb_forward_bf16_train(x, params, nb, 4, bp.cache)
+    assert torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------ filters / haar / losses
 def test_filters_haar_bilinear_losses(golden):
     from dasr_b200 import ops
