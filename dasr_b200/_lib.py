@@ -57,6 +57,13 @@ class PackJob(C.Structure):
                 ('dst_row_off', C.c_int), ('reserved', C.c_int)]
 
 
+class RdbParams(C.Structure):
+    """DasrRdbParams (include/dasr_b200.h)"""
+    _fields_ = [('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('nf', C.c_int), ('gc', C.c_int), ('cs', C.c_int),
+                ('next_cs', C.c_int), ('next_coff', C.c_int), ('res2_cs', C.c_int), ('res2_coff', C.c_int),
+                ('chunk_imgs', C.c_int), ('alpha', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('slope', C.c_float)]
+
+
 class PipeArgs(C.Structure):
     _fields_ = [('grid_x', C.c_int), ('dep0', C.c_void_p), ('dep0_g', C.c_int), ('dep1', C.c_void_p), ('dep1_g', C.c_int),
                 ('progress', C.c_void_p)]
@@ -102,6 +109,7 @@ SYMBOLS = {
     'dasr_bce_logits_loss': (_i, [_vp, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_mean': (_i, [_vp, _vp, _l, _vp, _vp]),
     'dasr_pack_filter_tc_batch': (_i, [_vp, _i, _i, _vp]),
+    'dasr_rdb_tc': (_i, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(RdbParams), _vp, _vp, _vp]),
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
     'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),

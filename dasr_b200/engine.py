@@ -228,6 +228,7 @@ def rrdb_backward_f32(ctx, params, dout, need_dx=False):
 # SLOWER on B200 (71 ms vs 62 ms per 16x256x256 forward: the shorter launches are latency-bound), so the default
 # keeps the whole batch in one pass; set e.g. 72 MiB to re-enable.
 TRUNK_L2_BYTES = float(os.environ.get('DASR_B200_TRUNK_BYTES', 'inf'))
+RDB_CHUNK_IMGS = int(os.environ.get('DASR_B200_RDB_CHUNK', '2'))   # images per L2-resident chunk of the persistent RDB kernel
 _TC_W_BUDGET = 150 * 1024   # resident-filter bytes per CTA that still leaves >= 5 halo stages
 
 
@@ -473,6 +474,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
     if pipelined is None:
         pipelined = fused and os.environ.get('DASR_B200_PIPE', '0') == '1'   # experimental: measured slower
     pipelined = bool(pipelined and fused and nf == 64)
+    rdb_kernel = fused and not pipelined and nf == 64 and GC == 32 and os.environ.get('DASR_B200_RDB', '0') == '1'
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -511,7 +513,11 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
                 tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
             else:
                 tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
-            if fused:
+            if fused and rdb_kernel:
+                fw = _fused_rdb_filters(cache, params, L, r, nf)
+                ops.rdb_tc(b, bufs[r + 1], bufs[r - 2] if r % 3 == 2 else None, [f[0] for f in fw], [f[1] for f in fw],
+                           tail['alpha'], tail['beta1'], tail.get('beta2', 0.0), chunk_imgs=RDB_CHUNK_IMGS)
+            elif fused:
                 fw = _fused_rdb_filters(cache, params, L, r, nf)
                 # Consecutive launches walk the tile grid in opposite directions: a launch starts with the tiles its
                 # predecessor wrote last, i.e. with the part of the partial sums that is still resident in L2.

@@ -218,6 +218,29 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
                                 C.byref(pa) if pa is not None else None, _stream()), 'conv_tc')
 
 
+_rdb_sync = {}
+
+
+def rdb_tc(buf, buf_next, res2, w_packed, bias, alpha, beta1, beta2=0.0, chunk_imgs=2, slope=0.2, next_coff=0, res2_coff=0):
+    """One persistent kernel for a whole dense block (dasr_rdb_tc): buf [N,H,W,256] bf16 with x in channels 0:64;
+    writes alpha*conv5 + beta1*x (+ beta2*res2[..., res2_coff:+64]) into buf_next[..., next_coff:+64]."""
+    N, H, W, cs = buf.shape
+    key = str(buf.device)
+    sync = _rdb_sync.get(key)
+    if sync is None:
+        sync = _rdb_sync[key] = torch.zeros(2, dtype=torch.int32, device=buf.device)      # [barrier counter, error flag]
+    p = _lib.RdbParams()
+    p.N, p.H, p.W, p.nf, p.gc, p.cs = N, H, W, 64, 32, cs
+    p.next_cs, p.next_coff = buf_next.shape[-1], next_coff
+    p.res2_cs, p.res2_coff = (res2.shape[-1] if res2 is not None else 0), res2_coff
+    p.chunk_imgs = chunk_imgs
+    p.alpha, p.beta1, p.beta2, p.slope = alpha, beta1, beta2, slope
+    wp = (C.c_void_p * 5)(*[t.data_ptr() for t in w_packed])
+    bp = (C.c_void_p * 5)(*[t.data_ptr() for t in bias])
+    check(_lib.load().dasr_rdb_tc(_p(buf), _p(buf_next), _p(res2), wp, bp, C.byref(p), C.c_void_p(sync.data_ptr()),
+                                  C.c_void_p(sync.data_ptr() + 4), _stream()), 'rdb_tc')
+
+
 def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):
     N, H, W, _ = inp.t.shape
     p = ConvTcParams()

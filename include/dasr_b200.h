@@ -213,6 +213,28 @@ int dasr_upsample2x_fwd(const void* src, void* dst, int N, int H, int W, int C, 
 /* dst = a*x + b*y on channel slices (gradient accumulation across concat consumers) */
 int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff,
                int y_cs, int y_coff, int d_cs, int d_coff, float a, float b, int is_bf16, void* stream);
+/* A whole ResidualDenseBlock_5C (block.py:254-286) of the inference forward as ONE persistent kernel: the five
+ * N-fused stages of the dasr_conv_tc schedule run image chunk by image chunk inside the kernel, separated by grid
+ * barriers, so the bf16 partial sums stay in L2 (chunk_imgs images: ~25 MB per 256x256 image).
+ *   buf      : NHWC bf16 [N,H,W,cs=256] = [x 0:64 | x1..x4 64:192 | conv5 partial 192:256]; x must be filled
+ *   buf_next : receives alpha*(conv5) + beta1*x (+ beta2*res2) in channels [next_coff, next_coff+64) (stride next_cs)
+ *   buf_res2 : optional second residual (the RRDB input, every third block), channels [res2_coff, +64), stride res2_cs
+ *   w_packed[j], bias[j] (j = 0..4): stacked filters / bias of stage j+1 exactly as the five dasr_conv_tc launches use them
+ *   counter  : one device uint32 (zeroed by this call);  error_flag: device int set to 1 if a grid barrier timed out.
+ * Results are bit-identical to the five-launch schedule. */
+typedef struct {
+  int N, H, W;
+  int nf, gc;               /* 64, 32 */
+  int cs;                   /* 256 */
+  int next_cs, next_coff;
+  int res2_cs, res2_coff;
+  int chunk_imgs;
+  float alpha, beta1, beta2, slope;
+} DasrRdbParams;
+int dasr_rdb_tc(void* buf, void* buf_next, const void* buf_res2, const void* const* w_packed,
+                const float* const* bias, const DasrRdbParams* p, unsigned int* counter, int* error_flag,
+                void* stream);
+
 /* 2x2 s2 max-pool NHWC fp32 fwd / bwd (VGG19 features, architecture.py:1076) */
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
 int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H,
