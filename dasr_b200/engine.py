@@ -748,15 +748,18 @@ class _TrainGraphs:
         torch.cuda.synchronize()
         self.pool = torch.cuda.graph_pool_handle()
         self.fwd = torch.cuda.CUDAGraph()
+        from . import _lib
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(self.fwd, pool=self.pool):
             self.packer.launch()
             self.out, self.ctx = rrdb_forward_bf16_train(self.x, plist, nb, upscale, self.packer.cache)
+        self.n_fwd = _lib.LAUNCHES - l0          # kernels of ours inside the forward graph (counted again per replay)
         self.dout = torch.zeros_like(self.out)
         self.bwd = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(self.bwd, pool=self.pool):
             _, self.grads = rrdb_backward_bf16(self.ctx, plist, self.dout, self.packer.cache)
-        from . import _lib
-        self.launches = 0
+        self.n_bwd = _lib.LAUNCHES - l0
 
 
 class RRDBNetFunctionBF16(torch.autograd.Function):
@@ -770,6 +773,7 @@ class RRDBNetFunctionBF16(torch.autograd.Function):
         if graphs is not None:
             graphs.x.copy_(x)
             graphs.fwd.replay()
+            ops._lib.LAUNCHES += graphs.n_fwd
             return graphs.out.clone()
         out, saved = rrdb_forward_bf16_train(x, [p.detach() for p in params], nb, upscale, cache)
         ctx.saved = saved
@@ -781,6 +785,7 @@ class RRDBNetFunctionBF16(torch.autograd.Function):
         if g is not None:
             g.dout.copy_(dout)
             g.bwd.replay()
+            ops._lib.LAUNCHES += g.n_bwd
             grads = [t.clone() for t in g.grads]
         else:
             _, grads = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)

@@ -282,3 +282,12 @@ class FilterHigh(nn.Module):
         if self.normalize:
             return self.filter_low._apply_once(img, 1)          # 0.5 + 0.5*(x - low(x)) fused
         return img - self.filter_low(img)
+
+
+def __getattr__(name):
+    """FS_Discriminator / DiscriminatorBasic (architecture.py:833-870,922-980) live in the DSN drop-in, which imports the
+    filters from this module — resolved lazily to avoid the import cycle."""
+    if name in ('FS_Discriminator', 'DiscriminatorBasic'):
+        from dasr_b200.dsn import model as _m
+        return _m.Discriminator if name == 'FS_Discriminator' else _m.DiscriminatorBasic
+    raise AttributeError(name)

@@ -107,6 +107,19 @@ def define_pairD(opt):
     return _wrap(netD, opt['gpu_ids'])
 
 
+def define_patchD(opt):
+    """FS_Discriminator (networks.py:229-245 / architecture.py:922-980): frequency-separation filter + patch
+    discriminator + sigmoid; shared with the DSN drop-in (dasr_b200/dsn/model.py)."""
+    from dasr_b200.dsn.model import Discriminator as FS_Discriminator
+    opt_net = opt['network_patchD']
+    if opt_net['which_patchD'] != 'FSD':
+        raise NotImplementedError('Patch Discriminator model [{:s}] not recognized'.format(str(opt_net)))
+    net = FS_Discriminator(kernel_size=opt_net['kernel_size'], D_arch='FSD', filter_type=opt_net['FS_type'],
+                           norm_layer=opt_net['norm_layer'])
+    init_weights(net, init_type='kaiming', scale=1)
+    return _wrap(net, opt['gpu_ids'])
+
+
 def define_F(opt, use_bn=False):
     gpu_ids = opt['gpu_ids']
     device = torch.device('cuda' if gpu_ids else 'cpu')
