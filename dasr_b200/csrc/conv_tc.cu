@@ -44,6 +44,7 @@ struct TcKernelArgs {
   int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
   int epi_bytes;     // bytes of ONE staged epilogue tile: 128 pixels x nt channels bf16
   int has_pre, has_res1, has_res2;
+  int nbuf;          // staged-epilogue tile buffers (2..4): pre / residual tiles are requested nbuf tiles ahead
   // cross-launch spatial pipelining (dense-block stages run CONCURRENTLY on disjoint SM subsets):
   //   dep{0,1}[k] = tiles finished by CTA k of a producer launch with dep_g CTAs (same tile order as this launch);
   //   a tile (and its pre/residual tiles) may be loaded once every producer tile up to the end of the NEXT tile row
@@ -66,20 +67,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + a.w_bytes;
-  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;          // [2] output staging (and pre-activation addend, in place)
-  uint8_t* sR1 = sS + 2 * a.epi_bytes;                            // [2]
-  uint8_t* sR2 = sR1 + (NRES >= 1 ? 2 * a.epi_bytes : 0);        // [2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (NRES >= 2 ? 2 * a.epi_bytes : 0));
+  const int nbuf = a.nbuf;
+  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;          // [nbuf] output staging (and pre-activation addend, in place)
+  uint8_t* sR1 = sS + nbuf * a.epi_bytes;                         // [nbuf]
+  uint8_t* sR2 = sR1 + (NRES >= 1 ? nbuf * a.epi_bytes : 0);     // [nbuf]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (NRES >= 2 ? nbuf * a.epi_bytes : 0));
   uint64_t* full_bar = bars;                     // [stages]  A chunk landed
   uint64_t* empty_bar = bars + MAX_STAGES;       // [stages]  A chunk consumed
   uint64_t* w_bar = bars + 2 * MAX_STAGES;       // [1]       resident filters landed
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES + 1;    // [2]  accumulator complete
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 3;   // [2]  accumulator drained
-  uint64_t* pre_bar = bars + 2 * MAX_STAGES + 5;      // [2]  pre / residual tiles landed in staging buffer b
-  uint64_t* sfull_bar = bars + 2 * MAX_STAGES + 7;    // [2]  staging buffer b holds a finished tile
-  uint64_t* sfree_bar = bars + 2 * MAX_STAGES + 9;    // [2]  staging buffer b has been read by its TMA stores
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 11);
-  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 12);   // [nt] (16-byte aligned)
+  uint64_t* pre_bar = bars + 2 * MAX_STAGES + 5;      // [4]  pre / residual tiles landed in staging buffer b
+  uint64_t* sfull_bar = bars + 2 * MAX_STAGES + 9;    // [4]  staging buffer b holds a finished tile
+  uint64_t* sfree_bar = bars + 2 * MAX_STAGES + 13;   // [4]  staging buffer b has been read by its TMA stores
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 17);
+  float* sBias = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 18);   // [nt] (16-byte aligned)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,6 +105,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
+    }
+    for (int b = 0; b < 4; b++) {
       mbar_init(&pre_bar[b], 1);
       mbar_init(&sfull_bar[b], 8);
       mbar_init(&sfree_bar[b], 1);
@@ -153,11 +157,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           uint8_t* dst = sA + (size_t)stage * a.a_stage_bytes;
           if (p.a_mode == 0) {
             mbar_expect_tx(&full_bar[stage], A_HALO_BYTES);
-            tma_load_4d(dst, &tmap_in, &full_bar[stage], p.in_coff + c * CHUNK, x0 - 1, y0 - 1, n);
+            tma_load_4d(dst, &tmap_in, &full_bar[stage], p.nchunk_list ? p.chunk_off[c] : p.in_coff + c * CHUNK, x0 - 1, y0 - 1, n);
           } else {
             mbar_expect_tx(&full_bar[stage], (uint32_t)(ntaps * A_TAP_BYTES));
             for (int tap = 0; tap < ntaps; tap++)
-              tma_load_4d(dst + (size_t)tap * A_TAP_BYTES, &tmap_in, &full_bar[stage], p.in_coff + c * CHUNK,
+              tma_load_4d(dst + (size_t)tap * A_TAP_BYTES, &tmap_in, &full_bar[stage], p.nchunk_list ? p.chunk_off[c] : p.in_coff + c * CHUNK,
                           x0 - 1 + p.tap_dx[var][tap], y0 - 1 + p.tap_dy[var][tap], n);
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -260,16 +264,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       };
       const long G = gridDim.x;
       if (has_loads) {
-        if ((long)blockIdx.x < a.ntiles) issue_loads(blockIdx.x, 0);
-        if ((long)blockIdx.x + G < a.ntiles) issue_loads(blockIdx.x + G, 1);
+        for (int k = 0; k < nbuf; k++)
+          if ((long)blockIdx.x + k * G < a.ntiles) issue_loads(blockIdx.x + k * G, k);
       }
       uint32_t it = 0;
       for (long tile = blockIdx.x; tile < a.ntiles; tile += G, it++) {
-        const int b = it & 1;
+        const int b = (int)(it % (uint32_t)nbuf);
         if (lane == 0) {
           int x0, y0, n;
           tile_xyz(tile, x0, y0, n);
-          mbar_wait(&sfull_bar[b], (it >> 1) & 1);
+          mbar_wait(&sfull_bar[b], (it / (uint32_t)nbuf) & 1);
           for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
             const int wide = i < nb64;
             const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
@@ -286,7 +290,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           if (!has_loads) mbar_arrive(&sfree_bar[b]);
         }
         __syncwarp();
-        if (has_loads && tile + 2 * G < a.ntiles) issue_loads(tile + 2 * G, b);
+        if (has_loads && tile + (long)nbuf * G < a.ntiles) issue_loads(tile + (long)nbuf * G, b);
       }
       if (lane == 0) {
         bulk_wait0();                              // all stores complete before the CTA (and its smem) goes away
@@ -329,13 +333,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const bool valid = (y < p.H) && (x < p.W);
       const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
       const long opix = ((long)n * OH + oy) * OW + ox;
-      const uint32_t bS = sS_u + acc * a.epi_bytes, bR1 = sR1_u + acc * a.epi_bytes, bR2 = sR2_u + acc * a.epi_bytes;
+      const int sb = (int)(it % (uint32_t)nbuf);                // staging buffer of this tile
+      const uint32_t sphase = (it / (uint32_t)nbuf) & 1;
+      const uint32_t bS = sS_u + sb * a.epi_bytes, bR1 = sR1_u + sb * a.epi_bytes, bR2 = sR2_u + sb * a.epi_bytes;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (EPI_MODE == 0) {
-        if (has_loads) mbar_wait(&pre_bar[acc], acc_phase);                  // pre / residual tiles of this tile landed
-        else if (it >= 2) mbar_wait(&sfree_bar[acc], ((it >> 1) - 1) & 1);   // stores of tile it-2 have read the buffer
+        if (has_loads) mbar_wait(&pre_bar[sb], sphase);                      // pre / residual tiles of this tile landed
+        else if (it >= (uint32_t)nbuf) mbar_wait(&sfree_bar[sb], sphase ^ 1); // stores of tile it-nbuf have read the buffer
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
       // One 16-column group: registers -> (+bias, +pre) -> act -> scale -> (+residuals) -> bf16 -> staged tile / global.
@@ -475,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       if constexpr (EPI_MODE == 0) {
         fence_proxy_async();          // generic-proxy writes of the staged tile -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sfull_bar[acc]);
+        if (lane == 0) mbar_arrive(&sfull_bar[sb]);
       }
     }
   }
@@ -681,6 +687,7 @@ extern "C" {
 
 int dasr_conv_tc_setup(DasrConvTcParams* p, int kind) {
   if (!p) return DASR_E_BADARG;
+  p->nchunk_list = 0;
   if (kind == 0 || kind == 1) {
     p->nvar = 1;
     p->ntaps = 9;
@@ -762,7 +769,13 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
   DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc: cin must be a multiple of 32 (got %d)", p->cin);
-  DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc: input slice");
+  if (p->nchunk_list > 0) {
+    DASR_REQUIRE(p->nchunk_list <= 8 && p->nchunk_list * CHUNK == p->cin && p->in_cs % 8 == 0, "conv_tc: chunk list must cover cin");
+    for (int i = 0; i < p->nchunk_list; i++)
+      DASR_REQUIRE(p->chunk_off[i] >= 0 && p->chunk_off[i] % 8 == 0 && p->chunk_off[i] + CHUNK <= p->in_cs, "conv_tc: chunk_off[%d]", i);
+  } else {
+    DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc: input slice");
+  }
   DASR_REQUIRE(p->nt >= 16 && p->nt <= 256 && p->nt % 16 == 0 && p->cout % p->nt == 0, "conv_tc: nt=%d cout=%d",
                p->nt, p->cout);
   DASR_REQUIRE(p->nvar >= 1 && p->nvar <= 4 && p->ntaps >= 1 && p->ntaps <= 9, "conv_tc: variants/taps");
@@ -821,9 +834,18 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
     a.dep1 = pipe->dep1; a.dep1_g = pipe->dep1_g;
     a.progress = pipe->progress;
   }
-  const int epi_total = 2 * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
-  const int bar_bytes = (2 * MAX_STAGES + 12) * 8 + 256 * 4 + 16;
-  int avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
+  const int bar_bytes = (2 * MAX_STAGES + 18) * 8 + 256 * 4 + 16;
+  // staged-epilogue buffers: as many (<= 4) as still leave 4 A stages; loads of pre / residual tiles are issued nbuf
+  // tiles ahead, which hides their latency (with 2 the read-modify-write launches are bound by that round trip)
+  int nbuf = (p->epi_mode == 0) ? 4 : 2;
+  if (pipe) nbuf = 2;
+  int epi_total = 0, avail = 0;
+  for (;; nbuf--) {
+    epi_total = nbuf * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
+    avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
+    if (nbuf == 2 || avail >= 4 * a.a_stage_bytes) break;
+  }
+  a.nbuf = nbuf;
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {

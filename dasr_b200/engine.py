@@ -316,6 +316,41 @@ def _fused_rdb_filters(cache, params, L, r, nf, halves=False):
     return out
 
 
+# Dense-block schedule 2 (inference): which (conv k, input chunk) products each of the five launches computes.
+# Launch j still completes conv j, but the later convs no longer take ALL their partial sums along from launch 1 on:
+#   1: x        -> x1 | p2 p3 p4 p5      2: x1 -> x2 | p3        3: x2 -> x3 | p4
+#   4: x1, x3   -> x4 | p5               5: x2, x4 -> out
+# Launches 2-5 of the column-strip schedule re-read and re-write 160/128/96/64 partial-sum channels per pixel and are HBM
+# bound (profiles/r1_summary.md); this assignment moves 1.9 KB instead of 2.7 KB per pixel and block at +23 % MMA cycles.
+SCHED2 = ((('x',), (1, 2, 3, 4, 5)), ((1,), (2, 3)), ((2,), (3, 4)), ((1, 3), (4, 5)), ((2, 4), (5,)))
+
+
+def _sched2_chunk_offsets(nf, chunk):
+    return [0, 32] if chunk == 'x' else [nf + (chunk - 1) * GC]
+
+
+def _sched2_rdb_filters(cache, params, L, r, nf):
+    """[(packed filters, bias, chunk channel offsets)] of the five launches of SCHED2 for dense block r."""
+    out = []
+    for j, (chunks, ks) in enumerate(SCHED2, start=1):
+        offs = [o for c in chunks for o in _sched2_chunk_offsets(nf, c)]
+        wj = params[2 * L.rdb_conv(r, j)]
+
+        def make_w(offs=offs, ks=ks):
+            idx = torch.cat([torch.arange(o, o + 32, device=wj.device) for o in offs])
+            st = torch.cat([params[2 * L.rdb_conv(r, k)].detach()[:, idx] for k in ks], 0).float().contiguous()
+            return ops.pack_filter_tc(st, TC_FPROP)
+
+        def make_b(j=j, ks=ks):
+            bj = params[2 * L.rdb_conv(r, j) + 1].detach().float()
+            n = sum(params[2 * L.rdb_conv(r, k)].shape[0] for k in ks)
+            b = torch.zeros(n, dtype=torch.float32, device=bj.device)
+            b[:bj.shape[0]] = bj
+            return b
+        out.append((cache.get(('s2w', r, j), wj, make_w), cache.get(('s2b', r, j), wj, make_b), offs))
+    return out
+
+
 class _BatchPacker:
     """All kernel-layout filter copies of one RRDBNet training step (N-fused fprop stacks, dgrad packs, padded
     first/last layers) as ONE dasr_pack_filter_tc_batch launch over a device-resident job table.  `cache` is a
@@ -475,6 +510,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
         pipelined = fused and os.environ.get('DASR_B200_PIPE', '0') == '1'   # experimental: measured slower
     pipelined = bool(pipelined and fused and nf == 64)
     rdb_kernel = fused and not pipelined and nf == 64 and GC == 32 and os.environ.get('DASR_B200_RDB', '0') == '1'
+    sched2 = fused and not pipelined and not rdb_kernel and nf == 64 and GC == 32 and os.environ.get('DASR_B200_SCHED', '2') == '2'
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -513,7 +549,18 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
                 tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
             else:
                 tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
-            if fused and rdb_kernel:
+            if fused and sched2:
+                fw = _sched2_rdb_filters(cache, params, L, r, nf)
+                ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2,
+                            act=ACT_LRELU, slope=0.2, act_cols=GC)
+                o = View(b, 2 * GC, nf + GC)                               # x2 | p3
+                ops.conv_tc(b, fw[1][0], fw[1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[1][2])
+                o = View(b, 2 * GC, nf + 2 * GC)                           # x3 | p4
+                ops.conv_tc(b, fw[2][0], fw[2][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[2][2])
+                o = View(b, GC + nf, nf + 3 * GC)                          # x4 | p5
+                ops.conv_tc(b, fw[3][0], fw[3][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[3][2])
+                ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], **tail)
+            elif fused and rdb_kernel:
                 fw = _fused_rdb_filters(cache, params, L, r, nf)
                 ops.rdb_tc(b, bufs[r + 1], bufs[r - 2] if r % 3 == 2 else None, [f[0] for f in fw], [f[1] for f in fw],
                            tail['alpha'], tail['beta1'], tail.get('beta2', 0.0), chunk_imgs=RDB_CHUNK_IMGS)

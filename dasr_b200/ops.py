@@ -168,8 +168,8 @@ def pack_filter_tc(w, kind):
 
 def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0, act_cols=None,
             pre=None, res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2,
-            a_mode=0, nchw_out=None, cout=None, pipe=None, tile_rev=False):
-    """tcgen05 3x3 conv on NHWC bf16 channel slices; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
+            a_mode=0, nchw_out=None, cout=None, pipe=None, tile_rev=False, chunks=None):
+    """tcgen05 3x3 conv on NHWC bf16 channel slices; chunks = optional list of 32-channel chunk offsets of `inp`'s buffer; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
     v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
     nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer)."""
     inp = as_view(inp)
@@ -182,6 +182,10 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup', 0)
     p.N, p.H, p.W = N, H, W
     p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
+    if chunks is not None:
+        p.cin, p.in_coff, p.nchunk_list = 32 * len(chunks), 0, len(chunks)
+        for i, c in enumerate(chunks):
+            p.chunk_off[i] = c
     p.cout, p.out_cs, p.out_coff = out.c, out.cs, out.coff
     p.nt = nt if nt else out.c
     p.act, p.slope, p.alpha = act, slope, alpha

@@ -141,6 +141,11 @@ typedef struct {
   int out_nc;                  /* epi_mode 2: real output channels */
   int tile_rev;                /* 1 = walk the tile grid backwards: a launch that re-reads what the previous launch
                                   just wrote (dense-block partial sums) starts with the tiles still resident in L2 */
+  int nchunk_list;             /* > 0: the K channels are nchunk_list (= cin/32) separate 32-channel chunks of the input
+                                  buffer starting at channels chunk_off[i] (absolute, multiples of 8) instead of the
+                                  contiguous slice [in_coff, in_coff + cin) — dense-block schedules that feed
+                                  non-adjacent activations (e.g. x1 and x3) to one launch */
+  int chunk_off[8];
 } DasrConvTcParams;
 
 int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,

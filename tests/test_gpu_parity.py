@@ -241,6 +241,7 @@ def test_persistent_rdb_kernel_is_bit_identical_to_stage_launches(shape, chunk, 
     params = [v.cuda() for v in sd.values()]
     x = O.synth_image(shape, 2).cuda()
     monkeypatch.setenv('DASR_B200_RDB', '0')
+    monkeypatch.setenv('DASR_B200_SCHED', '1')          # the persistent kernel implements the column-strip schedule
     ref = engine.rrdb_forward_bf16(x, params, nb, 4, engine._PackCache())
     monkeypatch.setenv('DASR_B200_RDB', '1')
     monkeypatch.setattr(engine, 'RDB_CHUNK_IMGS', chunk)
