@@ -163,14 +163,15 @@ class _Sigmoid(torch.autograd.Function):
         from dasr_b200 import ops
         y = torch.empty_like(x, dtype=torch.float32)
         ops.sigmoid_fwd(x.contiguous().float(), y)
-        ctx.y = y
+        ctx.save_for_backward(y)          # an output kept as a plain attribute would form a reference cycle (y -> grad_fn -> y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from dasr_b200 import ops
-        dx = torch.empty_like(ctx.y)
-        ops.sigmoid_bwd(ctx.y, dy.contiguous().float(), dx)
+        y, = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        ops.sigmoid_bwd(y, dy.contiguous().float(), dx)
         return dx
 
 

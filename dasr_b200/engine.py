@@ -680,7 +680,21 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
     bf = torch.bfloat16
     Wt = lambda i: params[2 * i]
     CS = nf + 4 * GC
-    grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+    # all gradients are views of ONE flat fp32 buffer [filters in conv order | biases in conv order]: one copy hands them to
+    # autograd, and the four LeakyReLU convs of a dense block get their bias gradients from a single reduction
+    n_conv = len(params) // 2
+    w_off, b_off, o = [], [], 0
+    for i in range(n_conv):
+        w_off.append(o)
+        o += params[2 * i].numel()
+    for i in range(n_conv):
+        b_off.append(o)
+        o += params[2 * i + 1].numel()
+    flat = torch.empty(o, dtype=torch.float32, device=dout.device)
+    grads = []
+    for i in range(n_conv):
+        grads.append(flat[w_off[i]:w_off[i] + params[2 * i].numel()].view_as(params[2 * i]))
+        grads.append(flat[b_off[i]:b_off[i] + params[2 * i + 1].numel()])
     gW = lambda i: grads[2 * i]
     gB = lambda i: grads[2 * i + 1]
     cache = cache if cache is not None else _PackCache()
@@ -691,7 +705,7 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
     bufs, ups, h0, fea, xin = ctx['bufs'], ctx['ups'], ctx['h0'], ctx['fea'], ctx['xin']
     dev = dout
 
-    def wgrad(xv, gv, i, cin_real=None, cout_real=None):
+    def wgrad(xv, gv, i, cin_real=None, cout_real=None, bias=True):
         """filter + bias gradient of conv i on the tcgen05 wgrad kernel (zero-padded channel chunks are cut off)"""
         xv, gv = ops.as_view(xv), ops.as_view(gv)
         if cin_real is None and cout_real is None:
@@ -700,7 +714,8 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
             tmp = torch.empty((gv.c, xv.c, 3, 3), dtype=torch.float32, device=dout.device)
             ops.conv3x3_wgrad_tc(xv, gv, tmp)
             gW(i).copy_(tmp[:cout_real or gv.c, :cin_real or xv.c])
-        ops.bias_grad(View(gv.t, cout_real or gv.c, gv.coff), gB(i))
+        if bias:
+            ops.bias_grad(View(gv.t, cout_real or gv.c, gv.coff), gB(i))
     out_nc = Wt(L.i_hr1).shape[0]
     hh, ww = dout.shape[2], dout.shape[3]
 
@@ -755,9 +770,12 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
             cin = _rdb_cin(nf, k)
             gk = View(GB, GC, nf + (k - 1) * GC)
             ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
-            wgrad(View(b, cin, 0), gk, ci)
+            wgrad(View(b, cin, 0), gk, ci, bias=False)
             o = View(GB, cin, 0)
             ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                          # accumulate in place
+        # bias gradients of conv1..4 in one reduction: their masked output gradients are the final x1..x4 slices of GB
+        c1 = L.rdb_conv(r, 1)
+        ops.bias_grad(View(GB, 4 * GC, nf), flat[b_off[c1]:b_off[c1] + 4 * GC])
         g_new = _empty((N, H, W, nf), dev, bf)
         if r % 3 == 0 and g_rrdb is not None:
             ops.axpby(View(GB, nf, 0), 1.0, g_rrdb, 1.0, g_new)
@@ -768,7 +786,7 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
     g_fea = _empty((N, H, W, nf), dev, bf)
     ops.axpby(g_y, 1.0, g_lr, 1.0, g_fea)
     wgrad(xin, g_fea, L.i_fea, cin_real=in_nc)
-    return None, grads
+    return None, grads, flat
 
 
 class _TrainGraphs:
@@ -805,7 +823,7 @@ class _TrainGraphs:
         self.bwd = torch.cuda.CUDAGraph()
         l0 = _lib.LAUNCHES
         with torch.cuda.graph(self.bwd, pool=self.pool):
-            _, self.grads = rrdb_backward_bf16(self.ctx, plist, self.dout, self.packer.cache)
+            _, self.grads, self.gflat = rrdb_backward_bf16(self.ctx, plist, self.dout, self.packer.cache)
         self.n_bwd = _lib.LAUNCHES - l0
 
 
@@ -833,9 +851,11 @@ class RRDBNetFunctionBF16(torch.autograd.Function):
             g.dout.copy_(dout)
             g.bwd.replay()
             ops._lib.LAUNCHES += g.n_bwd
-            grads = [t.clone() for t in g.grads]
+            fl = g.gflat.clone()                                  # one copy out of the graph's static buffer
+            base = g.gflat.data_ptr()
+            grads = [fl[(t.data_ptr() - base) // 4:(t.data_ptr() - base) // 4 + t.numel()].view(t.shape) for t in g.grads]
         else:
-            _, grads = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
+            _, grads, _ = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
             ctx.saved = None
         return (None, None, None, None, None) + tuple(gr.to(p.dtype) for gr, p in zip(grads, ctx.params))
 
