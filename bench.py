@@ -281,7 +281,8 @@ def main():
     if args.train_steps > 0:
         train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'bf16')
         train['fp32_mode'] = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'fp32')
-        dsn = bench_dsn(args, dev, rank, world, barrier, max_over_ranks)
+        dsn = bench_dsn(args, dev, rank, world, barrier, max_over_ranks, 'bf16')
+        dsn['fp32_mode'] = bench_dsn(args, dev, rank, world, barrier, max_over_ranks, 'fp32')
 
     if rank != 0:
         if world > 1:
@@ -391,7 +392,7 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision
     return res
 
 
-def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, dp_sync=None):
+def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, precision='fp32'):
     """BASELINE configs[4]: DSN DeResnet + wavelet-cat FS discriminator GAN iteration, batch 8, crop 256, per GPU."""
     import warnings
     import torch
@@ -408,6 +409,8 @@ def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, dp_sync=None):
         mg = De_resnet(n_res_blocks=8, scale=4).to(dev)
         md = Discriminator(kernel_size=5, D_arch='FSD', norm_layer='Instance', filter_type='wavelet', cs='cat').to(dev)
         gl = GeneratorLoss(per_type='VGG', filter='wavelet', kernel_size=5, w_col=1, w_tex=0.005, w_per=0.01, wgan=False).to(dev)
+    mg.precision = precision
+    gl.perceptual_loss.loss_network.precision = precision
     og = torch.optim.Adam(mg.parameters(), lr=1e-4, betas=[0.5, 0.999])
     od = torch.optim.Adam(md.parameters(), lr=1e-4, betas=[0.5, 0.999])
     B = 8
@@ -439,7 +442,8 @@ def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, dp_sync=None):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.train_steps)
     res = {'metric': 'DSN train iterations/sec (De_resnet + FS discriminator + VGG16 perceptual + LL colour loss, Adam x2)',
-           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps, 'dtype': 'f32',
+           'value': 1e3 / ms, 'unit': 'it/s', 'ms_per_step': ms, 'steps': args.train_steps,
+           'dtype': 'f32' if precision == 'fp32' else 'bf16 (De_resnet trunk and VGG16 on tcgen05, fp32 accumulation; stride-2 tail, discriminator, losses, Adam fp32)',
            'config': {'workload': 'BASELINE configs[4]: batch 8, crop 256 -> 64, wavelet cat, per GPU', 'global_batch': B * world},
            'gpu_launches_per_step': (_lib.LAUNCHES - l0) // args.train_steps}
     del mg, md, gl

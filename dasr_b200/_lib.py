@@ -114,6 +114,9 @@ SYMBOLS = {
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
     'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),
+    'dasr_prelu_fwd_bf16': (_i, [_vp, _vp, _vp, _l, _vp]),
+    'dasr_prelu_bwd_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),
+    'dasr_cast_bf16_f32': (_i, [_vp, _vp, _l, _i, _vp]),
     'dasr_sigmoid_fwd': (_i, [_vp, _vp, _l, _vp]),
     'dasr_sigmoid_bwd': (_i, [_vp, _vp, _vp, _l, _vp]),
 }

@@ -540,6 +540,33 @@ __global__ void prelu_fwd_kernel(const float* __restrict__ z, const float* __res
     y[i] = v > 0.f ? v : a * v;
   }
 }
+// bf16 PReLU (mixed-precision De_resnet), 8 elements per thread; slope gradient accumulated in fp32
+__global__ void prelu_fwd_bf16x8_kernel(const uint4* __restrict__ z, const float* __restrict__ slope, uint4* __restrict__ y, long n8) {
+  const float a = *slope;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float f[8];
+    bf8_to_f(z[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) f[k] = f[k] > 0.f ? f[k] : a * f[k];
+    y[i] = f_to_bf8(f);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const void* __restrict__ src, void* __restrict__ dst, long n8, int to_bf16) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float f[8];
+    if (to_bf16) {
+      const float4* s4 = reinterpret_cast<const float4*>(src) + 2 * i;
+      float4 a = s4[0], b = s4[1];
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      reinterpret_cast<uint4*>(dst)[i] = f_to_bf8(f);
+    } else {
+      bf8_to_f(reinterpret_cast<const uint4*>(src)[i], f);
+      float4* d4 = reinterpret_cast<float4*>(dst) + 2 * i;
+      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
 __global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = 1.f / (1.f + expf(-x[i]));
@@ -592,6 +619,26 @@ __global__ void prelu_bwd_kernel(const float* __restrict__ z, const float* __res
       dz[i] = a * g;
       acc += g * v;
     }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+__global__ void prelu_bwd_bf16x8_kernel(const uint4* __restrict__ z, const uint4* __restrict__ dy, const float* __restrict__ slope,
+                                        uint4* __restrict__ dz, float* __restrict__ part, long n8) {
+  const float a = *slope;
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8], g[8];
+    bf8_to_f(z[i], v);
+    bf8_to_f(dy[i], g);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (!(v[k] > 0.f)) {
+        acc += g[k] * v[k];
+        g[k] *= a;
+      }
+    }
+    dz[i] = f_to_bf8(g);
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
@@ -887,6 +934,33 @@ int dasr_prelu_bwd(const float* z, const float* dy, const float* slope, float* d
   prelu_bwd_kernel<<<blocks, RED_THREADS, 0, st>>>(z, dy, slope, dz, partials, n);
   final_acc_kernel<<<1, 256, 0, st>>>(partials, dslope, blocks, accumulate);
   return check_launch("prelu_bwd");
+}
+int dasr_prelu_fwd_bf16(const void* z, const float* slope, void* y, long n, void* stream) {
+  DASR_REQUIRE(z && slope && y && n > 0 && n % 8 == 0, "prelu_fwd_bf16: n must be a multiple of 8");
+  long n8 = n / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 8 * 148) blocks = 8 * 148;
+  prelu_fwd_bf16x8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)z, slope, (uint4*)y, n8);
+  return check_launch("prelu_fwd_bf16");
+}
+int dasr_prelu_bwd_bf16(const void* z, const void* dy, const float* slope, void* dz, float* dslope, int accumulate, long n,
+                        float* partials, void* stream) {
+  DASR_REQUIRE(z && dy && slope && dz && dslope && partials && n > 0 && n % 8 == 0, "prelu_bwd_bf16: bad arguments");
+  long n8 = n / 8;
+  int blocks = (int)((n8 + RED_THREADS - 1) / RED_THREADS);
+  if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+  cudaStream_t st = (cudaStream_t)stream;
+  prelu_bwd_bf16x8_kernel<<<blocks, RED_THREADS, 0, st>>>((const uint4*)z, (const uint4*)dy, slope, (uint4*)dz, partials, n8);
+  final_acc_kernel<<<1, 256, 0, st>>>(partials, dslope, blocks, accumulate);
+  return check_launch("prelu_bwd_bf16");
+}
+int dasr_cast_bf16_f32(const void* src, void* dst, long n, int to_bf16, void* stream) {
+  DASR_REQUIRE(src && dst && n > 0 && n % 8 == 0, "cast: n must be a multiple of 8");
+  long n8 = n / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 8 * 148) blocks = 8 * 148;
+  cast_bf16_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n8, to_bf16);
+  return check_launch("cast");
 }
 int dasr_sigmoid_fwd(const float* x, float* y, long n, void* stream) {
   DASR_REQUIRE(x && y && n > 0, "sigmoid_fwd: bad arguments");

@@ -90,6 +90,30 @@ class De_resnet(_SeqNet):
         # like the reference (model.py:33-52), any other scale leaves `down_sample` undefined and forward raises
         self.block_output = nn.Conv2d(64, 3, kernel_size=3, padding=1)
 
+    precision = None     # None -> DASR_B200_TRAIN_PRECISION or 'fp32'; 'bf16' = tcgen05 trunk (dsn/engine_bf16.py)
+
+    def _tail_spec(self):
+        s = []
+        for j in range(len(self.down_sample) // 2):
+            s += [{'op': 'conv', 'k': 3, 's': 2, 'p': 1, 'w': 'down_sample.%d.weight' % (2 * j),
+                   'b': 'down_sample.%d.bias' % (2 * j), 'act': ACT_NONE},
+                  {'op': 'prelu', 'a': 'down_sample.%d.weight' % (2 * j + 1)}]
+        s += [{'op': 'conv', 'k': 3, 's': 1, 'p': 1, 'w': 'block_output.weight', 'b': 'block_output.bias', 'act': ACT_NONE},
+              {'op': 'sigmoid'}]
+        return s
+
+    def forward(self, x):
+        import os
+        prec = self.precision or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')
+        if prec != 'bf16':
+            return super().forward(x)
+        from dasr_b200.dsn import engine_bf16
+        named = list(self.named_parameters())
+        n_trunk = 3 + 5 * len(self.res_blocks)
+        tail_named = named[n_trunk:]
+        tail_layers = _plan(tail_named, self._tail_spec())
+        return engine_bf16.DeResnetBF16Function.apply(x, len(self.res_blocks), tail_layers, n_trunk, *[p for _, p in named])
+
     def _spec(self):
         s = [{'op': 'conv', 'k': 3, 's': 1, 'p': 1, 'w': 'block_input.0.weight', 'b': 'block_input.0.bias', 'act': ACT_NONE},
              {'op': 'prelu', 'a': 'block_input.1.weight'}]

@@ -382,10 +382,15 @@ def log_loss(x, one_minus, eps, loss, grad, gscale):
 # --------------------------------------------------------------------------------------------------
 
 def prelu_fwd(z, slope, y):
+    if z.dtype == torch.bfloat16:
+        return check(_lib.load().dasr_prelu_fwd_bf16(_p(z), _p(slope), _p(y), z.numel(), _stream()), 'prelu_fwd_bf16')
     check(_lib.load().dasr_prelu_fwd(_p(z), _p(slope), _p(y), z.numel(), _stream()), 'prelu_fwd')
 
 
 def prelu_bwd(z, dy, slope, dz, dslope, accumulate=False):
+    if z.dtype == torch.bfloat16:
+        return check(_lib.load().dasr_prelu_bwd_bf16(_p(z), _p(dy), _p(slope), _p(dz), _p(dslope), int(accumulate), z.numel(),
+                                                     _p(_partials(z.device)), _stream()), 'prelu_bwd_bf16', 2)
     check(_lib.load().dasr_prelu_bwd(_p(z), _p(dy), _p(slope), _p(dz), _p(dslope), int(accumulate), z.numel(),
                                      _p(_partials(z.device)), _stream()), 'prelu_bwd', 2)
 
@@ -396,3 +401,10 @@ def sigmoid_fwd(x, y):
 
 def sigmoid_bwd(y, dy, dx):
     check(_lib.load().dasr_sigmoid_bwd(_p(y), _p(dy), _p(dx), y.numel(), _stream()), 'sigmoid_bwd')
+
+
+def cast(src, dst):
+    """bf16 <-> fp32 copy of equally shaped contiguous tensors (dasr_cast_bf16_f32)."""
+    to_bf16 = dst.dtype == torch.bfloat16
+    assert src.dtype == (torch.float32 if to_bf16 else torch.bfloat16) and src.numel() == dst.numel()
+    check(_lib.load().dasr_cast_bf16_f32(_p(src), _p(dst), src.numel(), int(to_bf16), _stream()), 'cast')

@@ -25,6 +25,18 @@ def forward(x, layers, params, save=True):
     N, C0, H, W = x.shape
     a = torch.empty((N, H, W, C0), dtype=torch.float32, device=x.device)
     ops.nchw_to_nhwc(x.contiguous().float(), a)
+    last, ctx = forward_nhwc(a, layers, params, save)
+    out = torch.empty((last.shape[0], last.shape[3], last.shape[1], last.shape[2]), dtype=torch.float32, device=x.device)
+    ops.nhwc_to_nchw(last, out)
+    if ctx is not None:
+        ctx['shape'] = (N, C0, H, W)
+    return out, ctx
+
+
+def forward_nhwc(a, layers, params, save=True):
+    """a: NHWC fp32 activation.  Returns (NHWC fp32 output, ctx)."""
+    x = a
+    H, W = a.shape[1], a.shape[2]
     acts, aux, res_stack = [a], [], []
     for L in layers:
         cur = acts[-1]
@@ -64,20 +76,29 @@ def forward(x, layers, params, save=True):
         else:
             raise ValueError(op)
         acts.append(o)
-    last = acts[-1]
-    out = torch.empty((last.shape[0], last.shape[3], last.shape[1], last.shape[2]), dtype=torch.float32, device=x.device)
-    ops.nhwc_to_nchw(last, out)
-    ctx = dict(acts=acts, aux=aux, shape=(N, C0, H, W)) if save else None
-    return out, ctx
+    ctx = dict(acts=acts, aux=aux) if save else None
+    return acts[-1], ctx
 
 
 def backward(ctx, layers, params, dout, need_dx=True, need_dw=True):
     """Returns (dx NCHW | None, grads list aligned with params (None where a param got no gradient))."""
-    acts, aux = ctx['acts'], ctx['aux']
+    acts = ctx['acts']
     N, C0, H, W = ctx['shape']
-    grads = [None] * len(params)
     g = torch.empty(tuple(acts[-1].shape), dtype=torch.float32, device=dout.device)
     ops.nchw_to_nhwc(dout.contiguous().float(), g)
+    g, grads = backward_nhwc(ctx, layers, params, g, need_dx, need_dw)
+    dx = None
+    if need_dx:
+        dx = torch.empty((N, C0, H, W), dtype=torch.float32, device=dout.device)
+        ops.nhwc_to_nchw(g, dx)
+    return dx, grads
+
+
+def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
+    """g: NHWC fp32 gradient of the output (may be modified in place).  Returns (NHWC input gradient | None, grads)."""
+    acts, aux = ctx['acts'], ctx['aux']
+    dout = g
+    grads = [None] * len(params)
     skip_stack = []
     first_conv = next(i for i, L in enumerate(layers) if L['op'] == 'conv')
     for li in reversed(range(len(layers))):
@@ -119,11 +140,7 @@ def backward(ctx, layers, params, dout, need_dx=True, need_dw=True):
         elif op == 'res_begin':
             gs = skip_stack.pop()
             ops.axpby(g, 1.0, gs, 1.0, g)
-    dx = None
-    if need_dx:
-        dx = torch.empty((N, C0, H, W), dtype=torch.float32, device=dout.device)
-        ops.nhwc_to_nchw(g, dx)
-    return dx, grads
+    return (g if need_dx else None), grads
 
 
 class SeqFunction(torch.autograd.Function):

@@ -301,6 +301,12 @@ int dasr_log_loss(const float* x, int one_minus, float eps, float* loss, float* 
 int dasr_prelu_fwd(const float* z, const float* slope, float* y, long n, void* stream);
 int dasr_prelu_bwd(const float* z, const float* dy, const float* slope, float* dz, float* dslope, int accumulate,
                    long n, float* partials, void* stream);
+/* the same on bf16 tensors (n % 8 == 0; slope and its gradient stay fp32) and a dtype cast between the bf16 tensor-core
+ * layers and the fp32 layers of the mixed-precision De_resnet (to_bf16: fp32 -> bf16, else bf16 -> fp32) */
+int dasr_prelu_fwd_bf16(const void* z, const float* slope, void* y, long n, void* stream);
+int dasr_prelu_bwd_bf16(const void* z, const void* dy, const float* slope, void* dz, float* dslope, int accumulate,
+                        long n, float* partials, void* stream);
+int dasr_cast_bf16_f32(const void* src, void* dst, long n, int to_bf16, void* stream);
 /* torch.sigmoid fwd / bwd (dx = dy * y * (1 - y)), fp32 (DSN/model.py:55,103) */
 int dasr_sigmoid_fwd(const float* x, float* y, long n, void* stream);
 int dasr_sigmoid_bwd(const float* y, const float* dy, float* dx, long n, void* stream);

@@ -8,10 +8,11 @@ import bench
 class A: train_steps = 3
 torch.cuda.set_device(0)
 dev = torch.device('cuda', 0)
-res = bench.bench_dsn(A, dev, 0, 1, torch.cuda.synchronize, lambda ms: ms)
+prec = os.environ.get('TRAIN_PREC', 'fp32')
+res = bench.bench_dsn(A, dev, 0, 1, torch.cuda.synchronize, lambda ms: ms, prec)
 print('standalone ms/iteration', res['ms_per_step'], flush=True)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    res = bench.bench_dsn(A, dev, 0, 1, torch.cuda.synchronize, lambda ms: ms)
+    res = bench.bench_dsn(A, dev, 0, 1, torch.cuda.synchronize, lambda ms: ms, prec)
 print('under profiler ms/iteration', res['ms_per_step'])
 tot = {}
 for e in prof.key_averages():
