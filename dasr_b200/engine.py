@@ -752,6 +752,7 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
 
     GB = _empty((N, H, W, CS), dev, bf)
     g_x5 = _empty((N, H, W, nf), dev, bf)
+    fused_wgrad = nf == 64 and GC == 32 and os.environ.get('DASR_B200_RDB_WGRAD', '1') == '1'
     g_rrdb = None
     for r in reversed(range(n_rdb)):
         b = bufs[r]
@@ -762,7 +763,10 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
             a5, b1 = 0.2, 1.0
         ops.axpby(g_y, a5, None, 0.0, g_x5)
         ci = L.rdb_conv(r, 5)
-        wgrad(View(b, CS, 0), g_x5, ci)
+        if fused_wgrad:
+            ops.bias_grad(g_x5, gB(ci))
+        else:
+            wgrad(View(b, CS, 0), g_x5, ci)
         ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)        # K=64 -> N=192 as 2 x 96
         ops.axpby(View(GB, nf, 0), 1.0, g_y, b1, View(GB, nf, 0))
         for k in (4, 3, 2, 1):
@@ -770,12 +774,15 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
             cin = _rdb_cin(nf, k)
             gk = View(GB, GC, nf + (k - 1) * GC)
             ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
-            wgrad(View(b, cin, 0), gk, ci, bias=False)
+            if not fused_wgrad:
+                wgrad(View(b, cin, 0), gk, ci, bias=False)
             o = View(GB, cin, 0)
             ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                          # accumulate in place
         # bias gradients of conv1..4 in one reduction: their masked output gradients are the final x1..x4 slices of GB
         c1 = L.rdb_conv(r, 1)
         ops.bias_grad(View(GB, 4 * GC, nf), flat[b_off[c1]:b_off[c1] + 4 * GC])
+        if fused_wgrad:     # all five filter gradients of the block: one tcgen05 launch + one reduction
+            ops.rdb_wgrad_tc(b, GB, nf, g_x5, 0, [gW(L.rdb_conv(r, k)) for k in range(1, 6)])
         g_new = _empty((N, H, W, nf), dev, bf)
         if r % 3 == 0 and g_rrdb is not None:
             ops.axpby(View(GB, nf, 0), 1.0, g_rrdb, 1.0, g_new)

@@ -122,6 +122,17 @@ def conv3x3_wgrad_tc(x, dy, dw, accumulate=False):
                                     _p(ws), ws.numel(), _stream()), 'conv3x3_wgrad_tc', 2)
 
 
+def rdb_wgrad_tc(xbuf, ga, ga_coff, gb, gb_coff, dws, accumulate=False):
+    """filter gradients of the five convs of a dense block (dasr_rdb_wgrad_tc); dws = [dW1..dW5] fp32 OIHW."""
+    N, H, W, _ = xbuf.shape
+    lib = _lib.load()
+    n = lib.dasr_rdb_wgrad_tc_workspace(N, H, W)
+    ws = _workspace(n, xbuf.device)
+    ptrs = (C.c_void_p * 5)(*[_p(t).value for t in dws])
+    check(lib.dasr_rdb_wgrad_tc(_p(xbuf), xbuf.shape[-1], _p(ga), ga.shape[-1], ga_coff, _p(gb), gb.shape[-1], gb_coff, ptrs,
+                                N, H, W, int(accumulate), _p(ws), ws.numel(), _stream()), 'rdb_wgrad_tc', 2)
+
+
 _bg_cache = {}
 
 

@@ -240,6 +240,15 @@ int dasr_rdb_tc(void* buf, void* buf_next, const void* buf_res2, const void* con
                 const float* const* bias, const DasrRdbParams* p, unsigned int* counter, int* error_flag,
                 void* stream);
 
+/* Filter gradients of all five convs of one ResidualDenseBlock_5C (nf 64, gc 32) in one tcgen05 launch + one
+ * deterministic reduction (mixed-precision training).  xbuf: bf16 NHWC, channels [x 0:64 | x1..x4 64:192];
+ * ga: bf16 NHWC holding the (LeakyReLU-masked) output gradients of conv1..4 in channels [ga_coff, ga_coff+128);
+ * gb: output gradient of conv5 in channels [gb_coff, gb_coff+64); dw[k]: OIHW fp32 [32|64][64+32k][3][3]. */
+size_t dasr_rdb_wgrad_tc_workspace(int N, int H, int W);
+int dasr_rdb_wgrad_tc(const void* xbuf, int x_cs, const void* ga, int ga_cs, int ga_coff, const void* gb, int gb_cs,
+                      int gb_coff, float* const* dw, int N, int H, int W, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* 2x2 s2 max-pool NHWC fp32 fwd / bwd (VGG19 features, architecture.py:1076) */
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
 int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H,

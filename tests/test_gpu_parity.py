@@ -250,6 +250,30 @@ def test_persistent_rdb_kernel_is_bit_identical_to_stage_launches(shape, chunk, 
     assert torch.equal(ref, got)
 
 
+@pytest.mark.parametrize('shape', [(2, 16, 24), (3, 40, 24), (1, 64, 64)])
+def test_rdb_wgrad_kernel_matches_per_conv_wgrad(shape):
+    """dasr_rdb_wgrad_tc (five filter gradients of a dense block, 7 (row tile, columns, taps) jobs in one launch) against
+    five dasr_conv3x3_wgrad_tc launches on the same bf16 operands: same products, different fp32 summation order."""
+    from dasr_b200 import ops
+    N, H, W = shape
+    xb = O.synth((N, H, W, 256), 21, 1.0).bfloat16().cuda()
+    ga = O.synth((N, H, W, 192), 22, 1.0).bfloat16().cuda()
+    gb = O.synth((N, H, W, 64), 23, 1.0).bfloat16().cuda()
+    ref, got = [], []
+    for k in range(1, 6):
+        cin, cout = 64 + 32 * (k - 1), (32 if k < 5 else 64)
+        r = torch.empty((cout, cin, 3, 3), device='cuda')
+        dy = ops.View(ga, 32, 64 + 32 * (k - 1)) if k < 5 else ops.View(gb, 64, 0)
+        ops.conv3x3_wgrad_tc(ops.View(xb, cin, 0), dy, r)
+        ref.append(r)
+        got.append(torch.full((cout, cin, 3, 3), float('nan'), device='cuda'))
+    ops.rdb_wgrad_tc(xb, ga, 64, gb, 0, got)
+    torch.cuda.synchronize()
+    for k in range(5):
+        err = float((got[k] - ref[k]).abs().max() / ref[k].abs().max())
+        assert err < 1e-5, (k + 1, err)
+
+
 def test_batch_packer_matches_per_filter_packs():
     """dasr_pack_filter_tc_batch (one launch, device job table) writes bit-identical kernel-layout filters to the
     per-filter path for every key the mixed-precision forward/backward asks for."""
