@@ -237,8 +237,11 @@ class DASR_Model(BaseModel):
 
         if do_D:
             if self.l_gan_H_target_w > 0:
-                pred_d_target_real = self.netD_target(self.real_HR_Hf_target.detach())
-                pred_d_target_fake = self.netD_target(self.fake_SR_Hf_target.detach())
+                # one discriminator pass over [real | fake] (DASR_model.py:271-272 runs two): InstanceNorm statistics are
+                # per sample, so the scores and the parameter gradients are the same sums
+                nreal = self.real_HR_Hf_target.shape[0]
+                pred_d = self.netD_target(torch.cat([self.real_HR_Hf_target.detach(), self.fake_SR_Hf_target.detach()], 0))
+                pred_d_target_real, pred_d_target_fake = pred_d[:nreal], pred_d[nreal:]
                 l_d_target_real = self.cri_gan(pred_d_target_real, True)
                 l_d_target_fake = self.cri_gan(pred_d_target_fake, False)
                 l_d_target_total = (l_d_target_real + l_d_target_fake) / 2
