@@ -746,7 +746,8 @@ static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, width == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   (width == 32 && cs > 32) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
     return DASR_E_LAUNCH;
@@ -867,8 +868,11 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
     cuuint32_t box[4] = {CHUNK, (cuuint32_t)(p->a_mode == 0 ? HALO_W : TILE_W),
                          (cuuint32_t)(p->a_mode == 0 ? HALO_H : TILE_H), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    // a 32-channel chunk is 64 B of a wider pixel row: promoting its L2 fills to 128 B doubled the DRAM reads of A
+    // (ncu: dram__bytes_read 311 MB for 234 MB requested by the SMs in a one-chunk launch)
     CUresult r = enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     p->in_cs > CHUNK ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r);

@@ -299,7 +299,7 @@ int dasr_conv3x3_wgrad_tc(const void* x, int x_cs, int x_coff, const void* dy, i
     cuuint32_t box[4] = {32, (cuuint32_t)(t ? wg::TILE_W : wg::HALO_W), (cuuint32_t)(t ? wg::TILE_H : wg::HALO_H), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(t ? &tmy : &tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("wgrad_tc: cuTensorMapEncodeTiled failed: %d", (int)r);
