@@ -84,9 +84,38 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def synth_weights(nb):
-    from oracle import srn_oracle as O           # deterministic synthetic weights only (bench legs may use oracle/)
-    return O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 1, 0.1)
+def synth(shape, seed, scale=1.0, offset=0.0):
+    """Deterministic pseudo-random fp32 tensor (64-bit mix hash of the element index; no RNG state, identical on every
+    rank / box).  The GPU arms generate their inputs and weights with this; oracle/ is only imported by the CPU legs."""
+    import numpy as np
+    import torch
+    n = 1
+    for d in shape:
+        n *= int(d)
+    x = np.arange(n, dtype=np.uint64) + np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+    for mul in (0xFF51AFD7ED558CCD, 0xC4CEB9FE1A85EC53):
+        x ^= x >> np.uint64(33)
+        x = (x * np.uint64(mul)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x ^= x >> np.uint64(33)
+    u = (x >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+    return torch.from_numpy(((u * 2.0 - 1.0) * scale + offset).astype(np.float32)).reshape(tuple(shape))
+
+
+def synth_image(shape, seed):
+    return synth(shape, seed, 0.5, 0.5)
+
+
+def synth_weights(net, seed=1, gain=0.1):
+    """Kaiming-like magnitudes for every tensor of net.state_dict() (random-init stand-in: no checkpoints offline)."""
+    import math
+    sd = {}
+    for i, (k, v) in enumerate(net.state_dict().items()):
+        if v.dim() == 4:
+            bound = gain * math.sqrt(2.0 / (v.shape[1] * v.shape[2] * v.shape[3])) * math.sqrt(3.0)
+            sd[k] = synth(tuple(v.shape), seed * 1000 + i, bound)
+        else:
+            sd[k] = synth(tuple(v.shape), seed * 1000 + i, 0.05)
+    return sd
 
 
 def pick_threads():
@@ -174,7 +203,6 @@ def main():
     from dasr_b200 import _lib
     from dasr_b200.srn.models import create_model
     from dasr_b200.srn.options.options import dict_to_nonedict
-    from oracle import srn_oracle as O
     W, K = max(args.warmup, 3), max(args.steps, 1)
 
     def barrier():
@@ -196,11 +224,11 @@ def main():
                       'out_nc': 3, 'gc': 32, 'scale': 4}})
     model = create_model(opt)
     netG = model.netG.module if hasattr(model.netG, 'module') else model.netG
-    netG.load_state_dict(synth_weights(NB))
+    netG.load_state_dict(synth_weights(netG))
     netG.precision = os.environ.get('DASR_BENCH_PRECISION', 'bf16')   # 'bf16' (dense-block N-fused) | 'bf16_layer'
     netG.eval()
 
-    x_host = O.synth_image((BATCH, 3, LR, LR), 100 + rank).pin_memory()
+    x_host = synth_image((BATCH, 3, LR, LR), 100 + rank).pin_memory()
     x_dev = x_host.to(dev)
     y_host = torch.empty((BATCH, 3, 4 * LR, 4 * LR), dtype=torch.float32).pin_memory()
 
@@ -336,7 +364,6 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision
     from dasr_b200 import _lib
     from dasr_b200.srn.models import create_model
     from dasr_b200.srn.options.options import dict_to_nonedict
-    from oracle import srn_oracle as O
     B, h = 32, 32
     opt = dict_to_nonedict({
         'name': 'bench_train', 'model': 'DASR', 'scale': 4, 'gpu_ids': [local_rank], 'is_train': True, 'chop': False,
@@ -360,9 +387,9 @@ def bench_train(args, dev, local_rank, world, barrier, max_over_ranks, precision
     if f is not None:
         (f.module if hasattr(f, 'module') else f).precision = precision
     rank = int(os.environ.get('RANK', 0))
-    data = {'LR_real': O.synth_image((B, 3, h, h), 200 + rank).pin_memory(), 'LR_fake': O.synth_image((B, 3, h, h), 300 + rank).pin_memory(),
-            'HR': O.synth_image((B, 3, 4 * h, 4 * h), 400 + rank).pin_memory(), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * h), 500 + rank).pin_memory(),
-            'fake_w': O.synth_image((B, 1, h, h), 600 + rank).pin_memory()}
+    data = {'LR_real': synth_image((B, 3, h, h), 200 + rank).pin_memory(), 'LR_fake': synth_image((B, 3, h, h), 300 + rank).pin_memory(),
+            'HR': synth_image((B, 3, 4 * h, 4 * h), 400 + rank).pin_memory(), 'HR_unpair': synth_image((B, 3, 4 * h, 4 * h), 500 + rank).pin_memory(),
+            'fake_w': synth_image((B, 1, h, h), 600 + rank).pin_memory()}
     step = 0
     for _ in range(2):
         step += 1
@@ -400,7 +427,6 @@ def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, precision='fp32')
     from dasr_b200.dsn.loss import GeneratorLoss
     from dasr_b200.dsn.model import De_resnet, Discriminator
     from dasr_b200.dsn.train import train_iteration
-    from oracle import srn_oracle as O
     import contextlib
     import io
     torch.manual_seed(0)
@@ -414,9 +440,9 @@ def bench_dsn(args, dev, rank, world, barrier, max_over_ranks, precision='fp32')
     og = torch.optim.Adam(mg.parameters(), lr=1e-4, betas=[0.5, 0.999])
     od = torch.optim.Adam(md.parameters(), lr=1e-4, betas=[0.5, 0.999])
     B = 8
-    inp = O.synth_image((B, 3, 256, 256), 700 + rank).to(dev)
-    bic = O.synth_image((B, 3, 64, 64), 800 + rank).to(dev)
-    dis = O.synth_image((B, 3, 64, 64), 900 + rank).to(dev)
+    inp = synth_image((B, 3, 256, 256), 700 + rank).to(dev)
+    bic = synth_image((B, 3, 64, 64), 800 + rank).to(dev)
+    dis = synth_image((B, 3, 64, 64), 900 + rank).to(dev)
     sync = None
     if world > 1:
         import torch.distributed as dist
