@@ -156,3 +156,40 @@ def test_dsn_modules_match_reference_state_dict_layout():
     assert [(k, tuple(v.shape)) for k, v in d.state_dict().items()] == list(D.fsd_shapes(9).items())
     with pytest.raises(DasrError):
         net(torch.zeros(1, 3, 16, 16))
+
+
+def test_reference_test_py_runs_unchanged_through_the_launcher(tmp_path):
+    """Drop-in boundary: the reference's own codes/SRN/test.py, executed unchanged by dasr_b200.launch, parses its JSON,
+    builds its dataset/dataloader with the reference's data/ package, creates the model through the mirror and reaches
+    the first kernel call — which must refuse loudly on this GPU-less host (no CPU fallback).  Skipped where the
+    reference checkout is absent (the GPU box)."""
+    import json
+    import subprocess
+    import sys
+    import numpy as np
+    import pytest
+    ref = '/root/reference/codes/SRN/test.py'
+    if not os.path.exists(ref):
+        pytest.skip('reference checkout not present')
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.RandomState(0)
+    (tmp_path / 'LR').mkdir()
+    (tmp_path / 'HR').mkdir()
+    cv2.imwrite(str(tmp_path / 'LR' / 'a.png'), (rng.rand(16, 16, 3) * 255).astype(np.uint8))
+    cv2.imwrite(str(tmp_path / 'HR' / 'a.png'), (rng.rand(64, 64, 3) * 255).astype(np.uint8))
+    opt = {'name': 'dropin_test', 'suffix': None, 'model': 'sr', 'scale': 4, 'gpu_ids': None, 'chop': False, 'val_lpips': False,
+           'save_RealorFake': False,
+           'datasets': {'test_1': {'name': 'toy', 'mode': 'LRHR', 'dataroot_HR': str(tmp_path / 'HR'), 'dataroot_LR': str(tmp_path / 'LR')}},
+           'path': {'root': str(tmp_path / 'out'), 'pretrain_model_G': None},
+           'network_G': {'which_model_G': 'RRDB_net', 'norm_type': None, 'mode': 'CNA', 'nf': 64, 'nb': 1, 'in_nc': 3, 'out_nc': 3,
+                         'gc': 32, 'group': 1}}
+    cfg = tmp_path / 'test.json'
+    cfg.write_text(json.dumps(opt))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, os.path.join(root, 'oracle', 'ref_stubs')]), CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, '-m', 'dasr_b200.launch', ref, '-opt', str(cfg)], cwd=str(tmp_path), env=env,
+                       capture_output=True, text=True, timeout=600)
+    err = r.stderr + r.stdout
+    assert r.returncode != 0
+    assert 'dasr_b200/srn/models/SR_model.py' in err, err[-2000:]          # the mirror, not the reference's models package
+    assert 'no CPU fallback exists' in err, err[-2000:]
