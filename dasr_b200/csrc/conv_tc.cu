@@ -19,6 +19,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + elected-lane MMA issuer,
 // warps 2..9 = epilogue (TMEM -> registers -> bias/pre/act/scale/residuals -> bf16 tile in swizzled shared
 // memory -> TMA store; pre-activation addend and residual tiles arrive by TMA as well).
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace dasr {
@@ -44,6 +45,7 @@ struct TcKernelArgs {
   int tmem_cols;     // allocated TMEM columns (pow2 >= 2*nt, >= 32)
   int epi_bytes;     // bytes of ONE staged epilogue tile: 128 pixels x nt channels bf16
   int has_pre, has_res1, has_res2;
+  int alt_epi;       // 1: the two epilogue warpgroups take alternate TILES (all columns) instead of alternate column groups
   int nbuf;          // staged-epilogue tile buffers (2..4): pre / residual tiles are requested nbuf tiles ahead
   // cross-launch spatial pipelining (dense-block stages run CONCURRENTLY on disjoint SM subsets):
   //   dep{0,1}[k] = tiles finished by CTA k of a producer launch with dep_g CTAs (same tile order as this launch);
@@ -104,11 +106,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     mbar_init(w_bar, 1);
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], a.alt_epi ? 4 : 8);  // one arrive per epilogue warp that reads this accumulator
     }
     for (int b = 0; b < 4; b++) {
       mbar_init(&pre_bar[b], 1);
-      mbar_init(&sfull_bar[b], 8);
+      mbar_init(&sfull_bar[b], a.alt_epi ? 4 : 8);
       mbar_init(&sfree_bar[b], 1);
     }
     fence_barrier_init();
@@ -321,7 +323,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const uint32_t sS_u = smem_u32(sS), sR1_u = smem_u32(sR1), sR2_u = smem_u32(sR2), sBias_u = smem_u32(sBias);
     const bool has_bias = a.bias != nullptr;
     uint32_t it = 0;
+    const bool alt = a.alt_epi != 0;
+    const int g0 = alt ? 0 : wg, gs = alt ? 1 : 2;     // first column group and stride of this warp's groups
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+      if (alt && (int)(it & 1) != wg) continue;         // alternate-tile mode: the other warpgroup owns this tile
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
@@ -461,18 +466,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       };
       // two register sets: the next group's accumulators are in flight while the current group is processed
       uint32_t ra[16], rb[16];
-      if (wg < ngroups) tmem_ld16(t_addr + wg * 16, ra);
-      for (int g = wg; g < ngroups; g += 4) {
+      if (g0 < ngroups) tmem_ld16(t_addr + g0 * 16, ra);
+      for (int g = g0; g < ngroups; g += 2 * gs) {
         tmem_ld_wait();
-        if (g + 2 < ngroups) tmem_ld16(t_addr + (g + 2) * 16, rb); else release_acc();
+        if (g + gs < ngroups) tmem_ld16(t_addr + (g + gs) * 16, rb); else release_acc();
         process(ra, g);
-        if (g + 2 < ngroups) {
+        if (g + gs < ngroups) {
           tmem_ld_wait();
-          if (g + 4 < ngroups) tmem_ld16(t_addr + (g + 4) * 16, ra); else release_acc();
-          process(rb, g + 2);
+          if (g + 2 * gs < ngroups) tmem_ld16(t_addr + (g + 2 * gs) * 16, ra); else release_acc();
+          process(rb, g + gs);
         }
       }
-      if (wg >= ngroups) {
+      if (g0 >= ngroups) {
         // this warpgroup had no column group in the tile (nt == 16): still release the accumulator
         tc_fence_before();
         __syncwarp();
@@ -847,6 +852,14 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
     if (nbuf == 2 || avail >= 4 * a.a_stage_bytes) break;
   }
   a.nbuf = nbuf;
+  {
+    static int alt_env = -1;
+    if (alt_env < 0) {
+      const char* e = getenv("DASR_TC_ALT_EPI");
+      alt_env = e ? atoi(e) : 0;
+    }
+    a.alt_epi = (p->epi_mode == 0 && alt_env) ? 1 : 0;
+  }
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
