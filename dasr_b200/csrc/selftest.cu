@@ -486,6 +486,13 @@ int main(int argc, char** argv) {
       bench_tc_fused(16, 256, 256, 32, 128, 128, 1, 10);
       bench_tc_fused(16, 256, 256, 32, 96, 96, 1, 10);
       bench_tc_fused(16, 256, 256, 32, 64, 64, 1, 10);
+      // what bounds the one-chunk N=64 launch: partial-sum tiles (pre) or not, HBM (16 images) or L2 (2 images)
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 0, 10);
+      bench_tc_fused(2, 256, 256, 32, 64, 64, 1, 40);
+      bench_tc_fused(2, 256, 256, 32, 64, 64, 0, 40);
+      bench_tc_fused(16, 256, 256, 64, 64, 64, 1, 10);
+      bench_tc_fused(16, 256, 256, 64, 64, 64, 0, 10);
+      bench_tc_fused(2, 256, 256, 64, 64, 64, 0, 40);
       return 0;
     }
     if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes
