@@ -404,6 +404,7 @@ static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int w
   p.cout = cout; p.out_cs = cs; p.out_coff = cs - cout; p.nt = nt;
   p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.act_cols = 32; p.epi_mode = 0;
   p.pre_cs = cs; p.pre_coff = cs - cout;
+  if (getenv("EPI1") && !with_pre) p.epi_mode = 1;     // direct st.global epilogue instead of staged tile + TMA store
   dasr_pack_filter_tc(dw, dwp, cout, cin, 0, 0);
   void* pre = with_pre ? (void*)buf : nullptr;
   int rc = 0;
@@ -470,13 +471,18 @@ int main(int argc, char** argv) {
       return 0;
     }
     if (!strcmp(argv[i], "mmarate")) {
-      int ns[] = {16, 32, 48, 64, 96, 128, 160, 192, 256};
-      for (int sbo : {512, 640})
-        for (int n : ns) {
-          double c = 0;
-          int rc = dasr_probe_mma_rate(n, sbo, 200, 64, &c);
-          printf("mma_rate M128 N%-3d K16 sbo%d : %7.1f cycles/MMA  (ideal N/2=%d) rc=%d\n", n, sbo, c, n / 2, rc);
-        }
+      int ns[] = {32, 64, 96, 128, 192, 256};
+      // latency of a dependent accumulate chain (wait after every 18 MMAs, one accumulator) vs throughput (no waits), and
+      // 1 / 2 / 4 independent accumulators the MMAs rotate over
+      for (int nowait = 0; nowait <= 1; nowait++)
+        for (int nacc : {1, 2, 4})
+          for (int n : ns) {
+            if (n * nacc > 512) continue;
+            double c = 0;
+            int rc = dasr_probe_mma_rate(n, 640, 200, 64 | (nacc << 16) | (nowait << 20), &c);
+            printf("mma_rate M128 N%-3d K16 accumulators=%d %s : %7.1f cycles/MMA  (N/2=%d) rc=%d\n", n, nacc,
+                   nowait ? "back-to-back" : "wait/18     ", c, n / 2, rc);
+          }
       return 0;
     }
     if (!strcmp(argv[i], "fused")) {
