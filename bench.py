@@ -144,7 +144,7 @@ def cpu_reference_forward(n_images, lr, threads, steps, warmup):
     import torch
     from oracle import srn_oracle as O
     torch.set_num_threads(threads)
-    sd = synth_weights(NB)
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=NB), 1, 0.1)
     x = O.synth_image((n_images, 3, lr, lr), 7)
     with torch.no_grad():
         for _ in range(warmup):

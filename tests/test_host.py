@@ -193,3 +193,13 @@ def test_reference_test_py_runs_unchanged_through_the_launcher(tmp_path):
     assert r.returncode != 0
     assert 'dasr_b200/srn/models/SR_model.py' in err, err[-2000:]          # the mirror, not the reference's models package
     assert 'no CPU fallback exists' in err, err[-2000:]
+
+
+def test_bench_cpu_leg_and_generators_run():
+    """bench.py: the CPU reference leg runs (tiny image) and the local deterministic generator matches the oracle's."""
+    import torch
+    import bench
+    from oracle import srn_oracle as O
+    mp_s, dt = bench.cpu_reference_forward(1, 8, 2, 1, 0)
+    assert mp_s > 0 and dt > 0
+    assert torch.equal(bench.synth((2, 3, 5), 9, 0.5, 0.5), O.synth((2, 3, 5), 9, 0.5, 0.5))
