@@ -89,7 +89,8 @@ class RRDBNet(nn.Module):
             if tp == 'bf16':      # mixed precision: tcgen05 fprop / dgrad / wgrad, fp32 accumulation, fp32 filter gradients
                 graphs = None
                 if os.environ.get('DASR_B200_GRAPH', '1') != '0' and x.is_cuda and not x.requires_grad:
-                    key = (tuple(x.shape), x.device.index, id(params[0]))
+                    # the graphs hold raw parameter addresses: re-capture if any parameter storage moved (.to(), .float(), ...)
+                    key = (tuple(x.shape), x.device.index, hash(tuple(p.data_ptr() for p in params)))
                     graphs = self._train_graphs.get(key)
                     if graphs is None:
                         self._train_graphs.clear()
@@ -102,7 +103,8 @@ class RRDBNet(nn.Module):
             fn = lambda t: engine.rrdb_forward_bf16(t, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
             if os.environ.get('DASR_B200_GRAPH', '1') == '0' or not x.is_cuda or engine.PROFILE is not None:
                 return fn(x)
-            key = (tuple(x.shape), x.dtype, x.device.index, prec, sum(p._version for p in params), id(params[0]))
+            key = (tuple(x.shape), x.dtype, x.device.index, prec, sum(p._version for p in params),
+                   hash(tuple(p.data_ptr() for p in params)))
             g = self._graphs.get(key)
             if g is None:
                 if len(self._graphs) >= 2:        # each graph pins its activation pool: keep at most two shapes
