@@ -19,7 +19,6 @@ from collections import OrderedDict
 
 import torch
 import torch.nn as nn
-from torch.optim import lr_scheduler
 
 from dasr_b200 import dp, ops
 from dasr_b200.srn.utils.util import b_split, forward_chop
@@ -91,78 +90,48 @@ class DASR_Model(BaseModel):
             raise NotImplementedError('FS type [{:s}] not recognized.'.format(str(fs)))
 
         if self.is_train:
-            if train_opt['pixel_weight'] > 0:
-                l_pix_type = train_opt['pixel_criterion']
-                if l_pix_type == 'l1':
-                    self.cri_pix = L.L1Loss().to(self.device)
-                elif l_pix_type == 'l2':
-                    self.cri_pix = L.MSELoss().to(self.device)
-                else:
-                    raise NotImplementedError('Loss type [{:s}] not recognized.'.format(l_pix_type))
-                self.l_pix_w = train_opt['pixel_weight']
-                self.l_pix_LL_w = train_opt['pixel_LL_weight']
-                self.sup_LL = train_opt['sup_LL']
-            else:
-                logger.info('Remove pixel loss.')
-                self.cri_pix = None
-
-            self.l_fea_type = train_opt['feature_criterion']
-            if train_opt['feature_weight'] > 0:
-                if self.l_fea_type == 'l1':
-                    self.cri_fea = L.L1Loss().to(self.device)
-                elif self.l_fea_type == 'l2':
-                    self.cri_fea = L.MSELoss().to(self.device)
-                elif self.l_fea_type == 'LPIPS':
-                    raise NotImplementedError('feature_criterion LPIPS (AlexNet trunk) is a "next" row (SURVEY §8f.3); '
-                                              'use l1/l2 (VGG19 features)')
-                else:
-                    raise NotImplementedError('Loss type [{:s}] not recognized.'.format(self.l_fea_type))
-                self.l_fea_w = train_opt['feature_weight']
-            else:
-                logger.info('Remove feature loss.')
-                self.cri_fea = None
-            if self.cri_fea and self.l_fea_type in ['l1', 'l2']:
-                self.netF = networks.define_F(opt, use_bn=False).to(self.device)
-
-            self.G_update_inter = train_opt['G_update_inter'] or 1
-            self.D_update_inter = train_opt['D_update_inter'] or 1
-            self.D_update_ratio = train_opt['D_update_ratio'] if train_opt['D_update_ratio'] else 1
-            self.D_init_iters = train_opt['D_init_iters'] if train_opt['D_init_iters'] else 0
-
-            wd_G = train_opt['weight_decay_G'] if train_opt['weight_decay_G'] else 0
-            optim_params = []
-            for k, v in self.netG.named_parameters():
-                if v.requires_grad:
-                    optim_params.append(v)
-                else:
-                    logger.warning('Params [{:s}] will not optimize.'.format(k))
-            self.optimizer_G = torch.optim.Adam(optim_params, lr=train_opt['lr_G'], weight_decay=wd_G,
-                                                betas=(train_opt['beta1_G'], 0.999))
-            self.optimizers.append(self.optimizer_G)
-            wd_D = train_opt['weight_decay_D'] if train_opt['weight_decay_D'] else 0
-            if self.l_gan_H_target_w > 0:
-                self.optimizer_D_target = torch.optim.Adam(self.netD_target.parameters(), lr=train_opt['lr_D'],
-                                                           weight_decay=wd_D, betas=(train_opt['beta1_D'], 0.999))
-                self.optimizers.append(self.optimizer_D_target)
-            if self.l_gan_H_source_w > 0:
-                self.optimizer_D_source = torch.optim.Adam(self.netD_source.parameters(), lr=train_opt['lr_D'],
-                                                           weight_decay=wd_D, betas=(train_opt['beta1_D'], 0.999))
-                self.optimizers.append(self.optimizer_D_source)
-
-            if train_opt['lr_scheme'] == 'MultiStepLR':
-                for optimizer in self.optimizers:
-                    self.schedulers.append(lr_scheduler.MultiStepLR(optimizer, train_opt['lr_steps'], train_opt['lr_gamma']))
-            else:
-                raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
-            self.log_dict = OrderedDict()
-            self._log_t = OrderedDict()
-            # data parallel: one flat gradient bucket over [G | D_target | D_source]
-            nets = [self.netG] + ([self.netD_target] if self.l_gan_H_target_w > 0 else []) + \
-                   ([self.netD_source] if self.l_gan_H_source_w > 0 else [])
-            self.grad_sync = dp.GradBucket([p for n in nets for p in n.parameters() if p.requires_grad])
+            self._init_training(opt, train_opt)
         self.print_network()
         if self.val_lpips:
             logger.warning('val_lpips requested: LPIPS is not part of the B200 path; LPIPS is reported as nan')
+
+    def _init_training(self, opt, cfg):
+        """Losses, perceptual network, update cadence, optimisers and schedulers of the GAN step (DASR_model.py:75-151)."""
+        # pixel / LL losses
+        self.cri_pix = None
+        if cfg['pixel_weight'] > 0:
+            self.cri_pix = self._criterion(cfg['pixel_criterion'])
+            self.l_pix_w, self.l_pix_LL_w, self.sup_LL = cfg['pixel_weight'], cfg['pixel_LL_weight'], cfg['sup_LL']
+        else:
+            logger.info('Remove pixel loss.')
+        # perceptual loss on VGG19 features
+        self.cri_fea, self.l_fea_type = None, cfg['feature_criterion']
+        if cfg['feature_weight'] > 0:
+            if self.l_fea_type == 'LPIPS':
+                raise NotImplementedError('feature_criterion LPIPS (AlexNet trunk) is a "next" row (SURVEY §8f.3); '
+                                          'use l1/l2 (VGG19 features)')
+            self.cri_fea = self._criterion(self.l_fea_type)
+            self.l_fea_w = cfg['feature_weight']
+            self.netF = networks.define_F(opt, use_bn=False).to(self.device)
+        else:
+            logger.info('Remove feature loss.')
+        # update cadence
+        self.G_update_inter = cfg['G_update_inter'] or 1
+        self.D_update_inter = cfg['D_update_inter'] or 1
+        self.D_update_ratio = cfg['D_update_ratio'] or 1
+        self.D_init_iters = cfg['D_init_iters'] or 0
+        # optimisers: G first, then the discriminators that are switched on (order = checkpoint order)
+        self.optimizer_G = self._adam(self.netG, cfg['lr_G'], cfg['weight_decay_G'], cfg['beta1_G'])
+        trained = [self.netG]
+        for weight, attr in ((self.l_gan_H_target_w, 'target'), (self.l_gan_H_source_w, 'source')):
+            if weight > 0:
+                net = getattr(self, 'netD_' + attr)
+                setattr(self, 'optimizer_D_' + attr, self._adam(net, cfg['lr_D'], cfg['weight_decay_D'], cfg['beta1_D']))
+                trained.append(net)
+        self._make_schedulers(cfg)
+        self.log_dict, self._log_t = OrderedDict(), OrderedDict()
+        # data parallel: one flat gradient bucket over [G | D_target | D_source]
+        self.grad_sync = dp.GradBucket([p for n in trained for p in n.parameters() if p.requires_grad])
 
     # ------------------------------------------------------------------------------------------ data
     def feed_data(self, data, istrain):
@@ -335,13 +304,7 @@ class DASR_Model(BaseModel):
             if self.cri_fea and self.l_fea_type in ['l1', 'l2']:
                 nets.append(('F', self.netF))
         for label, net in nets:
-            s, n = self.get_network_description(net)
-            if isinstance(net, nn.DataParallel):
-                name = '{} - {}'.format(net.__class__.__name__, net.module.__class__.__name__)
-            else:
-                name = '{}'.format(net.__class__.__name__)
-            logger.info('Network {} structure: {}, with parameters: {:,d}'.format(label, name, n))
-            logger.info(s)
+            self._log_network(net, label)
 
     def load(self):
         path = self.opt['path']

@@ -1,19 +1,29 @@
-"""BaseModel: device pick, LR stepping, network / training-state save + load
-(reference: codes/SRN/models/base_model.py:6-85; file names and dict layout are the checkpoint contract)."""
+"""BaseModel of the SRN mirror: device selection, schedulers, checkpoint files (reference: codes/SRN/models/
+base_model.py:6-85 — the file names `{iter}_{label}.pth`, `{iter}.state` and their dict layout are the checkpoint
+contract), plus the small factories the model classes share."""
+import logging
 import os
 
 import torch
 import torch.nn as nn
+from torch.optim import lr_scheduler
+
+logger = logging.getLogger('base')
+
+
+def unwrap(net):
+    """The module behind an optional nn.DataParallel wrapper."""
+    return net.module if isinstance(net, nn.DataParallel) else net
 
 
 class BaseModel():
     def __init__(self, opt):
         self.opt = opt
-        self.device = torch.device('cuda' if opt['gpu_ids'] is not None else 'cpu')
         self.is_train = opt['is_train']
-        self.schedulers = []
-        self.optimizers = []
+        self.device = torch.device('cpu' if opt['gpu_ids'] is None else 'cuda')
+        self.optimizers, self.schedulers = [], []
 
+    # --- interface stubs the concrete models override -------------------------------------------------
     def feed_data(self, data):
         pass
 
@@ -35,41 +45,73 @@ class BaseModel():
     def load(self):
         pass
 
+    # --- shared factories ------------------------------------------------------------------------------
+    def _criterion(self, kind, what='Loss'):
+        """'l1' | 'l2' -> fused value+gradient loss module on this model's device."""
+        from .modules import loss as L
+        table = {'l1': L.L1Loss, 'l2': L.MSELoss}
+        if kind not in table:
+            raise NotImplementedError('{} type [{:s}] not recognized.'.format(what, str(kind)))
+        return table[kind]().to(self.device)
+
+    def _adam(self, net, lr, weight_decay, beta1=None):
+        """Adam over the trainable parameters of `net` (frozen ones are reported like the reference does)."""
+        trainable = []
+        for name, p in net.named_parameters():
+            if p.requires_grad:
+                trainable.append(p)
+            else:
+                logger.warning('Params [{:s}] will not optimize.'.format(name))
+        kw = {} if beta1 is None else {'betas': (beta1, 0.999)}
+        opt = torch.optim.Adam(trainable, lr=lr, weight_decay=weight_decay or 0, **kw)
+        self.optimizers.append(opt)
+        return opt
+
+    def _make_schedulers(self, train_opt):
+        if train_opt['lr_scheme'] != 'MultiStepLR':
+            raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
+        self.schedulers.extend(lr_scheduler.MultiStepLR(o, train_opt['lr_steps'], train_opt['lr_gamma']) for o in self.optimizers)
+
+    def _log_network(self, net, tag):
+        text, count = self.get_network_description(net)
+        inner = unwrap(net).__class__.__name__
+        name = '{} - {}'.format(net.__class__.__name__, inner) if isinstance(net, nn.DataParallel) else inner
+        logger.info('Network {} structure: {}, with parameters: {:,d}'.format(tag, name, count))
+        logger.info(text)
+
+    # --- learning rate ----------------------------------------------------------------------------------
     def update_learning_rate(self):
-        for scheduler in self.schedulers:
-            scheduler.step()
+        for sch in self.schedulers:
+            sch.step()
 
     def get_current_learning_rate(self):
-        s = self.schedulers[0]
-        return (s.get_last_lr() if hasattr(s, 'get_last_lr') else s.get_lr())[0]
+        first = self.schedulers[0]
+        lrs = first.get_last_lr() if hasattr(first, 'get_last_lr') else first.get_lr()
+        return lrs[0]
 
-    @staticmethod
-    def _unwrap(network):
-        return network.module if isinstance(network, nn.DataParallel) else network
+    # --- checkpoints --------------------------------------------------------------------------------------
+    _unwrap = staticmethod(unwrap)
 
     def get_network_description(self, network):
-        network = self._unwrap(network)
-        return str(network), sum(p.numel() for p in network.parameters())
+        net = unwrap(network)
+        return str(net), sum(p.numel() for p in net.parameters())
 
     def save_network(self, network, network_label, iter_step):
-        path = os.path.join(self.opt['path']['models'], '{}_{}.pth'.format(iter_step, network_label))
-        sd = self._unwrap(network).state_dict()
-        torch.save({k: v.cpu() for k, v in sd.items()}, path)
+        target = os.path.join(self.opt['path']['models'], '{}_{}.pth'.format(iter_step, network_label))
+        torch.save({k: t.cpu() for k, t in unwrap(network).state_dict().items()}, target)
 
     def load_network(self, load_path, network, strict=True):
-        self._unwrap(network).load_state_dict(torch.load(load_path, map_location='cpu'), strict=strict)
+        unwrap(network).load_state_dict(torch.load(load_path, map_location='cpu'), strict=strict)
 
     def save_training_state(self, epoch, iter_step):
-        state = {'epoch': epoch, 'iter': iter_step,
-                 'schedulers': [s.state_dict() for s in self.schedulers],
-                 'optimizers': [o.state_dict() for o in self.optimizers]}
-        torch.save(state, os.path.join(self.opt['path']['training_state'], '{}.state'.format(iter_step)))
+        snapshot = {'epoch': epoch, 'iter': iter_step,
+                    'schedulers': [s.state_dict() for s in self.schedulers],
+                    'optimizers': [o.state_dict() for o in self.optimizers]}
+        torch.save(snapshot, os.path.join(self.opt['path']['training_state'], '{}.state'.format(iter_step)))
 
     def resume_training(self, resume_state, opt=None):
-        ro, rs = resume_state['optimizers'], resume_state['schedulers']
-        assert len(ro) == len(self.optimizers), 'Wrong lengths of optimizers'
-        assert len(rs) == len(self.schedulers), 'Wrong lengths of schedulers'
-        for o, st in zip(self.optimizers, ro):
-            o.load_state_dict(st)
-        for s, st in zip(self.schedulers, rs):
-            s.load_state_dict(st)
+        for kind, mine in (('optimizers', self.optimizers), ('schedulers', self.schedulers)):
+            saved = resume_state[kind]
+            assert len(saved) == len(mine), 'Wrong lengths of {}'.format(kind)
+            for obj, st in zip(mine, saved):
+                obj.load_state_dict(st)
