@@ -89,3 +89,17 @@ def test_dsn_train_iterations(golden):
         assert rel_linf(sdG[k], ref) < 1e-4, k
     for k, ref in g['paramsD'].items():
         assert rel_linf(sdD[k], ref) < 1e-4, k
+
+
+def test_lpips_alex_oracle(golden):
+    """oracle/lpips_oracle.py (prepared for the LPIPS feature criterion) against the reference's PNetLin."""
+    from oracle import lpips_oracle as LP
+    g = golden('lpips_alex.pt')
+    sd = O.synth_state_dict(LP.alex_shapes(), g['w_seed'], 1.0)
+    pred = O.synth_image(g['shape'], g['pred_seed']).requires_grad_(True)
+    target = O.synth_image(g['shape'], g['target_seed'])
+    val = LP.lpips(pred, target, sd, g['lins'])
+    assert val.shape == g['value'].shape
+    assert rel_linf(val.detach(), g['value']) < 1e-5
+    val.mean().backward()
+    assert rel_linf(pred.grad, g['dpred']) < 1e-4
