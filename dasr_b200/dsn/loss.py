@@ -79,8 +79,11 @@ class _VGG16Features31(nn.Module):
         if os.path.exists(path):
             sd = torch.load(path, map_location='cpu')
             self.load_state_dict({k[len('features.'):]: v for k, v in sd.items() if k.startswith('features.')})
-        else:
-            warnings.warn('PerceptualLossVGG16: no pretrained VGG16 weights found offline; using random init')
+        elif os.environ.get('DASR_B200_ALLOW_RANDOM_VGG', '0') == '1':
+            warnings.warn('PerceptualLossVGG16: DASR_B200_ALLOW_RANDOM_VGG=1 — random-init VGG16 features')
+        else:     # the reference builds vgg16(pretrained=True) (DSN/loss.py:122): weights or failure, never random features
+            raise RuntimeError('PerceptualLossVGG16: no pretrained VGG16 weights at %s; supply torchvision\'s '
+                               'vgg16-397923af.pth or set DASR_B200_ALLOW_RANDOM_VGG=1 (tests / benchmarks only)' % path)
 
     def forward(self, x):
         prec = self.precision or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')

@@ -259,7 +259,11 @@ class _PackCache:
         self.d = {}
 
     def get(self, key, param, make):
-        ver = (param.data_ptr(), param._version)
+        """`param`: the tensor — or the list of ALL tensors — the cached value is derived from."""
+        if isinstance(param, (list, tuple)):
+            ver = tuple((q.data_ptr(), q._version) for q in param)
+        else:
+            ver = (param.data_ptr(), param._version)
         e = self.d.get(key)
         if e is None or e[0] != ver:
             e = (ver, make())
@@ -307,11 +311,13 @@ def _fused_rdb_filters(cache, params, L, r, nf, halves=False):
             b[:bj.shape[0]] = bj          # the bias of conv j is added when conv j completes (this launch)
             return b
 
-        ent = [cache.get(('fw', r, j), wj, make_w), cache.get(('fb', r, j), wj, make_b)]
+        wsrc = [params[2 * L.rdb_conv(r, k)] for k in ks]            # every filter the stack is built from
+        bj_p = params[2 * L.rdb_conv(r, j) + 1]
+        ent = [cache.get(('fw', r, j), wsrc, make_w), cache.get(('fb', r, j), bj_p, make_b)]
         if j == 1 and halves:   # the two Cout halves of launch 1 as separately packed filters (pipelined mode: two launches)
             half = (nf + 4 * GC) // 2
-            ent.append(cache.get(('fw1a', r), wj, lambda: ops.pack_filter_tc(stacked()[:half].contiguous(), TC_FPROP)))
-            ent.append(cache.get(('fw1b', r), wj, lambda: ops.pack_filter_tc(stacked()[half:].contiguous(), TC_FPROP)))
+            ent.append(cache.get(('fw1a', r), wsrc, lambda: ops.pack_filter_tc(stacked()[:half].contiguous(), TC_FPROP)))
+            ent.append(cache.get(('fw1b', r), wsrc, lambda: ops.pack_filter_tc(stacked()[half:].contiguous(), TC_FPROP)))
         out.append(tuple(ent))
     return out
 
@@ -347,7 +353,8 @@ def _sched2_rdb_filters(cache, params, L, r, nf):
             b = torch.zeros(n, dtype=torch.float32, device=bj.device)
             b[:bj.shape[0]] = bj
             return b
-        out.append((cache.get(('s2w', r, j), wj, make_w), cache.get(('s2b', r, j), wj, make_b), offs))
+        wsrc = [params[2 * L.rdb_conv(r, k)] for k in ks]
+        out.append((cache.get(('s2w', r, j), wsrc, make_w), cache.get(('s2b', r, j), params[2 * L.rdb_conv(r, j) + 1], make_b), offs))
     return out
 
 
@@ -368,6 +375,8 @@ class _BatchPacker:
         Bv = lambda i: params[2 * i + 1]
 
         def ver(p):
+            if isinstance(p, (list, tuple)):
+                return tuple((q.data_ptr(), q._version) for q in p)
             return (p.data_ptr(), p._version)
 
         def add(key, param, kind, rows_total, k_ch, parts, nvar_taps):
@@ -419,9 +428,8 @@ class _BatchPacker:
                 for k, co in zip(ks, couts):
                     parts.append((W(L.rdb_conv(r, k)), lo, hi - lo, co, 0, off))
                     off += co
-                wj = W(L.rdb_conv(r, j))
-                add(('fw', r, j), wj, TC_FPROP, off, hi - lo, parts, 9)
-                bias_copy(('fb', r, j), wj, Bv(L.rdb_conv(r, j)), off)
+                add(('fw', r, j), [W(L.rdb_conv(r, k)) for k in ks], TC_FPROP, off, hi - lo, parts, 9)
+                bias_copy(('fb', r, j), Bv(L.rdb_conv(r, j)), Bv(L.rdb_conv(r, j)), off)
                 dgrad(L.rdb_conv(r, j))
         arr = (PackJob * len(jobs))(*jobs)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -669,7 +677,7 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
     return out, ctx
 
 
-def rrdb_backward_bf16(ctx, params, dout, cache=None):
+def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
     """Backward of the mixed-precision mode: input gradients (dgrad) on the tcgen05 kernel (3x3 conv with flipped,
     transposed filters; gradient contributions of a dense block accumulate in place in one bf16 buffer), filter
     gradients on the tcgen05 wgrad kernel (MN-major operands straight from the NHWC tiles, fp32 TMEM accumulation).  Returns fp32 grads."""
@@ -690,7 +698,10 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None):
     for i in range(n_conv):
         b_off.append(o)
         o += params[2 * i + 1].numel()
-    flat = torch.empty(o, dtype=torch.float32, device=dout.device)
+    if flat is None:
+        flat = torch.empty(o, dtype=torch.float32, device=dout.device)
+    elif flat.numel() != o or flat.dtype != torch.float32:
+        raise ops._lib.DasrError('rrdb_backward_bf16: gradient arena has %d elements, the network has %d' % (flat.numel(), o))
     grads = []
     for i in range(n_conv):
         grads.append(flat[w_off[i]:w_off[i] + params[2 * i].numel()].view_as(params[2 * i]))
@@ -832,21 +843,40 @@ class _TrainGraphs:
         with torch.cuda.graph(self.bwd, pool=self.pool):
             _, self.grads, self.gflat = rrdb_backward_bf16(self.ctx, plist, self.dout, self.packer.cache)
         self.n_bwd = _lib.LAUNCHES - l0
+        self.pending = None
+
+    def mark_pending(self, out):
+        import weakref
+        self.pending = weakref.ref(out)
+
+    def busy(self):
+        """True while a forward's output is still alive and its backward has not run."""
+        return self.pending is not None and self.pending() is not None
 
 
 class RRDBNetFunctionBF16(torch.autograd.Function):
     """Mixed-precision training node (tcgen05 fprop + dgrad + wgrad); graphs = None runs eagerly."""
 
     @staticmethod
-    def forward(ctx, x, nb, upscale, cache, graphs, *params):
+    def forward(ctx, x, nb, upscale, cache, graphs, arena, *params):
+        """arena: optional flat fp32 tensor (numel = all parameters) that receives the gradients in the layout
+        [filters in conv order | biases in conv order]; the returned gradients are then views of it (data-parallel
+        bucket segment, dasr_b200.dp) instead of views of a fresh tensor."""
+        ctx.arena = arena
         if x.requires_grad:
             raise ops._lib.DasrError('bf16 training mode does not return the input-image gradient; use precision fp32')
+        if graphs is not None and graphs.busy():
+            # the graphs own ONE set of static activations: a second forward before the pending backward would overwrite
+            # what that backward reads, so this call runs eagerly on fresh buffers instead
+            graphs = None
         ctx.params, ctx.cache, ctx.graphs = params, cache, graphs
         if graphs is not None:
             graphs.x.copy_(x)
             graphs.fwd.replay()
             ops._lib.LAUNCHES += graphs.n_fwd
-            return graphs.out.clone()
+            out = graphs.out.clone()
+            graphs.mark_pending(out)
+            return out
         out, saved = rrdb_forward_bf16_train(x, [p.detach() for p in params], nb, upscale, cache)
         ctx.saved = saved
         return out
@@ -855,16 +885,21 @@ class RRDBNetFunctionBF16(torch.autograd.Function):
     def backward(ctx, dout):
         g = ctx.graphs
         if g is not None:
+            g.pending = None
             g.dout.copy_(dout)
             g.bwd.replay()
             ops._lib.LAUNCHES += g.n_bwd
-            fl = g.gflat.clone()                                  # one copy out of the graph's static buffer
+            if ctx.arena is not None:
+                fl = ctx.arena
+                fl.copy_(g.gflat)                                 # one copy out of the graph's static buffer, into the bucket
+            else:
+                fl = g.gflat.clone()                              # one copy out of the graph's static buffer
             base = g.gflat.data_ptr()
             grads = [fl[(t.data_ptr() - base) // 4:(t.data_ptr() - base) // 4 + t.numel()].view(t.shape) for t in g.grads]
         else:
-            _, grads, _ = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache)
+            _, grads, _ = rrdb_backward_bf16(ctx.saved, [p.detach() for p in ctx.params], dout, ctx.cache, flat=ctx.arena)
             ctx.saved = None
-        return (None, None, None, None, None) + tuple(gr.to(p.dtype) for gr, p in zip(grads, ctx.params))
+        return (None, None, None, None, None, None) + tuple(gr.to(p.dtype) for gr, p in zip(grads, ctx.params))
 
 
 class RRDBNetFunction(torch.autograd.Function):

@@ -88,7 +88,17 @@ def conv2d_f32(inp, w_packed, bias, out, k, stride, pad, **kw):
 _ws_cache = {}
 
 
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def _workspace(nbytes, device):
+    """Scratch memory for split reductions.  Eager calls share one grow-only tensor per device.  While a CUDA graph is
+    being captured the scratch comes from the graph's private pool instead (a fresh tensor per call: the caching
+    allocator re-uses freed capture-time blocks in capture order, which is the replay order), so a graph never holds a
+    pointer into the shared tensor that a later, larger eager call would replace."""
+    if _capturing():
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
     key = str(device)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -140,9 +150,12 @@ def bias_grad(dy, db, accumulate=False):
     dy = as_view(dy)
     npix = dy.t.numel() // dy.cs
     key = str(dy.t.device)
-    part = _bg_cache.get(key)
-    if part is None or part.numel() < 64 * dy.c:
-        part = _bg_cache[key] = torch.empty(64 * max(dy.c, 512), dtype=torch.float32, device=dy.t.device)
+    if _capturing():      # graph-private partials (see _workspace)
+        part = torch.empty(64 * max(dy.c, 512), dtype=torch.float32, device=dy.t.device)
+    else:
+        part = _bg_cache.get(key)
+        if part is None or part.numel() < 64 * dy.c:
+            part = _bg_cache[key] = torch.empty(64 * max(dy.c, 512), dtype=torch.float32, device=dy.t.device)
     check(_lib.load().dasr_bias_grad(dy.ptr, _p(db), npix, dy.c, dy.cs, dy.coff, int(dy.t.dtype == torch.bfloat16),
                                      int(accumulate), _p(part), _stream()), 'bias_grad', 2)
 

@@ -9,9 +9,10 @@ behaviour-preserving:
   * while G's loss is back-propagated through D, D's filter gradients (which the reference computes and
     then discards with optimizer_D_target.zero_grad(), :282) are not computed;
   * log values are kept as device scalars and only synchronised in get_current_log();
-  * under torch.distributed (one process per GPU) the G and D gradients are all-reduced once per step in
-    a single flat bucket before both optimiser steps (dasr_b200.dp) — equivalent to the reference order
-    because the D step only consumes tensors detached before the G update.
+  * under torch.distributed (one process per GPU) the G and D gradients live in one flat bucket and are averaged over
+    NCCL before both optimiser steps (dasr_b200.dp; G's segment is exchanged while the discriminator step runs) —
+    equivalent to the reference order because the D step only consumes tensors detached before the G update
+    (SURVEY.md §8e); rank 0's initial weights are broadcast, checkpoints are written by rank 0 only.
 """
 import contextlib
 import logging
@@ -131,7 +132,8 @@ class DASR_Model(BaseModel):
         self._make_schedulers(cfg)
         self.log_dict, self._log_t = OrderedDict(), OrderedDict()
         # data parallel: one flat gradient bucket over [G | D_target | D_source]
-        self.grad_sync = dp.GradBucket([p for n in trained for p in n.parameters() if p.requires_grad])
+        # (construction broadcasts rank 0's weights; G's mixed-precision backward writes straight into its bucket segment)
+        self.grad_sync = dp.GradBucket(trained)
 
     # ------------------------------------------------------------------------------------------ data
     def feed_data(self, data, istrain):
@@ -203,6 +205,8 @@ class DASR_Model(BaseModel):
             l_g_total.backward()
             if not self.grad_sync.active:
                 self.optimizer_G.step()
+            else:
+                self.grad_sync.reduce_segment(0)      # G's all-reduce starts now and overlaps the discriminator step
 
         if do_D:
             if self.l_gan_H_target_w > 0:
@@ -230,8 +234,9 @@ class DASR_Model(BaseModel):
                     self.optimizer_D_source.step()
 
         if self.grad_sync.active:
-            # ONE all-reduce (mean) of [G | D] gradients per step over NCCL, then the deferred optimiser steps
-            self.grad_sync.all_reduce_mean()
+            # gradient exchange over NCCL (G's segment already in flight, D's now; DASR_B200_DP_OVERLAP=0: one all-reduce of
+            # the whole [G | D] bucket here), then the deferred optimiser steps
+            self.grad_sync.finish()
             if do_G:
                 self.optimizer_G.step()
             if do_D and self.l_gan_H_target_w > 0:

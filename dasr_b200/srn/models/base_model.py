@@ -96,7 +96,15 @@ class BaseModel():
         net = unwrap(network)
         return str(net), sum(p.numel() for p in net.parameters())
 
+    @staticmethod
+    def _is_writer():
+        """Under torch.distributed every replica holds the same weights: only rank 0 writes checkpoint files."""
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
     def save_network(self, network, network_label, iter_step):
+        if not self._is_writer():
+            return
         target = os.path.join(self.opt['path']['models'], '{}_{}.pth'.format(iter_step, network_label))
         torch.save({k: t.cpu() for k, t in unwrap(network).state_dict().items()}, target)
 
@@ -104,6 +112,8 @@ class BaseModel():
         unwrap(network).load_state_dict(torch.load(load_path, map_location='cpu'), strict=strict)
 
     def save_training_state(self, epoch, iter_step):
+        if not self._is_writer():
+            return
         snapshot = {'epoch': epoch, 'iter': iter_step,
                     'schedulers': [s.state_dict() for s in self.schedulers],
                     'optimizers': [o.state_dict() for o in self.optimizers]}

@@ -79,7 +79,17 @@ class RRDBNet(nn.Module):
         self.train_precision = None    # training:  None -> DASR_B200_TRAIN_PRECISION or 'fp32' ('fp32' | 'bf16')
         self._pack_cache = engine._PackCache()
         self._graphs = {}
+        self._graph_seen = None
         self._train_graphs = {}
+        self._grad_arena = None
+
+    def set_grad_arena(self, flat):
+        """Data parallel (dasr_b200.dp): the mixed-precision backward writes its flat gradient tensor
+        [filters in conv order | biases in conv order] into `flat` and returns views of it, so every .grad lives in the
+        all-reduce bucket without a per-tensor copy.  None switches back to a fresh tensor per step."""
+        if flat is not None and flat.numel() != sum(p.numel() for p in self.parameters()):
+            raise ValueError('gradient arena size does not match the parameter count')
+        self._grad_arena = flat
 
     def forward(self, x):
         params = list(self.parameters())
@@ -95,7 +105,8 @@ class RRDBNet(nn.Module):
                     if graphs is None:
                         self._train_graphs.clear()
                         graphs = self._train_graphs[key] = engine._TrainGraphs(x.contiguous().float(), params, self.nb, self.upscale)
-                return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, graphs, *params)
+                arena = self._grad_arena if all(p.requires_grad for p in params) else None
+                return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, graphs, arena, *params)
             return engine.RRDBNetFunction.apply(x, self.nb, self.upscale, *params)
         prec = self.precision or _precision('bf16')
         if prec in ('bf16', 'bf16_layer'):
@@ -103,10 +114,15 @@ class RRDBNet(nn.Module):
             fn = lambda t: engine.rrdb_forward_bf16(t, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
             if os.environ.get('DASR_B200_GRAPH', '1') == '0' or not x.is_cuda or engine.PROFILE is not None:
                 return fn(x)
-            key = (tuple(x.shape), x.dtype, x.device.index, prec, sum(p._version for p in params),
+            key = (tuple(x.shape), x.dtype, x.device.index, prec, tuple(p._version for p in params),
                    params[0].data_ptr(), params[len(params) // 2].data_ptr(), params[-1].data_ptr())
             g = self._graphs.get(key)
             if g is None:
+                # capture only the SECOND time a (shape, parameter version) is seen: validation over differently sized
+                # images, or one test() per training interval, would otherwise pay warm-up + capture + replay per image
+                if self._graph_seen != key:
+                    self._graph_seen = key
+                    return fn(x)
                 if len(self._graphs) >= 2:        # each graph pins its activation pool: keep at most two shapes
                     self._graphs.clear()
                 g = self._graphs[key] = _GraphedForward(fn, x.contiguous().float())
@@ -190,7 +206,15 @@ class VGGFeatureExtractor(nn.Module):
                     sd = torch.load(c, map_location='cpu')
                     break
         if sd is None:
-            warnings.warn('VGGFeatureExtractor: no pretrained VGG19 weights found offline; using random init')
+            # the reference builds torchvision.models.vgg19(pretrained=True) (architecture.py:1068-1070), which either has
+            # ImageNet weights or fails; a perceptual loss on random features must never happen silently
+            if os.environ.get('DASR_B200_ALLOW_RANDOM_VGG', '0') != '1':
+                raise RuntimeError(
+                    'VGGFeatureExtractor: no pretrained VGG19 weights found (looked at the `weights` argument / '
+                    "opt['path']['pretrain_model_F'] and %s).  Supply torchvision's vgg19-dcbb9e9d.pth, or set "
+                    'DASR_B200_ALLOW_RANDOM_VGG=1 to run with a random-init extractor (tests / benchmarks only).'
+                    % os.path.join(torch.hub.get_dir(), 'checkpoints', 'vgg19-dcbb9e9d.pth'))
+            warnings.warn('VGGFeatureExtractor: DASR_B200_ALLOW_RANDOM_VGG=1 — random-init VGG19 features')
             return
         own = self.state_dict()
         self.load_state_dict({k: v for k, v in sd.items() if k in own and k.startswith('features')}, strict=False)

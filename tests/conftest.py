@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+# the parity tests load synthetic VGG weights AFTER construction; pretrained torchvision weights are not available offline
+os.environ.setdefault('DASR_B200_ALLOW_RANDOM_VGG', '1')
 
 
 def pytest_configure(config):

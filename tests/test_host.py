@@ -107,25 +107,75 @@ sys.path.insert(0, %r)
 from dasr_b200.dp import GradBucket
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% sys.argv[2], rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
-torch.manual_seed(0)
-net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
-bucket = GradBucket(list(net.parameters()))
-assert bucket.active and bucket.numel() == sum(p.numel() for p in net.parameters())
-x = torch.arange(10, dtype=torch.float32).reshape(2, 5) * (rank + 1)
-net(x).sum().backward()
-local = [p.grad.clone() for p in net.parameters()]
-bucket.all_reduce_mean()
-# reference: mean of the two ranks' gradients
-outs = []
-for r in range(2):
-    net.zero_grad()
-    net(torch.arange(10, dtype=torch.float32).reshape(2, 5) * (r + 1)).sum().backward()
-    outs.append([p.grad.clone() for p in net.parameters()])
-for i, p in enumerate(net.parameters()):
-    pass
-ok = all(torch.allclose(bucket.views[i], (outs[0][i] + outs[1][i]) / 2, atol=1e-6) for i in range(len(local)))
-assert ok, 'bucket mismatch'
-assert all(p.grad.data_ptr() != 0 for p in net.parameters())
+os.environ['DASR_B200_DP_OVERLAP'] = sys.argv[3]
+torch.manual_seed(100 + rank)                       # every process draws its OWN initial weights (train.py, manual_seed null)
+
+
+class ArenaNet(torch.nn.Module):
+    # stands in for RRDBNet in mixed precision: its backward writes ONE flat gradient tensor in its own layout
+    # ([weights | biases], not parameter order) into the bucket segment it was handed
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(5, 7)
+        self.b = torch.nn.Linear(7, 3)
+        self.arena = None
+
+    def set_grad_arena(self, flat):
+        self.arena = flat
+
+    def forward(self, x):
+        return self.b(self.a(x))
+
+    def flat_backward(self, loss):
+        ps = list(self.parameters())
+        gs = torch.autograd.grad(loss, ps)
+        order = [0, 2, 1, 3]                         # weights first, then biases
+        o = 0
+        for i in order:
+            v = self.arena[o:o + ps[i].numel()].view_as(ps[i])
+            v.copy_(gs[i])
+            ps[i].grad = v
+            o += ps[i].numel()
+
+
+G, D = ArenaNet(), torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Linear(6, 1))
+bucket = GradBucket([G, D])
+assert bucket.active and bucket.numel() == sum(p.numel() for n in (G, D) for p in n.parameters())
+# rank 0's weights were broadcast at construction
+for p in list(G.parameters()) + list(D.parameters()):
+    t = [torch.zeros_like(p), torch.zeros_like(p)]
+    dist.all_gather(t, p.data)
+    assert torch.equal(t[0], t[1]), 'replicas differ after construction'
+assert G.arena is not None and G.arena.data_ptr() == bucket.flat.data_ptr()
+
+
+def data(r):
+    return torch.arange(10, dtype=torch.float32).reshape(2, 5) * (r + 1), torch.arange(8, dtype=torch.float32).reshape(2, 4) - r
+
+
+def local_grads(r):
+    xg, xd = data(r)
+    gg = torch.autograd.grad(G(xg).sum(), list(G.parameters()))
+    gd = torch.autograd.grad(D(xd).square().sum(), list(D.parameters()))
+    return [g.clone() for g in gg], [g.clone() for g in gd]
+
+
+ref = [local_grads(r) for r in range(2)]
+for step in range(2):                               # two steps: views / arena are persistent, .grad is reset in between
+    for p in list(G.parameters()) + list(D.parameters()):
+        p.grad = None
+    xg, xd = data(rank)
+    G.flat_backward(G(xg).sum())
+    bucket.reduce_segment(0)                        # starts G's exchange (no-op with overlap off)
+    D(xd).square().sum().backward()
+    bucket.finish()
+    assert bucket.last_copies == len(list(D.parameters())), bucket.last_copies     # only D's tensors are gathered by copy
+    lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + 4 * bucket.numel()
+    for net, k in ((G, 0), (D, 1)):
+        for i, p in enumerate(net.parameters()):
+            assert lo <= p.grad.data_ptr() < hi
+            want = (ref[0][k][i] + ref[1][k][i]) / 2
+            assert torch.allclose(p.grad, want, atol=1e-5), (step, k, i)
 print('rank', rank, 'ok')
 '''
 
@@ -133,12 +183,13 @@ print('rank', rank, 'ok')
 def test_grad_bucket_allreduce_gloo_world2(tmp_path):
     script = tmp_path / 'w.py'
     script.write_text(DP_WORKER % ROOT)
-    port = str(29500 + os.getpid() % 2000)
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-             for r in range(2)]
-    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
-    assert all(p.returncode == 0 for p in procs), outs
-    assert all('ok' in o for o in outs)
+    for k, overlap in enumerate(('1', '0')):          # overlapped per-network exchange / one all-reduce of the whole bucket
+        port = str(29500 + (os.getpid() + k) % 2000)
+        procs = [subprocess.Popen([sys.executable, str(script), str(r), port, overlap], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+                 for r in range(2)]
+        outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        assert all('ok' in o for o in outs)
 
 
 def test_dsn_modules_match_reference_state_dict_layout():
