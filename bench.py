@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# synthetic weights everywhere (no checkpoints offline): the perceptual networks run with deterministic random features
+os.environ.setdefault('DASR_B200_ALLOW_RANDOM_VGG', '1')
 
 NB, NF, BATCH, LR = 23, 64, 16, 256
 FLOP_PER_LR_PIXEL = 35853696          # whole G forward, SURVEY.md §8(d): conv MACs x2, no recompute credit

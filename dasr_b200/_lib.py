@@ -58,18 +58,6 @@ class PackJob(C.Structure):
                 ('dst_row_off', C.c_int), ('reserved', C.c_int)]
 
 
-class RdbParams(C.Structure):
-    """DasrRdbParams (include/dasr_b200.h)"""
-    _fields_ = [('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('nf', C.c_int), ('gc', C.c_int), ('cs', C.c_int),
-                ('next_cs', C.c_int), ('next_coff', C.c_int), ('res2_cs', C.c_int), ('res2_coff', C.c_int),
-                ('chunk_imgs', C.c_int), ('alpha', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('slope', C.c_float)]
-
-
-class PipeArgs(C.Structure):
-    _fields_ = [('grid_x', C.c_int), ('dep0', C.c_void_p), ('dep0_g', C.c_int), ('dep1', C.c_void_p), ('dep1_g', C.c_int),
-                ('progress', C.c_void_p)]
-
-
 # every symbol include/dasr_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _f, _l, _sz = C.c_void_p, C.c_int, C.c_float, C.c_long, C.c_size_t
 SYMBOLS = {
@@ -85,7 +73,8 @@ SYMBOLS = {
     'dasr_upsample2x_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasr_pack_filter_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
-    'dasr_conv_tc_pipe': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), C.POINTER(PipeArgs), _vp]),
+    'dasr_conv_tc2_supported': (_i, [C.POINTER(ConvTcParams)]),
+    'dasr_conv_tc2': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
     'dasr_conv_tc_setup': (_i, [C.POINTER(ConvTcParams), _i]),
     'dasr_pack_filter_tc_bytes': (_sz, [_i, _i, _i]),
     'dasr_pack_filter_tc': (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -112,7 +101,6 @@ SYMBOLS = {
     'dasr_pack_filter_tc_batch': (_i, [_vp, _i, _i, _vp]),
     'dasr_rdb_wgrad_tc_workspace': (_sz, [_i, _i, _i]),
     'dasr_rdb_wgrad_tc': (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _vp, _sz, _vp]),
-    'dasr_rdb_tc': (_i, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(RdbParams), _vp, _vp, _vp]),
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
     'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),

@@ -30,6 +30,8 @@ inline int check_launch(const char* what) {
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+// programmatic dependent launch of the tensor-core conv kernels (DASR_B200_PDL=0 switches it off)
+bool pdl_enabled();
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == DASR_ACT_LRELU) return v > 0.f ? v : v * slope;

@@ -6,6 +6,7 @@
 // Reference call sites replaced: nn.Conv2d in block.py:142-143 (conv_block), architecture.py:998-1018
 // (NLayerDiscriminator), architecture.py:1076 (VGG19 features); autograd's conv backward for them.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dasr {
@@ -26,6 +27,15 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DASR_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 // ---- gather: output coordinate + tap -> stored input coordinate ---------------------------------

@@ -57,16 +57,7 @@ struct TcKernelArgs {
   int acc_stride;
   int epi_bytes;     // bytes of ONE staged epilogue tile: 128 pixels x nt channels bf16
   int has_pre, has_res1, has_res2;
-  int alt_epi;       // 1: the two epilogue warpgroups take alternate TILES (all columns) instead of alternate column groups
   int nbuf;          // staged-epilogue tile buffers (2..4): pre / residual tiles are requested nbuf tiles ahead
-  // cross-launch spatial pipelining (dense-block stages run CONCURRENTLY on disjoint SM subsets):
-  //   dep{0,1}[k] = tiles finished by CTA k of a producer launch with dep_g CTAs (same tile order as this launch);
-  //   a tile (and its pre/residual tiles) may be loaded once every producer tile up to the end of the NEXT tile row
-  //   is finished; progress[blockIdx.x] = tiles of this launch whose stores are complete.
-  const int* dep0;
-  const int* dep1;
-  int dep0_g, dep1_g;
-  int* progress;
 };
 
 
@@ -119,11 +110,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     mbar_init(w_bar, 1);
     for (int b = 0; b < 4; b++) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], a.alt_epi ? 4 : EPI_WARPS);  // one arrive per epilogue warp that reads this accumulator
+      mbar_init(&tempty_bar[b], EPI_WARPS);  // one arrive per epilogue warp that reads this accumulator
     }
     for (int b = 0; b < 4; b++) {
       mbar_init(&pre_bar[b], 1);
-      mbar_init(&sfull_bar[b], a.alt_epi ? 4 : EPI_WARPS);
+      mbar_init(&sfull_bar[b], EPI_WARPS);
       mbar_init(&sfree_bar[b], 1);
     }
     fence_barrier_init();
@@ -134,6 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();               // the next launch may start its prologue on SMs this grid has left
 
   if (warp == 0) {
     // =========================== TMA producer (A halo tiles, resident filters) ===========================
@@ -149,7 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
     int stage = 0;
     uint32_t phase = 0;
-    long dep_ok = -1;                    // largest raster index already known to be finished by the producers
+    if (lane == 0) pdl_wait();           // activations come from the previous launch (filters / bias above do not)
+    __syncwarp();
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
       int tx = (int)(te % a.tiles_x);
@@ -157,15 +150,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       int ty = (int)(r % a.tiles_y);
       int n = (int)(r / a.tiles_y);
       int x0 = tx * TILE_W, y0 = ty * TILE_H;
-      if (a.dep0 != nullptr) {
-        long tmax = tile - tx + 2L * a.tiles_x - 1;          // halo: through the end of the next tile row
-        if (tmax > a.ntiles - 1) tmax = a.ntiles - 1;
-        if (tmax > dep_ok) {
-          wait_producer(a.dep0, a.dep0_g, tmax, lane);
-          wait_producer(a.dep1, a.dep1_g, tmax, lane);
-          dep_ok = tmax;
-        }
-      }
       if (lane == 0) {
         for (int c = 0; c < a.nchunks; c++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -246,12 +230,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else if (warp == TCK_WARPS - MMA_WARPS) {
     // =========================== epilogue TMA warp ===========================
-    // Feeds the staged epilogue: pre-activation / residual tiles in (two tiles ahead), finished tiles out;
-    // publishes per-CTA progress for consumer launches that run concurrently on other SMs.
+    // Feeds the staged epilogue: pre-activation / residual tiles in (nbuf tiles ahead), finished tiles out.
     if constexpr (EPI_MODE == 0) {
       const int co_base = p.out_coff + ntile * nt;
       const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * a.epi_bytes);
-      long dep_ok = -1;
+      pdl_wait();                      // pre / residual tiles and the output slots belong to earlier launches until now
       auto tile_xyz = [&](long tile, int& x0, int& y0, int& n) {
         const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
         int tx = (int)(te % a.tiles_x);
@@ -261,14 +244,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         x0 = tx * TILE_W;
         y0 = ty * TILE_H;
       };
-      auto issue_loads = [&](long tile, int b) {      // whole warp: dependency wait, then lane 0 issues
+      auto issue_loads = [&](long tile, int b) {      // lane 0 issues
         int x0, y0, n;
         tile_xyz(tile, x0, y0, n);
-        if (a.dep0 != nullptr && tile > dep_ok) {     // pre/residual tiles have no halo: the tile itself suffices
-          wait_producer(a.dep0, a.dep0_g, tile, lane);
-          wait_producer(a.dep1, a.dep1_g, tile, lane);
-          dep_ok = tile;
-        }
         if (lane == 0) {
           mbar_expect_tx(&pre_bar[b], load_bytes);
           const int cb = ntile * nt;
@@ -302,24 +280,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           }
           bulk_commit();
           bulk_wait_read0();                       // buffer b has been read by the stores
-          if (a.progress != nullptr && it > 0) {
-            // publish with one store group still in flight: everything up to the PREVIOUS tile is complete
-            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-            __threadfence();
-            st_release_gpu(a.progress + blockIdx.x, (int)it);
-          }
           if (!has_loads) mbar_arrive(&sfree_bar[b]);
         }
         __syncwarp();
         if (has_loads && tile + (long)nbuf * G < a.ntiles) issue_loads(tile + (long)nbuf * G, b);
       }
-      if (lane == 0) {
-        bulk_wait0();                              // all stores complete before the CTA (and its smem) goes away
-        if (a.progress != nullptr && it > 0) {
-          __threadfence();
-          st_release_gpu(a.progress + blockIdx.x, (int)it);
-        }
-      }
+      if (lane == 0) bulk_wait0();                 // all stores complete before the CTA (and its smem) goes away
     }
   } else {
     // =========================== epilogue warps (2..9) ===========================
@@ -327,6 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // The epilogue is instruction-latency bound (one warp per scheduler), so: branch-free activation,
     // the next TMEM load in flight while the current group is processed, finished tile staged in swizzled
     // shared memory and written by the TMA warp.
+    if constexpr (EPI_MODE != 0) pdl_wait();   // direct epilogues read residual / mask tensors and write the output themselves
     const int ew = warp - 2;                // 0..EPI_WARPS-1
     const int wg = ew >> 2;                 // warpgroup 0..EPI_WGS-1
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -342,10 +309,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const uint32_t sS_u = smem_u32(sS), sR1_u = smem_u32(sR1), sR2_u = smem_u32(sR2), sBias_u = smem_u32(sBias);
     const bool has_bias = a.bias != nullptr;
     uint32_t it = 0;
-    const bool alt = a.alt_epi != 0;
-    const int g0 = alt ? 0 : wg, gs = alt ? 1 : EPI_WGS;     // first column group and stride of this warp's groups
+    const int g0 = wg, gs = EPI_WGS;        // first column group and stride of this warp's groups
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-      if (alt && (int)(it % EPI_WGS) != wg) continue;   // alternate-tile mode: another warpgroup owns this tile
       const int acc = (int)(it % nacc);
       const uint32_t acc_phase = (it / nacc) & 1;
       const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
@@ -789,18 +754,8 @@ static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base
   return DASR_OK;
 }
 
-int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const void* pre, const void* res1,
-                      const void* res2, const void* mask_src, void* out, const DasrConvTcParams* p,
-                      const DasrPipeArgs* pipe, void* stream);
-
 int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
                  const void* mask_src, void* out, const DasrConvTcParams* p, void* stream) {
-  return dasr_conv_tc_pipe(in, w, bias, pre, res1, res2, mask_src, out, p, nullptr, stream);
-}
-
-int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const void* pre, const void* res1,
-                      const void* res2, const void* mask_src, void* out, const DasrConvTcParams* p,
-                      const DasrPipeArgs* pipe, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc: cin must be a multiple of 32 (got %d)", p->cin);
@@ -862,21 +817,10 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
   a.has_res1 = (p->epi_mode == 0 && res1) ? 1 : 0;
   a.has_res2 = (p->epi_mode == 0 && res2) ? 1 : 0;
   a.epi_bytes = (p->epi_mode == 0) ? p->nt * 128 * 2 : 0;
-  a.dep0 = a.dep1 = nullptr;
-  a.dep0_g = a.dep1_g = 0;
-  a.progress = nullptr;
-  if (pipe) {
-    DASR_REQUIRE(p->epi_mode == 0 && p->nvar == 1 && p->nt == p->cout && !p->tile_rev, "conv_tc: pipelined launches need the staged epilogue, one Cout tile, forward tile order");
-    DASR_REQUIRE(pipe->grid_x >= 1 && pipe->dep0_g >= 0 && pipe->dep1_g >= 0 && (pipe->dep0 || !pipe->dep1), "conv_tc: pipe args");
-    a.dep0 = pipe->dep0; a.dep0_g = pipe->dep0_g;
-    a.dep1 = pipe->dep1; a.dep1_g = pipe->dep1_g;
-    a.progress = pipe->progress;
-  }
   const int bar_bytes = (2 * MAX_STAGES + 22) * 8 + 256 * 4 + 16;
   // staged-epilogue buffers: as many (<= 4) as still leave 4 A stages; loads of pre / residual tiles are issued nbuf
   // tiles ahead, which hides their latency (with 2 the read-modify-write launches are bound by that round trip)
   int nbuf = (p->epi_mode == 0) ? 4 : 2;
-  if (pipe) nbuf = 2;
   int epi_total = 0, avail = 0;
   for (;; nbuf--) {
     epi_total = nbuf * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
@@ -884,14 +828,6 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
     if (nbuf == 2 || avail >= 4 * a.a_stage_bytes) break;
   }
   a.nbuf = nbuf;
-  {
-    static int alt_env = -1;
-    if (alt_env < 0) {
-      const char* e = getenv("DASR_TC_ALT_EPI");
-      alt_env = e ? atoi(e) : 0;
-    }
-    a.alt_epi = (p->epi_mode == 0 && alt_env) ? 1 : 0;
-  }
   int stages = avail / a.a_stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
@@ -969,11 +905,26 @@ int dasr_conv_tc_pipe(const void* in, const void* w, const float* bias, const vo
     attr_set[ki] = true;
   }
   int gy = p->nvar * a.n_ntiles;
-  int gx = (pipe && pipe->grid_x > 0) ? pipe->grid_x : num_sms() / gy;
+  int gx = num_sms() / gy;
   if (gx < 1) gx = 1;
   if ((long)gx > a.ntiles) gx = (int)a.ntiles;
-  dim3 grid(gx, gy);
-  kernels[ki]<<<grid, TCK_THREADS, smem, (cudaStream_t)stream>>>(tm_in, tm_w, em, a);
+  // programmatic dependent launch: this kernel's prologue (barrier init, TMEM allocation, resident filter load) may run
+  // while the previous kernel of the stream drains; every global access that depends on it sits behind griddepcontrol.wait
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, 1);
+  cfg.blockDim = dim3(TCK_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kernels[ki], tm_in, tm_w, em, a);
+  if (le != cudaSuccess) {
+    set_error("conv_tc: launch failed: %s", cudaGetErrorString(le));
+    return DASR_E_LAUNCH;
+  }
   return check_launch("conv_tc");
 }
 

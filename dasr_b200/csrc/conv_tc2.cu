@@ -1,0 +1,469 @@
+// CTA-pair (tcgen05 cta_group::2) 3x3 convolution for the first launch of a dense block — sm_100a.
+//
+// Replaces (reference, codes/SRN): the products of ResidualDenseBlock_5C's input x with conv1..conv5
+// (models/modules/block.py:262-286) — launch 1 of the N-fused dense-block schedule (engine.SCHED2): K = 64 input
+// channels against the 192 stacked output channels [x1 | p2 p3 p4 | p5].
+//
+// Why a pair: a tcgen05.mma M=128 K=16 costs ~84 cycles back to back for every N <= 128 (the 4 KB A read from shared
+// memory is the floor) and 101 cycles at N = 192, but a 192-wide resident filter set (9 taps x 64 x 192 bf16 = 221 KB)
+// does not fit one SM, so the single-CTA kernel runs this launch as two Cout tiles of 96 (two CTAs each reading every A
+// tile: 2 x 84 cycles per K step and pixel tile).  With cta_group::2 the two SMs of a TPC each keep HALF of the filters
+// (96 rows, 110 KB), each loads the A halo tile of its own pixel tile, and one M=256 N=192 instruction issued by the
+// leader CTA feeds both tensor cores: ~84-101 cycles per K step for TWO pixel tiles.
+//
+// Layout per CTA: [filters: 9 taps x nchunks x (N/2 rows x 64 B)] [A stages: halo tile 18x10 px x 64 B, SWIZZLE_64B]
+// [output staging ring: 64-channel blocks of 128 px x 128 B, SWIZZLE_128B] [barriers, bias].
+// Warp roles (TC2_THREADS = 352): warp 0 TMA producer (filters once, A halo tiles) / warp 1 TMEM allocator + (leader
+// only) MMA issuer / warps 2..9 epilogue (TMEM -> registers -> bias, LeakyReLU on the first act_cols columns -> bf16
+// block in shared memory) / warp 10 TMA stores.
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace dasr {
+
+constexpr int TC2_EPI_WARPS = 8;
+constexpr int TC2_WARPS = 2 + TC2_EPI_WARPS + 1;
+constexpr int TC2_THREADS = 32 * TC2_WARPS;
+constexpr int TC2_MAX_STAGES = 6;
+constexpr int TC2_MAX_BLOCKS = 6;      // staging ring entries (64-channel output blocks)
+
+struct Tc2Args {
+  DasrConvTcParams p;
+  const float* bias;
+  int nchunks;        // cin / 32
+  int n_half;         // cout / 2: filter rows resident in one CTA
+  int tiles_x, tiles_y;
+  long ntiles;
+  int stages, a_stage_bytes, w_bytes;
+  int nblk;           // staging ring entries
+  int nb64;           // 64-channel blocks per tile (cout / 64)
+  int acc_stride;     // TMEM columns between the two accumulators
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_out, const Tc2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + a.w_bytes;
+  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;                  // [nblk] 64-channel output blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)a.nblk * EPI_BLK64_BYTES);
+  uint64_t* full_bar = bars;                              // [stages] LEADER: both CTAs' A chunks landed
+  uint64_t* empty_bar = bars + TC2_MAX_STAGES;            // [stages] each CTA: A chunk consumed (multicast commit)
+  uint64_t* w_bar = bars + 2 * TC2_MAX_STAGES;            // [1]      LEADER: both filter halves landed
+  uint64_t* tfull_bar = w_bar + 1;                        // [2]      each CTA: accumulator complete (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;                   // [2]      LEADER: accumulator drained by BOTH CTAs' epilogues
+  uint64_t* sfull_bar = tempty_bar + 2;                   // [nblk]   block written by the epilogue warps
+  uint64_t* sfree_bar = sfull_bar + TC2_MAX_BLOCKS;       // [nblk]   block read by its TMA store
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + TC2_MAX_BLOCKS);
+  float* sBias = reinterpret_cast<float*>(tmem_ptr + 4);  // [cout]
+
+  const DasrConvTcParams& p = a.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int cout = p.cout;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < a.stages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 2 * TC2_EPI_WARPS);
+    }
+    for (int b = 0; b < a.nblk; b++) {
+      mbar_init(&sfull_bar[b], TC2_EPI_WARPS);
+      mbar_init(&sfree_bar[b], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < cout; i += TC2_THREADS) sBias[i] = a.bias ? a.bias[i] : 0.f;
+  cluster_sync();                       // barriers of both CTAs initialised before any cross-CTA signal
+  if (warp == 1) tmem_alloc2(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();              // the next launch may start its prologue on SMs this grid has left
+
+  auto tile_of = [&](long it, int& x0, int& y0, int& n) -> bool {     // tile of THIS CTA in pair-iteration `it`
+    const long t = 2 * (pair + it * npairs) + rank;
+    int tx = (int)(t % a.tiles_x);
+    long r = t / a.tiles_x;
+    int ty = (int)(r % a.tiles_y);
+    n = (int)(r / a.tiles_y);           // n >= N for the odd tail tile: TMA zero-fills, nothing is stored
+    x0 = tx * TILE_W;
+    y0 = ty * TILE_H;
+    return t < a.ntiles;
+  };
+  const long niter = (a.ntiles / 2 + (a.ntiles & 1) - pair + npairs - 1) / npairs;   // pair-iterations of this pair
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      if (rank == 0) mbar_expect_tx(w_bar, 2u * (uint32_t)a.w_bytes);
+      for (int tap = 0; tap < 9; tap++)
+        for (int c = 0; c < a.nchunks; c++) {
+          const int slot = tap * a.nchunks + c;
+          const int row = slot * cout + (int)rank * a.n_half;
+          tma2_load_2d(sW + (size_t)slot * a.n_half * ROW_B, &tmap_w, w_bar, 0, row);
+        }
+      pdl_wait();                       // activations are written by the previous launch
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long it = 0; it < niter; it++) {
+        int x0, y0, n;
+        tile_of(it, x0, y0, n);
+        for (int c = 0; c < a.nchunks; c++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * A_HALO_BYTES);
+          tma2_load_4d(sA + (size_t)stage * a.a_stage_bytes, &tmap_in, &full_bar[stage],
+                       p.nchunk_list ? p.chunk_off[c] : p.in_coff + c * CHUNK, x0 - 1, y0 - 1, n);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, cout);
+      const uint32_t a_sbo = (uint32_t)(HALO_W * ROW_B);
+      const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
+      const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
+      const uint32_t a_lo0 = smem_u32(sA) >> 4;
+      const uint32_t a_stage_lo = (uint32_t)a.a_stage_bytes >> 4;
+      const uint32_t b_lo0 = smem_u32(sW) >> 4;
+      const uint32_t b_slot_lo = (uint32_t)(a.n_half * ROW_B) >> 4;
+      uint32_t tap_lo[9];
+#pragma unroll
+      for (int t = 0; t < 9; t++) tap_lo[t] = (uint32_t)(((t / 3) * HALO_W + (t % 3)) * ROW_B) >> 4;
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long it = 0; it < niter; it++) {
+        const int acc = (int)(it & 1);
+        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
+        for (int c = 0; c < a.nchunks; c++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage_lo;
+            uint32_t b_lo = b_lo0 + (uint32_t)c * b_slot_lo;
+            const uint32_t b_tap_step = (uint32_t)a.nchunks * b_slot_lo;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+              const uint32_t al = a_lo + tap_lo[tap];
+              umma2_bf16(d_tmem, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc, (uint32_t)((c | tap) != 0));
+              umma2_bf16(d_tmem, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
+              b_lo += b_tap_step;
+            }
+            umma2_commit_mc(&empty_bar[stage]);                       // both CTAs' A slots reusable
+            if (c == a.nchunks - 1) umma2_commit_mc(&tfull_bar[acc]);  // both CTAs' accumulators complete
+          }
+          __syncwarp();
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC2_WARPS - 1) {
+    // =========================== TMA store warp ===========================
+    if (lane == 0) {
+      pdl_wait();                       // the slots written here may still be read by the previous launch
+      uint32_t k = 0;                   // running block index
+      for (long it = 0; it < niter; it++) {
+        int x0, y0, n;
+        const bool live = tile_of(it, x0, y0, n);
+        for (int i = 0; i < a.nb64; i++, k++) {
+          const int b = (int)(k % (uint32_t)a.nblk);
+          mbar_wait(&sfull_bar[b], (k / (uint32_t)a.nblk) & 1);
+          if (live) {
+            tma_store_4d(&tmap_out, sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + i * 64, x0, y0, n);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          mbar_arrive(&sfree_bar[b]);
+        }
+      }
+      bulk_wait0();
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue warps (2..9) ===========================
+    // Two warpgroups share every 64-channel block: warpgroup w takes the 16-column groups g with g % 2 == w.
+    const int ew = warp - 2;
+    const int wg = ew >> 2;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int sw128 = m & 7;
+    const int act = p.act;
+    const float slope = p.slope, alpha = p.alpha;
+    const bool scale = alpha != 1.f;
+    const uint32_t sS_u = smem_u32(sS), sBias_u = smem_u32(sBias);
+    const bool has_bias = a.bias != nullptr;
+    uint32_t k = 0;
+    for (long it = 0; it < niter; it++) {
+      const int acc = (int)(it & 1);
+      mbar_wait(&tfull_bar[acc], (uint32_t)(it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.acc_stride);
+      for (int i = 0; i < a.nb64; i++, k++) {
+        const int b = (int)(k % (uint32_t)a.nblk);
+        if (k >= (uint32_t)a.nblk) mbar_wait(&sfree_bar[b], ((k / (uint32_t)a.nblk) & 1) ^ 1);
+        const uint32_t bS = sS_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
+        uint32_t ra[16], rb[16];
+        const int c0 = i * 64 + wg * 16, c1 = c0 + 32;        // this warp's two 16-column groups of the block
+        tmem_ld16(t_addr + c0, ra);
+        tmem_ld16(t_addr + c1, rb);
+        tmem_ld_wait();
+        if (i == a.nb64 - 1) {          // last TMEM read of this tile: hand the accumulator back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t* rr = h ? rb : ra;
+          const int cg = h ? c1 : c0;
+          const bool do_act = (act != DASR_ACT_NONE) && (cg + 16 <= p.act_cols);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rr[j]);
+          if (has_bias) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+              const float4 b4 = lds128f(sBias_u + (cg + 4 * j4) * 4);
+              v[4 * j4 + 0] += b4.x;
+              v[4 * j4 + 1] += b4.y;
+              v[4 * j4 + 2] += b4.z;
+              v[4 * j4 + 3] += b4.w;
+            }
+          }
+          if (do_act) {
+            if (act == DASR_ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], v[j] * slope);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+            }
+          }
+          if (scale) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] *= alpha;
+          }
+          uint4 o[2];
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          const int ch = (cg & 63) >> 3;                      // 16-byte chunk index inside the 128 B row
+          sts128(bS + (((ch) ^ sw128) << 4), o[0]);
+          sts128(bS + (((ch + 1) ^ sw128) << 4), o[1]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull_bar[b]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();                       // no CTA leaves while its peer may still signal its barriers / read its filters
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05.mma cta_group::2 issue-rate probe (selftest only): the leader issues `iters` groups of 18 MMAs
+// (M=256, N=n, K=16, bf16; A descriptors walk the 9 tap offsets of a halo tile), back to back, one commit at the end.
+// ---------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_rate_kernel(int n, int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  cluster_sync();
+  if (threadIdx.x < 32) tmem_alloc2(&tptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x < 32 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, n);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 16384);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+      if (elect_one()) {
+#pragma unroll 1
+        for (int tap = 0; tap < 9; tap++) {
+          uint32_t aa = a0 + (uint32_t)(((tap / 3) * 10 + (tap % 3)) * 64);
+#pragma unroll
+          for (int k = 0; k < 2; k++)
+            umma2_bf16(tb, make_desc_sw64(aa + k * 32, 640), make_desc_sw64(b0 + k * 32, 512), idesc, 1u);
+        }
+        if (it == iters - 1)
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (t1 - t0);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc2(tb, 512); }
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" {
+
+int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
+  // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 output in 64-channel blocks, no pre / residual tiles
+  if (!p) return 0;
+  if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
+  if (p->cout % 64 != 0 || p->cout < 64 || p->cout > 256 || p->cin % CHUNK != 0 || p->tile_rev) return 0;
+  const int nchunks = p->cin / CHUNK;
+  const size_t w_bytes = (size_t)9 * nchunks * (p->cout / 2) * ROW_B;
+  const size_t need = w_bytes + 2 * 12288 + 3 * (size_t)EPI_BLK64_BYTES + 1024 + 2048;
+  return need <= (size_t)SMEM_LIMIT ? 1 : 0;
+}
+
+int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, const DasrConvTcParams* p, void* stream) {
+  DASR_REQUIRE(p && in && w && out, "conv_tc2: null argument");
+  DASR_REQUIRE(dasr_conv_tc2_supported(p), "conv_tc2: unsupported configuration (3x3, staged epilogue, cout %% 64 == 0, filters must fit)");
+  DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc2: bad dims");
+  if (p->nchunk_list > 0) {
+    DASR_REQUIRE(p->nchunk_list <= 8 && p->nchunk_list * CHUNK == p->cin, "conv_tc2: chunk list must cover cin");
+  } else {
+    DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc2: input slice");
+  }
+  DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc2: output slice");
+  DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc2: act_cols must be a multiple of 16");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("conv_tc2: cuTensorMapEncodeTiled not available");
+    return DASR_E_NODRIVER;
+  }
+  Tc2Args a;
+  a.p = *p;
+  a.bias = bias;
+  a.nchunks = p->cin / CHUNK;
+  a.n_half = p->cout / 2;
+  a.tiles_x = cdiv(p->W, TILE_W);
+  a.tiles_y = cdiv(p->H, TILE_H);
+  a.ntiles = (long)p->N * a.tiles_x * a.tiles_y;
+  a.w_bytes = 9 * a.nchunks * a.n_half * ROW_B;
+  a.a_stage_bytes = (A_HALO_BYTES + 1023) / 1024 * 1024;
+  a.nb64 = p->cout / 64;
+  a.acc_stride = 256;
+  const int bar_bytes = 1024 + 256 * 4 + 64;
+  int nblk = TC2_MAX_BLOCKS, stages = 0;
+  for (;; nblk--) {
+    const long avail = (long)SMEM_LIMIT - 1024 - a.w_bytes - (long)nblk * EPI_BLK64_BYTES - bar_bytes;
+    stages = (int)(avail / a.a_stage_bytes);
+    if (stages >= 4 || nblk == 3) break;
+  }
+  if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
+  if (stages < 2) {
+    set_error("conv_tc2: filters (%d B per CTA) leave no room for 2 A stages", a.w_bytes);
+    return DASR_E_SMEM;
+  }
+  a.stages = stages;
+  a.nblk = nblk;
+  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + (size_t)nblk * EPI_BLK64_BYTES + bar_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM (the pair allocates all 512 TMEM columns)
+
+  CUtensorMap tm_in, tm_w, tm_out;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2, (cuuint64_t)p->H * p->W * p->in_cs * 2};
+    cuuint32_t box[4] = {CHUNK, HALO_W, HALO_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     p->in_cs > CHUNK ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(input) failed: %d", (int)r); return DASR_E_LAUNCH; }
+  }
+  {
+    cuuint64_t rows = (cuuint64_t)9 * a.nchunks * p->cout;
+    cuuint64_t gdim[2] = {CHUNK, rows};
+    cuuint64_t gstr[1] = {ROW_B};
+    cuuint32_t box[2] = {CHUNK, (cuuint32_t)a.n_half};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(filter) failed: %d", (int)r); return DASR_E_LAUNCH; }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p->out_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)p->out_cs * 2, (cuuint64_t)p->W * p->out_cs * 2, (cuuint64_t)p->H * p->W * p->out_cs * 2};
+    cuuint32_t box[4] = {64, TILE_W, TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(output) failed: %d", (int)r); return DASR_E_LAUNCH; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
+    attr_set = true;
+  }
+  long npairs = (a.ntiles + 1) / 2;
+  int gx = num_sms() & ~1;
+  if ((long)gx > 2 * npairs) gx = (int)(2 * npairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, 1, 1);
+  cfg.blockDim = dim3(TC2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tm_in, tm_w, tm_out, a);
+  if (e != cudaSuccess) {
+    set_error("conv_tc2: launch failed: %s", cudaGetErrorString(e));
+    return DASR_E_LAUNCH;
+  }
+  return check_launch("conv_tc2");
+}
+
+// selftest-only probe (declared in selftest.cu, not in the public header)
+int dasr_probe_mma2_rate(int n, int iters, double* cycles_per_mma) {
+  long long* d;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return DASR_E_LAUNCH;
+  cudaFuncSetAttribute(mma2_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  mma2_rate_kernel<<<num_sms() & ~1, 128, 64 * 1024>>>(n, iters, d);
+  long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { set_error("probe mma2: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
+  *cycles_per_mma = (double)h / ((double)iters * 18.0);
+  return DASR_OK;
+}
+
+}  // extern "C"

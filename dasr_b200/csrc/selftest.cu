@@ -23,6 +23,7 @@
 
 extern "C" int dasr_probe_mma_rate(int n, int sbo, int iters, int a_step, double* cycles_per_mma);
 extern "C" int dasr_probe_tma_rate(int row_elems, int rows_per_box, int cs, int store, double* cycles_per_box);
+extern "C" int dasr_probe_mma2_rate(int n, int iters, double* cycles_per_mma);
 static unsigned long long rng_state = 0x1234567ULL;
 static inline unsigned rnd() {
   rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -201,7 +202,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   const float slope = 0.25f, alpha = 0.5f, mslope = 0.25f;
   const float beta1 = (epi == 2 && gn > 96) ? 0.f : 2.f;   // wide fused launches only carry the in-place pre addend
   const int mc0 = gn >= 32 ? gn - 24 : 0, mc1 = gn;
-  const int act_cols = (epi == 2) ? 16 * ((gn / 16 + 1) / 2) : gn;
+  const int act_cols = (epi == 2 || epi == 4) ? 16 * ((gn / 16 + 1) / 2) : gn;
   const float beta2 = (gn > 96) ? 0.f : -0.5f;   // three staged tiles of a wide launch do not fit shared memory
   if (epi == 1)
     for (size_t i = 0; i < ref.size(); i++) {
@@ -219,6 +220,14 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
       if (c < act_cols) v = v > 0 ? v : v * slope;
       ref[i] = alpha * v + beta1 * res1[i] + beta2 * res1[(i + gn) % ref.size()];
     }
+  if (epi == 4)      // CTA-pair kernel: bias + LeakyReLU on the first act_cols channels + scale, no pre / residual tiles
+    for (size_t i = 0; i < ref.size(); i++) {
+      int c = (int)(i % gn);
+      double v = ref[i];
+      const int ac = 16 * ((gn / 16 + 1) / 2);
+      if (c < ac) v = v > 0 ? v : v * slope;
+      ref[i] = alpha * v;
+    }
   auto in_b = to_bf16(in);
   auto res_b = to_bf16(res1);
   auto msk_b = to_bf16(msk);
@@ -235,7 +244,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   int rc = dasr_conv_tc_setup(&p, kind);
   p.N = N; p.H = H; p.W = W; p.cin = gk; p.in_cs = in_cs; p.in_coff = in_coff;
   p.cout = gn; p.out_cs = out_cs; p.out_coff = out_coff; p.nt = nt;
-  p.act = (epi == 1 || epi == 2) ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = (epi == 1 || epi == 2) ? alpha : 1.f;
+  p.act = (epi == 1 || epi == 2 || epi == 4) ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = (epi == 1 || epi == 2 || epi == 4) ? alpha : 1.f;
   p.act_cols = act_cols;
   p.beta1 = beta1; p.res1_cs = gn; p.res1_coff = 0;
   p.beta2 = beta2; p.res2_cs = gn; p.res2_coff = 0;
@@ -254,8 +263,11 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     dres2 = dalloc<__nv_bfloat16>(r2.size());
     h2d(dres2, r2);
   }
-  rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
-                     epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
+  if (epi == 4)
+    rc |= dasr_conv_tc2(din, dwp, db, dout, &p, 0);
+  else
+    rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
+                       epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
   if (rc == DASR_E_SMEM && e == cudaSuccess) {
@@ -485,6 +497,15 @@ int main(int argc, char** argv) {
           }
       return 0;
     }
+    if (!strcmp(argv[i], "mma2rate")) {     // cta_group::2: M=256 per instruction, two pixel tiles
+      for (int n : {64, 96, 128, 160, 192, 256}) {
+        double c = 0;
+        int rc = dasr_probe_mma2_rate(n, 200, &c);
+        printf("mma2_rate M256 N%-3d K16 cta_group::2 back-to-back : %7.1f cycles/MMA  (%.1f per 128-pixel tile) rc=%d %s\n", n, c, c / 2,
+               rc, rc ? dasr_last_error() : "");
+      }
+      return 0;
+    }
     if (!strcmp(argv[i], "fused")) {
       bench_tc_fused(16, 256, 256, 64, 192, 96, 0, 10);
       bench_tc_fused(16, 256, 256, 32, 160, 160, 1, 10);
@@ -542,6 +563,14 @@ int main(int argc, char** argv) {
       test_tc(1, 21, 10, 64, 16, 16, 0, am, 3);        // last layer: Cout padded to 16, NCHW fp32 out
       test_tc(1, 24, 24, 160, 32, 160, 1, am, 1);      // dgrad conv4-like: K=32 -> N=160
       test_tc(1, 16, 16, 192, 64, 96, 1, am, 0);       // dgrad conv5-like: K=64 -> N=192 split 2x96
+      if (am == 0) {                                   // CTA-pair kernel (cta_group::2): dense-block launch 1 and conv5's dgrad
+        test_tc(1, 16, 8, 64, 192, 192, 0, 0, 4);      // one tile: odd tail (the peer CTA runs an empty tile)
+        test_tc(1, 19, 11, 64, 192, 192, 0, 0, 4);     // ragged, 4 tiles
+        test_tc(2, 32, 16, 64, 192, 192, 0, 0, 4);
+        test_tc(4, 96, 64, 64, 192, 192, 0, 0, 4);     // 192 tiles: pairs take a second iteration, ring wrap-around
+        test_tc(1, 24, 16, 32, 128, 128, 0, 0, 4);     // one chunk, two 64-channel blocks
+        test_tc(1, 16, 16, 192, 64, 192, 1, 0, 4);     // dgrad conv5-like: K=64 -> N=192
+      }
       test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
       test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);
     }

@@ -224,11 +224,6 @@ def rrdb_backward_f32(ctx, params, dout, need_dx=False):
 
 # ---- bf16 tcgen05 inference -----------------------------------------------------------------------
 
-# Dense-block working set per trunk pass.  Chunking the batch so that one pass fits the 126 MB L2 was measured
-# SLOWER on B200 (71 ms vs 62 ms per 16x256x256 forward: the shorter launches are latency-bound), so the default
-# keeps the whole batch in one pass; set e.g. 72 MiB to re-enable.
-TRUNK_L2_BYTES = float(os.environ.get('DASR_B200_TRUNK_BYTES', 'inf'))
-RDB_CHUNK_IMGS = int(os.environ.get('DASR_B200_RDB_CHUNK', '2'))   # images per L2-resident chunk of the persistent RDB kernel
 _TC_W_BUDGET = 150 * 1024   # resident-filter bytes per CTA that still leaves >= 5 halo stages
 
 
@@ -289,7 +284,7 @@ def _pad_vec(b, n):
     return o
 
 
-def _fused_rdb_filters(cache, params, L, r, nf, halves=False):
+def _fused_rdb_filters(cache, params, L, r, nf):
     """Dense-block N-fusion: launch j multiplies ONE input chunk (x for j=1, x_{j-1} otherwise) against the
     filters of ALL convs k >= j that consume it, stacked along Cout.  Returns [(w_packed, bias)] for j=1..5."""
     out = []
@@ -314,10 +309,6 @@ def _fused_rdb_filters(cache, params, L, r, nf, halves=False):
         wsrc = [params[2 * L.rdb_conv(r, k)] for k in ks]            # every filter the stack is built from
         bj_p = params[2 * L.rdb_conv(r, j) + 1]
         ent = [cache.get(('fw', r, j), wsrc, make_w), cache.get(('fb', r, j), bj_p, make_b)]
-        if j == 1 and halves:   # the two Cout halves of launch 1 as separately packed filters (pipelined mode: two launches)
-            half = (nf + 4 * GC) // 2
-            ent.append(cache.get(('fw1a', r), wsrc, lambda: ops.pack_filter_tc(stacked()[:half].contiguous(), TC_FPROP)))
-            ent.append(cache.get(('fw1b', r), wsrc, lambda: ops.pack_filter_tc(stacked()[half:].contiguous(), TC_FPROP)))
         out.append(tuple(ent))
     return out
 
@@ -442,66 +433,27 @@ class _BatchPacker:
                   'pack_filter_tc_batch')
 
 
-# CTAs per dense-block stage when the six stage launches of an RDB run concurrently (sum = 148 SMs); proportional to
-# the per-tile cost floor of each stage (MMA cycles for 1a/1b, TMA bytes for the partial-sum read-modify-write stages)
-PIPE_CTAS = (26, 26, 30, 24, 20, 22)
+PAIR_STAGE1 = os.environ.get('DASR_B200_PAIR', '1') != '0'    # dense-block launch 1 on the CTA-pair kernel (conv_tc2)
 
 
-def _rrdb_trunk_pipelined(L, params, cache, rot, fea, lr, wk, bk, nf, BW, CS):
-    """The 23 x 3 dense blocks with their stages SPATIALLY PIPELINED: the six stage launches of an RDB (1a, 1b, 2..5)
-    run concurrently on disjoint SM subsets, each on its own stream; a stage processes a tile as soon as its
-    producer stage(s) have finished the tiles around it (per-CTA progress counters in global memory, acquire/release).
-    The partial sums a stage re-reads were written microseconds earlier by a neighbouring SM, so the read-modify-write
-    traffic of the N-fused schedule stays in L2 instead of streaming through HBM once per launch."""
-    n_rdb = L.n_rdb
-    dev = fea.device
-    main = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream(device=dev) for _ in range(6)]
-    prog = torch.zeros((n_rdb, 6, 32), dtype=torch.int32, device=dev)      # progress[r][stage][cta]
-    bufs = [rot[i % 3] for i in range(n_rdb + 1)]
-    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
-    for s_ in streams:
-        s_.wait_stream(main)
-    G = PIPE_CTAS
-    half = (BW - nf) // 2
-    for r in range(n_rdb):
-        b = bufs[r]
-        fw = _fused_rdb_filters(cache, params, L, r, nf, halves=True)
-        prev5 = [(prog[r - 1, 5], G[5])] if r > 0 else []
-        bias1 = fw[0][1]
-        with torch.cuda.stream(streams[0]):     # 1a: x -> x1 (complete) | partial conv2, conv3
-            ops.conv_tc(View(b, nf, 0), fw[0][2], bias1[:half].contiguous(), View(b, half, nf), act=ACT_LRELU, slope=0.2,
-                        act_cols=GC, pipe=dict(grid_x=G[0], deps=prev5, progress=prog[r, 0]))
-        with torch.cuda.stream(streams[1]):     # 1b: x -> partial conv4, conv5
-            ops.conv_tc(View(b, nf, 0), fw[0][3], None, View(b, half, nf + half),
-                        pipe=dict(grid_x=G[1], deps=prev5, progress=prog[r, 1]))
-        for j in (2, 3, 4):                     # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, in place
-            o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
-            deps = [(prog[r, 0], G[0]), (prog[r, 1], G[1])] if j == 2 else [(prog[r, j - 1], G[j - 1])]
-            with torch.cuda.stream(streams[j]):
-                ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
-                            act_cols=GC, pre=o, pipe=dict(grid_x=G[j], deps=deps, progress=prog[r, j]))
-        dst = View(bufs[r + 1], nf, 0)
-        if r % 3 == 2:
-            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
-        else:
-            tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
-        with torch.cuda.stream(streams[5]):
-            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS),
-                        pipe=dict(grid_x=G[5], deps=[(prog[r, 4], G[4])], progress=prog[r, 5]), **tail)
-    for s_ in streams:
-        main.wait_stream(s_)
-    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+def _rdb_stage1(b, w, bias, out, nf):
+    """Launch 1 of a dense block: x (K = nf) against the stacked filters of conv1..5 (N = 4*GC + nf = 192), LeakyReLU on the
+    first GC columns (= x1).  One CTA cannot keep the 192-wide filter set resident, so the single-CTA kernel runs it as
+    two Cout tiles of 96; the CTA-pair kernel splits the filters over the two SMs of a TPC and issues M=256, N=192."""
+    if PAIR_STAGE1 and nf == 64 and GC == 32:
+        ops.conv_tc(View(b, nf, 0), w, bias, out, act=ACT_LRELU, slope=0.2, act_cols=GC, pair=True)
+    else:
+        ops.conv_tc(View(b, nf, 0), w, bias, out, nt=out.c // 2, act=ACT_LRELU, slope=0.2, act_cols=GC)
 
 
-def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipelined=None):
+def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
     """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between.
 
-    fused=True : dense-block N-fusion.  Each RDB runs 5 launches; launch j reads one 32/64-channel chunk ONCE
-                 and produces conv j's output plus the partial sums of every later conv of the block
-                 (GEMM N = 192,160,128,96,64 instead of 32,32,32,32,64 — a tcgen05.mma of N<=96 costs the same
-                 ~72 cycles as N=32).  Partial sums live IN PLACE in the channel slots the finished activations
-                 will occupy (bf16), so the only extra state is a 64-channel slot for conv5.
+    fused=True : dense-block N-fusion.  Each RDB runs 5 launches; launch j reads one or two 32-channel chunks ONCE
+                 and produces conv j's output plus partial sums of later convs of the block (a tcgen05.mma of
+                 N <= 128 costs the same ~84 cycles as N = 32).  Partial sums live IN PLACE in the channel slots the
+                 finished activations will occupy (bf16), so the only extra state is a 64-channel slot for conv5.
+                 DASR_B200_SCHED=2 (default): engine.SCHED2 assignment; =1: every launch carries all later partial sums.
     fused=False: one launch per conv over the growing concat (the straightforward restatement).
     """
     _need_cuda(x, 'RRDBNet')
@@ -514,11 +466,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
     bf = torch.bfloat16
     CS = nf + 4 * GC
     BW = CS + (nf if fused else 0)        # fused: extra slot for conv5's partial sums
-    if pipelined is None:
-        pipelined = fused and os.environ.get('DASR_B200_PIPE', '0') == '1'   # experimental: measured slower
-    pipelined = bool(pipelined and fused and nf == 64)
-    rdb_kernel = fused and not pipelined and nf == 64 and GC == 32 and os.environ.get('DASR_B200_RDB', '0') == '1'
-    sched2 = fused and not pipelined and not rdb_kernel and nf == 64 and GC == 32 and os.environ.get('DASR_B200_SCHED', '2') == '2'
+    sched2 = fused and nf == 64 and GC == 32 and os.environ.get('DASR_B200_SCHED', '2') == '2'
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -530,71 +478,48 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, pipeline
 
     xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)       # Cin 3 -> one zero-padded 32-channel chunk
     ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
+    n_rdb = L.n_rdb
+    rot = [_empty((N, H, W, BW), x, bf) for _ in range(3)]
+    bufs = [rot[i % 3] for i in range(n_rdb + 1)]
     fea = _empty((N, H, W, nf), x, bf)
     _mark('tc_begin')
     ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
-    n_rdb = L.n_rdb
+    ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
     lr = _empty((N, H, W, nf), x, bf)
-    # The trunk runs image-chunk by image-chunk so that the dense-block buffer of a chunk (partial sums that the
-    # next launch re-reads) stays resident in the 126 MB L2 instead of round-tripping through HBM.
-    per_img = H * W * BW * 2
-    cn = N if (not fused or TRUNK_L2_BYTES == float('inf')) else max(1, min(N, int(TRUNK_L2_BYTES // max(per_img, 1))))
-    rot = [_empty((cn, H, W, BW), x, bf) for _ in range(3)]
-    rev = False
-    if pipelined:
-        _rrdb_trunk_pipelined(L, params, cache, rot, fea, lr, wk, bk, nf, BW, CS)
-        cn = 0
-    for n0 in (range(0, N, cn) if cn else ()):
-        n1 = min(N, n0 + cn)
-        c = n1 - n0
-        bufs = [rot[i % 3][:c] for i in range(n_rdb + 1)]
-        fea_c = fea[n0:n1]
-        ops.axpby(fea_c, 1.0, None, 0.0, View(bufs[0], nf, 0))
-        for r in range(n_rdb):
-            b = bufs[r]
-            dst = View(bufs[r + 1], nf, 0)
-            if r % 3 == 2:      # (x5*0.2 + x)*0.2 + x_rrdb
-                tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
-            else:
-                tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
-            if fused and sched2:
-                fw = _sched2_rdb_filters(cache, params, L, r, nf)
-                ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2,
-                            act=ACT_LRELU, slope=0.2, act_cols=GC)
-                o = View(b, 2 * GC, nf + GC)                               # x2 | p3
-                ops.conv_tc(b, fw[1][0], fw[1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[1][2])
-                o = View(b, 2 * GC, nf + 2 * GC)                           # x3 | p4
-                ops.conv_tc(b, fw[2][0], fw[2][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[2][2])
-                o = View(b, GC + nf, nf + 3 * GC)                          # x4 | p5
-                ops.conv_tc(b, fw[3][0], fw[3][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[3][2])
-                ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], **tail)
-            elif fused and rdb_kernel:
-                fw = _fused_rdb_filters(cache, params, L, r, nf)
-                ops.rdb_tc(b, bufs[r + 1], bufs[r - 2] if r % 3 == 2 else None, [f[0] for f in fw], [f[1] for f in fw],
-                           tail['alpha'], tail['beta1'], tail.get('beta2', 0.0), chunk_imgs=RDB_CHUNK_IMGS)
-            elif fused:
-                fw = _fused_rdb_filters(cache, params, L, r, nf)
-                # Consecutive launches walk the tile grid in opposite directions: a launch starts with the tiles its
-                # predecessor wrote last, i.e. with the part of the partial sums that is still resident in L2.
-                # launch 1: x -> x1 (complete) | partial conv2..5
-                ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2,
-                            act=ACT_LRELU, slope=0.2, act_cols=GC, tile_rev=rev)
-                rev = not rev
-                for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
-                    o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
-                    ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
-                                act_cols=GC, pre=o, tile_rev=rev)
-                    rev = not rev
-                ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), tile_rev=rev, **tail)
-                rev = not rev
-            else:
-                for k in range(1, 5):
-                    ci = L.rdb_conv(r, k)
-                    ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
-                ci = L.rdb_conv(r, 5)
-                ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=_pick_nt(nf, CS), **tail)
-        ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr[n0:n1], nt=_pick_nt(nf, nf), res1=fea_c, beta1=1.0)
-    del rot
+    for r in range(n_rdb):
+        b = bufs[r]
+        dst = View(bufs[r + 1], nf, 0)
+        if r % 3 == 2:      # (x5*0.2 + x)*0.2 + x_rrdb
+            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+        else:
+            tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
+        if sched2:
+            fw = _sched2_rdb_filters(cache, params, L, r, nf)
+            _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
+            o = View(b, 2 * GC, nf + GC)                               # x2 | p3
+            ops.conv_tc(b, fw[1][0], fw[1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[1][2])
+            o = View(b, 2 * GC, nf + 2 * GC)                           # x3 | p4
+            ops.conv_tc(b, fw[2][0], fw[2][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[2][2])
+            o = View(b, GC + nf, nf + 3 * GC)                          # x4 | p5
+            ops.conv_tc(b, fw[3][0], fw[3][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[3][2])
+            ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], **tail)
+        elif fused:
+            fw = _fused_rdb_filters(cache, params, L, r, nf)
+            # launch 1: x -> x1 (complete) | partial conv2..5
+            _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
+            for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
+                o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
+                ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
+                            act_cols=GC, pre=o)
+            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+        else:
+            for k in range(1, 5):
+                ci = L.rdb_conv(r, k)
+                ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
+            ci = L.rdb_conv(r, 5)
+            ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=_pick_nt(nf, CS), **tail)
+    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+    del rot, bufs
     cur, h, w = lr, H, W
     for u in range(L.n_up):
         h, w = 2 * h, 2 * w
@@ -651,8 +576,7 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
         else:
             tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
         fw = _fused_rdb_filters(cache, params, L, r, nf)
-        ops.conv_tc(View(b, nf, 0), fw[0][0], fw[0][1], View(b, BW - nf, nf), nt=(BW - nf) // 2, act=ACT_LRELU, slope=0.2,
-                    act_cols=GC)
+        _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
         for j in (2, 3, 4):
             o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
             ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o)
@@ -778,7 +702,10 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
             ops.bias_grad(g_x5, gB(ci))
         else:
             wgrad(View(b, CS, 0), g_x5, ci)
-        ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)        # K=64 -> N=192 as 2 x 96
+        if PAIR_STAGE1 and nf == 64 and GC == 32:                                          # K=64 -> N=192 on a CTA pair
+            ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True)
+        else:
+            ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)    # ... or as 2 x 96
         ops.axpby(View(GB, nf, 0), 1.0, g_y, b1, View(GB, nf, 0))
         for k in (4, 3, 2, 1):
             ci = L.rdb_conv(r, k)

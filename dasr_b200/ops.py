@@ -192,10 +192,12 @@ def pack_filter_tc(w, kind):
 
 def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0, act_cols=None,
             pre=None, res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2,
-            a_mode=0, nchw_out=None, cout=None, pipe=None, tile_rev=False, chunks=None):
+            a_mode=0, nchw_out=None, cout=None, tile_rev=False, chunks=None, pair=None):
     """tcgen05 3x3 conv on NHWC bf16 channel slices; chunks = optional list of 32-channel chunk offsets of `inp`'s buffer; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
     v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
-    nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer)."""
+    nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer).
+    pair: True = run on the CTA-pair kernel (dasr_conv_tc2: cta_group::2, filters split over two SMs; `nt` is ignored),
+          None = use it when the launch has no pre / residual tiles and its filter set does not fit one SM as one Cout tile."""
     inp = as_view(inp)
     N, H, W, _ = inp.t.shape
     if nchw_out is not None:
@@ -229,44 +231,19 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
         p.mask_cs, p.mask_coff, p.mask_c0, p.mask_c1, p.mask_slope = mask.cs, mask.coff, mask_c0, mask_c1, mask_slope
     p.a_mode = a_mode
     p.tile_rev = int(bool(tile_rev))
-    pa = None
-    if pipe is not None:
-        # pipe = dict(grid_x=int, deps=[(int32 tensor, producer CTAs), ...] (<= 2), progress=int32 tensor or None)
-        pa = _lib.PipeArgs()
-        pa.grid_x = pipe['grid_x']
-        deps = pipe.get('deps') or []
-        if len(deps) > 0:
-            pa.dep0, pa.dep0_g = deps[0][0].data_ptr(), deps[0][1]
-        if len(deps) > 1:
-            pa.dep1, pa.dep1_g = deps[1][0].data_ptr(), deps[1][1]
-        if pipe.get('progress') is not None:
-            pa.progress = pipe['progress'].data_ptr()
-    check(lib.dasr_conv_tc_pipe(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
-                                res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p),
-                                C.byref(pa) if pa is not None else None, _stream()), 'conv_tc')
-
-
-_rdb_sync = {}
-
-
-def rdb_tc(buf, buf_next, res2, w_packed, bias, alpha, beta1, beta2=0.0, chunk_imgs=2, slope=0.2, next_coff=0, res2_coff=0):
-    """One persistent kernel for a whole dense block (dasr_rdb_tc): buf [N,H,W,256] bf16 with x in channels 0:64;
-    writes alpha*conv5 + beta1*x (+ beta2*res2[..., res2_coff:+64]) into buf_next[..., next_coff:+64]."""
-    N, H, W, cs = buf.shape
-    key = str(buf.device)
-    sync = _rdb_sync.get(key)
-    if sync is None:
-        sync = _rdb_sync[key] = torch.zeros(2, dtype=torch.int32, device=buf.device)      # [barrier counter, error flag]
-    p = _lib.RdbParams()
-    p.N, p.H, p.W, p.nf, p.gc, p.cs = N, H, W, 64, 32, cs
-    p.next_cs, p.next_coff = buf_next.shape[-1], next_coff
-    p.res2_cs, p.res2_coff = (res2.shape[-1] if res2 is not None else 0), res2_coff
-    p.chunk_imgs = chunk_imgs
-    p.alpha, p.beta1, p.beta2, p.slope = alpha, beta1, beta2, slope
-    wp = (C.c_void_p * 5)(*[t.data_ptr() for t in w_packed])
-    bp = (C.c_void_p * 5)(*[t.data_ptr() for t in bias])
-    check(_lib.load().dasr_rdb_tc(_p(buf), _p(buf_next), _p(res2), wp, bp, C.byref(p), C.c_void_p(sync.data_ptr()),
-                                  C.c_void_p(sync.data_ptr() + 4), _stream()), 'rdb_tc')
+    if pair is None:
+        pair = False
+    if pair:
+        if pre is not None or res1 is not None or res2 is not None or mask is not None:
+            raise _lib.DasrError('conv_tc: the CTA-pair kernel has no pre / residual / mask inputs')
+        p.nt = p.cout
+        p.epi_mode = 0
+        if not lib.dasr_conv_tc2_supported(C.byref(p)):
+            raise _lib.DasrError('conv_tc: launch not supported by the CTA-pair kernel (cin=%d cout=%d)' % (p.cin, p.cout))
+        check(lib.dasr_conv_tc2(inp.ptr, _p(w_packed), _p(bias), out.ptr, C.byref(p), _stream()), 'conv_tc2')
+        return
+    check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
+                           res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
 
 
 def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):

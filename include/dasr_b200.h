@@ -152,21 +152,13 @@ int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bi
                  const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16,
                  void* out /* bf16 NHWC, or fp32 NCHW in epi_mode 2 */, const DasrConvTcParams* p, void* stream);
 
-/* Spatially pipelined launches (dense-block stages running concurrently on disjoint SM subsets, each on its own
- * stream): this launch uses grid_x persistent CTAs; a tile is loaded only after every CTA of the producer launch(es)
- * has finished its tiles up to the end of the next tile row (dep*[k] = tiles finished by producer CTA k, int32, zeroed
- * before the producers start; producer and consumer must walk the same tile grid); progress[k] (>= grid_x ints) is
- * published by this launch.  All pointers are device pointers; dep1/progress may be NULL. */
-typedef struct {
-  int grid_x;
-  const int* dep0; int dep0_g;
-  const int* dep1; int dep1_g;
-  int* progress;
-} DasrPipeArgs;
-
-int dasr_conv_tc_pipe(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
-                      const void* res1_bf16, const void* res2_bf16, const void* mask_src_bf16, void* out,
-                      const DasrConvTcParams* p, const DasrPipeArgs* pipe /* NULL = plain launch */, void* stream);
+/* The same convolution on a CTA PAIR (tcgen05 cta_group::2, csrc/conv_tc2.cu): the two SMs of a TPC each keep half of
+ * the filter rows resident and each load the A tile of their own pixel tile; one M=256 instruction feeds both tensor
+ * cores.  For launches whose full filter set does not fit one SM (dense-block launch 1: K = 64, N = 192).
+ * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 64 == 0, no pre / residual tiles. */
+int dasr_conv_tc2_supported(const DasrConvTcParams* p);
+int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* bias, void* out_bf16,
+                  const DasrConvTcParams* p, void* stream);
 
 /* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
  *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)
@@ -218,28 +210,6 @@ int dasr_upsample2x_fwd(const void* src, void* dst, int N, int H, int W, int C, 
 /* dst = a*x + b*y on channel slices (gradient accumulation across concat consumers) */
 int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_cs, int x_coff,
                int y_cs, int y_coff, int d_cs, int d_coff, float a, float b, int is_bf16, void* stream);
-/* A whole ResidualDenseBlock_5C (block.py:254-286) of the inference forward as ONE persistent kernel: the five
- * N-fused stages of the dasr_conv_tc schedule run image chunk by image chunk inside the kernel, separated by grid
- * barriers, so the bf16 partial sums stay in L2 (chunk_imgs images: ~25 MB per 256x256 image).
- *   buf      : NHWC bf16 [N,H,W,cs=256] = [x 0:64 | x1..x4 64:192 | conv5 partial 192:256]; x must be filled
- *   buf_next : receives alpha*(conv5) + beta1*x (+ beta2*res2) in channels [next_coff, next_coff+64) (stride next_cs)
- *   buf_res2 : optional second residual (the RRDB input, every third block), channels [res2_coff, +64), stride res2_cs
- *   w_packed[j], bias[j] (j = 0..4): stacked filters / bias of stage j+1 exactly as the five dasr_conv_tc launches use them
- *   counter  : one device uint32 (zeroed by this call);  error_flag: device int set to 1 if a grid barrier timed out.
- * Results are bit-identical to the five-launch schedule. */
-typedef struct {
-  int N, H, W;
-  int nf, gc;               /* 64, 32 */
-  int cs;                   /* 256 */
-  int next_cs, next_coff;
-  int res2_cs, res2_coff;
-  int chunk_imgs;
-  float alpha, beta1, beta2, slope;
-} DasrRdbParams;
-int dasr_rdb_tc(void* buf, void* buf_next, const void* buf_res2, const void* const* w_packed,
-                const float* const* bias, const DasrRdbParams* p, unsigned int* counter, int* error_flag,
-                void* stream);
-
 /* Filter gradients of all five convs of one ResidualDenseBlock_5C (nf 64, gc 32) in one tcgen05 launch + one
  * deterministic reduction (mixed-precision training).  xbuf: bf16 NHWC, channels [x 0:64 | x1..x4 64:192];
  * ga: bf16 NHWC holding the (LeakyReLU-masked) output gradients of conv1..4 in channels [ga_coff, ga_coff+128);
