@@ -101,6 +101,10 @@ SYMBOLS = {
     'dasr_pack_filter_tc_batch': (_i, [_vp, _i, _i, _vp]),
     'dasr_rdb_wgrad_tc_workspace': (_sz, [_i, _i, _i]),
     'dasr_rdb_wgrad_tc': (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, C.POINTER(_vp), _i, _i, _i, _i, _vp, _sz, _vp]),
+    'dasr_maxpool_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasr_maxpool_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasr_lpips_layer_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'dasr_lpips_layer_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),
     'dasr_prelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp, _vp]),

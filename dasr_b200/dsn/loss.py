@@ -113,8 +113,9 @@ class GeneratorLoss(nn.Module):
             self.color_filter = self.filter_wavelet_LL
         else:
             raise NotImplementedError('Frequency Separation type [{:s}] not recognized'.format(kwargs['filter']))
-        if self.per_type == 'LPIPS':
-            raise NotImplementedError('LPIPS perceptual loss is not on the B200 path yet (use per_type="VGG")')
+        if self.per_type == 'LPIPS':          # DSN/loss.py:65-66 (the CLI default, DSN/train.py:54)
+            from dasr_b200.lpips import PerceptualLossAug
+            self.perceptual_loss = PerceptualLossAug(rotations=lpips_rot_flip, flips=lpips_rot_flip)
         elif self.per_type == 'VGG':
             self.perceptual_loss = PerceptualLossVGG16()
         else:

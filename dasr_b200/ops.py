@@ -317,6 +317,33 @@ def maxpool2_bwd(x, out, dout, din):
     check(_lib.load().dasr_maxpool2_bwd(_p(x), _p(out), _p(dout), _p(din), N, H, W, Cc, _stream()), 'maxpool2_bwd')
 
 
+def maxpool_fwd(x, out, k, s):
+    """k x k stride-s max-pool without padding, NHWC fp32 (AlexNet's MaxPool2d(3, 2))."""
+    N, H, W, Cc = x.shape
+    check(_lib.load().dasr_maxpool_fwd(_p(x), _p(out), N, H, W, Cc, k, s, _stream()), 'maxpool_fwd')
+
+
+def maxpool_bwd(x, out, dout, din, k, s):
+    N, H, W, Cc = x.shape
+    check(_lib.load().dasr_maxpool_bwd(_p(x), _p(out), _p(dout), _p(din), N, H, W, Cc, k, s, _stream()), 'maxpool_bwd')
+
+
+def lpips_layer_fwd(feats, lin_w, val, eps, accumulate):
+    """feats: NHWC fp32 [2N,H,W,C] = [target ; pred] features; val[N] (+)= spatial mean of the lin-weighted squared
+    difference of the channel-normalised features (networks_basic.py:66-79)."""
+    M, H, W, Cc = feats.shape
+    N = M // 2
+    scratch = torch.empty(N * H * W, dtype=torch.float32, device=feats.device)
+    check(_lib.load().dasr_lpips_layer_fwd(_p(feats), _p(lin_w), _p(val), _p(scratch), N, H, W, Cc, eps, int(accumulate),
+                                           _stream()), 'lpips_layer_fwd', 2)
+
+
+def lpips_layer_bwd(feats, lin_w, dval, dpred, eps, accumulate):
+    M, H, W, Cc = feats.shape
+    check(_lib.load().dasr_lpips_layer_bwd(_p(feats), _p(lin_w), _p(dval), _p(dpred), M // 2, H, W, Cc, eps, int(accumulate),
+                                           _stream()), 'lpips_layer_bwd')
+
+
 def instnorm_lrelu_fwd(x, stats, eps=1e-5, slope=0.2):
     N, H, W, Cc = x.shape
     check(_lib.load().dasr_instnorm_lrelu_fwd(_p(x), _p(stats), N, H * W, Cc, eps, slope, _stream()), 'instnorm_lrelu_fwd')

@@ -93,8 +93,9 @@ class DASR_Model(BaseModel):
         if self.is_train:
             self._init_training(opt, train_opt)
         self.print_network()
-        if self.val_lpips:
-            logger.warning('val_lpips requested: LPIPS is not part of the B200 path; LPIPS is reported as nan')
+        if self.val_lpips:      # DASR_model.py:158-159
+            from dasr_b200.lpips import PerceptualLoss as val_lpips
+            self.cri_fea_lpips = val_lpips(model='net-lin', net='alex').to(self.device)
 
     def _init_training(self, opt, cfg):
         """Losses, perceptual network, update cadence, optimisers and schedulers of the GAN step (DASR_model.py:75-151)."""
@@ -108,12 +109,13 @@ class DASR_Model(BaseModel):
         # perceptual loss on VGG19 features
         self.cri_fea, self.l_fea_type = None, cfg['feature_criterion']
         if cfg['feature_weight'] > 0:
-            if self.l_fea_type == 'LPIPS':
-                raise NotImplementedError('feature_criterion LPIPS (AlexNet trunk) is a "next" row (SURVEY §8f.3); '
-                                          'use l1/l2 (VGG19 features)')
-            self.cri_fea = self._criterion(self.l_fea_type)
             self.l_fea_w = cfg['feature_weight']
-            self.netF = networks.define_F(opt, use_bn=False).to(self.device)
+            if self.l_fea_type == 'LPIPS':       # DASR_model.py:97: PerceptualLoss() = mean LPIPS(alex) of [0,1] images
+                from dasr_b200.lpips import PerceptualLossAug
+                self.cri_fea = PerceptualLossAug().to(self.device)
+            else:
+                self.cri_fea = self._criterion(self.l_fea_type)
+                self.netF = networks.define_F(opt, use_bn=False).to(self.device)
         else:
             logger.info('Remove feature loss.')
         # update cadence
@@ -190,6 +192,9 @@ class DASR_Model(BaseModel):
                 real_fea = self.netF(self.real_HR_source).detach()
                 fake_fea = self.netF(self.fake_SR_source)
                 l_g_fea = self.cri_fea(fake_fea, real_fea)
+                l_g_total += self.l_fea_w * l_g_fea
+            elif self.cri_fea and self.l_fea_type == 'LPIPS':
+                l_g_fea = self.cri_fea(self.fake_SR_source, self.real_HR_source)
                 l_g_total += self.l_fea_w * l_g_fea
             if self.l_gan_H_target_w > 0:
                 with _params_frozen(self.netD_target):
@@ -273,7 +278,8 @@ class DASR_Model(BaseModel):
             else:
                 self.fake_H = self.netG(self.var_L)
             if not tsamples and self.val_lpips:
-                self.LPIPS = torch.tensor(float('nan'))
+                from .SR_model import _val_lpips
+                self.LPIPS = _val_lpips(self.cri_fea_lpips, self.fake_H, self.var_H, self.device)
             self.netG.train()
 
     def get_current_log(self):

@@ -26,6 +26,16 @@ def _view(img, t, h, v, inverse=False):
     return img.contiguous()
 
 
+def _val_lpips(metric, a, b, device):
+    """LPIPS of the 8-bit round trip of two image batches (SR_model.py:95-99 / DASR_model.py:340-344): tensor2img
+    (clamp, x255, round, BGR) -> RGB -> im2tensor ([-1, 1]) -> net-lin alex distance of the first image."""
+    from dasr_b200.lpips import im2tensor
+    from dasr_b200.srn.utils import util
+    ia, ib = util.tensor2img(a.detach().float().cpu().clone()), util.tensor2img(b.detach().float().cpu().clone())
+    ia, ib = ia[:, :, [2, 1, 0]], ib[:, :, [2, 1, 0]]
+    return metric(im2tensor(ia).to(device), im2tensor(ib).to(device))[0][0][0][0]
+
+
 class SRModel(BaseModel):
     def __init__(self, opt):
         super().__init__(opt)
@@ -35,9 +45,9 @@ class SRModel(BaseModel):
         if self.is_train:
             self._init_training(opt['train'])
         self.print_network()
-        if self.val_lpips:
-            # LPIPS (AlexNet trunk) is outside the hot path and its weights are not available offline
-            logger.warning('val_lpips requested: LPIPS is not part of the B200 path; LPIPS is reported as nan')
+        if self.val_lpips:      # SR_model.py:66-67: PerceptualLoss(model='net-lin', net='alex')
+            from dasr_b200.lpips import PerceptualLoss
+            self.cri_fea_lpips = PerceptualLoss(model='net-lin', net='alex').to(self.device)
 
     def _init_training(self, cfg):
         self.netG.train()
@@ -65,7 +75,7 @@ class SRModel(BaseModel):
         with torch.no_grad():
             self.fake_H = forward_chop(self.var_L, self.scale, self.netG) if self.chop else self.netG(self.var_L)
             if self.val_lpips:
-                self.LPIPS = torch.tensor(float('nan'))
+                self.LPIPS = _val_lpips(self.cri_fea_lpips, self.real_H, self.fake_H, self.device)
         self.netG.train()
 
     def test_x8(self):

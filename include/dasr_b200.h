@@ -219,6 +219,25 @@ int dasr_rdb_wgrad_tc(const void* xbuf, int x_cs, const void* ga, int ga_cs, int
                       int gb_coff, float* const* dw, int N, int H, int W, int accumulate, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LPIPS (AlexNet trunk + learned linear calibration; codes/PerceptualSimilarity/models/networks_basic.py:27-107,
+ * pretrained_networks.py:57-96) — the feature criterion "LPIPS" of DASR_model.py:97,231-233, the validation metric of
+ * SR_model.py:66-67,95-99 / DASR_model.py:158-159,340-344 and DSN's default perceptual loss (DSN/loss.py:65-66).
+ * The trunk's convolutions (+ReLU) run on dasr_conv2d_f32; these are the remaining pieces.
+ * ---------------------------------------------------------------------------------------------- */
+/* k x k stride-s max-pool without padding, floor mode, NHWC fp32 (nn.MaxPool2d(3, 2) of alexnet.features); the backward
+ * gives the gradient to the first maximal element of every window (ATen's tie rule), gather form (no atomics). */
+int dasr_maxpool_fwd(const float* in, float* out, int N, int H, int W, int C, int k, int s, void* stream);
+int dasr_maxpool_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H, int W, int C, int k,
+                     int s, void* stream);
+/* One LPIPS layer.  feats: NHWC fp32 [2N,H,W,C] = [target features ; pred features]; lin_w: C non-negative weights.
+ *   val[n] (+)= mean_{h,w} sum_c lin_w[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2        (accumulate = add to val)
+ * pix_scratch: N*H*W floats.  bwd: gradient with respect to the PRED features ([N,H,W,C], accumulate = add). */
+int dasr_lpips_layer_fwd(const float* feats, const float* lin_w, float* val, float* pix_scratch, int N, int H, int W, int C,
+                         float eps, int accumulate, void* stream);
+int dasr_lpips_layer_bwd(const float* feats, const float* lin_w, const float* dval, float* dpred_feats, int N, int H, int W,
+                         int C, float eps, int accumulate, void* stream);
+
 /* 2x2 s2 max-pool NHWC fp32 fwd / bwd (VGG19 features, architecture.py:1076) */
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
 int dasr_maxpool2_bwd(const float* in, const float* out, const float* dout, float* din, int N, int H,
