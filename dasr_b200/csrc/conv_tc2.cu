@@ -57,7 +57,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   uint64_t* sfull_bar = tempty_bar + 2;                   // [nblk]   block written by the epilogue warps
   uint64_t* sfree_bar = sfull_bar + TC2_MAX_BLOCKS;       // [nblk]   block read by its TMA store
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + TC2_MAX_BLOCKS);
-  float* sBias = reinterpret_cast<float*>(tmem_ptr + 4);  // [cout]
+  float* sBias = reinterpret_cast<float*>(bars + 32);     // [cout]  (16-byte aligned: read with ld.shared.v4)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,7 +376,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, c
   a.a_stage_bytes = (A_HALO_BYTES + 1023) / 1024 * 1024;
   a.nb64 = p->cout / 64;
   a.acc_stride = 256;
-  const int bar_bytes = 1024 + 256 * 4 + 64;
+  const int bar_bytes = 32 * 8 + 256 * 4 + 64;
   int nblk = TC2_MAX_BLOCKS, stages = 0;
   for (;; nblk--) {
     const long avail = (long)SMEM_LIMIT - 1024 - a.w_bytes - (long)nblk * EPI_BLK64_BYTES - bar_bytes;

@@ -400,10 +400,16 @@ static void bench_tc(int N, int H, int W, int cin, int cout, int nt, int kind, i
 
 // dense-block fused launch shape: one 32-channel chunk in, `cout` channels (finished conv + partial sums) out,
 // partial sums accumulated IN PLACE (pre == out), activation on the first 32 channels only.
-static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int with_pre, int iters) {
+// in_cs / out_cs = 0: both operands are channel slices of ONE 256-channel buffer (the dense-block layout of the engine);
+// otherwise the input is a dense [N,H,W,in_cs] tensor and the output / partial-sum tile a dense [N,H,W,out_cs] tensor
+// (what a slab-planar activation layout would look like to the kernel).  pair = 1: CTA-pair kernel (dasr_conv_tc2).
+static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int with_pre, int iters, int in_cs = 0, int out_cs = 0,
+                           int pair = 0) {
   const int cs = 256;
-  size_t n = (size_t)N * H * W * cs;
+  const bool planar = in_cs > 0;
+  size_t n = (size_t)N * H * W * (planar ? in_cs : cs);
   __nv_bfloat16* buf = dalloc<__nv_bfloat16>(n);
+  __nv_bfloat16* obuf = planar ? dalloc<__nv_bfloat16>((size_t)N * H * W * out_cs) : buf;
   std::vector<float> w((size_t)cout * cin * 9);
   for (auto& v : w) v = rnd_q(4, 64.f);
   float* dw = dalloc<float>(w.size());
@@ -412,15 +418,19 @@ static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int w
   DasrConvTcParams p;
   memset(&p, 0, sizeof(p));
   dasr_conv_tc_setup(&p, 0);
-  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = cs; p.in_coff = 0;
-  p.cout = cout; p.out_cs = cs; p.out_coff = cs - cout; p.nt = nt;
+  p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = planar ? in_cs : cs; p.in_coff = 0;
+  p.cout = cout; p.out_cs = planar ? out_cs : cs; p.out_coff = planar ? 0 : cs - cout; p.nt = nt;
   p.act = DASR_ACT_LRELU; p.slope = 0.2f; p.alpha = 1.f; p.act_cols = 32; p.epi_mode = 0;
-  p.pre_cs = cs; p.pre_coff = cs - cout;
+  p.pre_cs = p.out_cs; p.pre_coff = p.out_coff;
   if (getenv("EPI1") && !with_pre) p.epi_mode = 1;     // direct st.global epilogue instead of staged tile + TMA store
   dasr_pack_filter_tc(dw, dwp, cout, cin, 0, 0);
-  void* pre = with_pre ? (void*)buf : nullptr;
+  void* pre = with_pre ? (void*)obuf : nullptr;
   int rc = 0;
-  for (int i = 0; i < 3; i++) rc |= dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, buf, &p, 0);
+  auto run = [&]() {
+    return pair ? dasr_conv_tc2(buf, dwp, nullptr, obuf, &p, 0)
+                : dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, obuf, &p, 0);
+  };
+  for (int i = 0; i < 3; i++) rc |= run();
   cudaError_t e = cudaDeviceSynchronize();
   if (rc || e != cudaSuccess) {
     printf("bench fused cin%d cout%d nt%d: rc=%d %s cuda=%s\n", cin, cout, nt, rc, dasr_last_error(), cudaGetErrorString(e));
@@ -430,14 +440,16 @@ static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int w
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; i++) dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, buf, &p, 0);
+  for (int i = 0; i < iters; i++) run();
   cudaEventRecord(e1);
   CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
   double tiles_per_sm = (double)N * (H / 16) * (W / 8) / 148.0 * (cout / nt);
-  printf("bench fused  %dx%dx%d K%-3d N%-3d nt%-3d pre%d : %8.3f ms  %7.1f TFLOP/s  %6.2f us/tile\n", N, H, W, cin, cout, nt,
-         with_pre, ms, 2.0 * N * H * W * cin * cout * 9 / ms * 1e-9, ms * 1e3 / tiles_per_sm);
+  if (pair) tiles_per_sm = (double)N * (H / 16) * (W / 8) / 148.0;
+  printf("bench fused  %dx%dx%d K%-3d N%-3d nt%-3d pre%d %s%s: %8.3f ms  %7.1f TFLOP/s  %6.2f us/tile\n", N, H, W, cin, cout, nt,
+         with_pre, planar ? "planar " : "", pair ? "pair " : "", ms, 2.0 * N * H * W * cin * cout * 9 / ms * 1e-9, ms * 1e3 / tiles_per_sm);
+  if (planar) cudaFree(obuf);
   cudaFree(buf); cudaFree(dw); cudaFree(dwp);
 }
 
@@ -520,6 +532,16 @@ int main(int argc, char** argv) {
       bench_tc_fused(16, 256, 256, 64, 64, 64, 1, 10);
       bench_tc_fused(16, 256, 256, 64, 64, 64, 0, 10);
       bench_tc_fused(2, 256, 256, 64, 64, 64, 0, 40);
+      // slab-planar activations: dense 32/64-channel tensors instead of slices of a 256-channel pixel row
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 1, 10, 32, 64);
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 0, 10, 32, 64);
+      bench_tc_fused(16, 256, 256, 64, 64, 64, 1, 10, 64, 64);
+      bench_tc_fused(16, 256, 256, 32, 128, 128, 1, 10, 32, 128);
+      bench_tc_fused(16, 256, 256, 64, 192, 96, 0, 10, 64, 192);
+      // CTA-pair kernel: dense-block launch 1
+      bench_tc_fused(16, 256, 256, 64, 192, 192, 0, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 64, 192, 192, 0, 10, 64, 192, 1);
+      bench_tc_fused(16, 256, 256, 32, 128, 128, 0, 10, 0, 0, 1);
       return 0;
     }
     if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes

@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from dasr_b200 import engine, ops
+from dasr_b200.srn.models.modules.architecture import FilterLow
 from dasr_b200.srn.models.modules.loss import L1Loss, MSELoss, haar_split, mean
 
 
@@ -107,8 +108,9 @@ class GeneratorLoss(nn.Module):
         super().__init__()
         self.pixel_loss = L1Loss()
         self.per_type = kwargs['per_type']
-        if kwargs['filter'].lower() in ('gau', 'avg_pool'):
-            raise NotImplementedError('un-padded FilterLow colour filter is not on the B200 path (use filter="wavelet")')
+        if kwargs['filter'].lower() in ('gau', 'avg_pool'):     # un-padded low-pass colour filter (DSN/loss.py:50-56)
+            self.color_filter = FilterLow(recursions=recursions, stride=stride, kernel_size=kernel_size, padding=False,
+                                          gaussian=kwargs['filter'].lower() == 'gau')
         elif kwargs['filter'].lower() == 'wavelet':
             self.color_filter = self.filter_wavelet_LL
         else:

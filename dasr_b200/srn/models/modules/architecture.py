@@ -233,19 +233,34 @@ class VGGFeatureExtractor(nn.Module):
 # --------------------------------------------------------------------------------------------------
 
 class _DWFilterFunction(torch.autograd.Function):
+    """valid=True: the un-padded filter (FilterLow(padding=False), DSN/loss.py:50-56).  Away from the border the padded
+    and the un-padded filter are the same stencil, so the kernel runs in 'same' mode and the interior is cropped
+    (forward) / the gradient is zero-extended (backward) — copies only, on 3-channel crops."""
+
     @staticmethod
-    def forward(ctx, x, taps, k, mode, include_pad):
+    def forward(ctx, x, taps, k, mode, include_pad, valid=False):
         out = torch.empty_like(x, dtype=torch.float32)
         ops.dwfilter(x.contiguous().float(), out, taps, k, mode, include_pad)
-        ctx.cfg = (taps, k, mode, include_pad)
+        ctx.cfg = (taps, k, mode, include_pad, valid, tuple(x.shape))
+        if valid:
+            p = (k - 1) // 2
+            if x.shape[2] <= 2 * p or x.shape[3] <= 2 * p:
+                raise ValueError('image smaller than the un-padded %dx%d filter' % (k, k))
+            out = out[:, :, p:x.shape[2] - p, p:x.shape[3] - p].contiguous()
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        taps, k, mode, include_pad = ctx.cfg
+        taps, k, mode, include_pad, valid, shape = ctx.cfg
+        dout = dout.contiguous().float()
+        if valid:
+            p = (k - 1) // 2
+            full = torch.zeros(shape, dtype=torch.float32, device=dout.device)
+            full[:, :, p:shape[2] - p, p:shape[3] - p] = dout
+            dout = full
         dx = torch.empty_like(dout)
-        ops.dwfilter(dout.contiguous(), dx, taps, k, mode, include_pad, backward=True)
-        return dx, None, None, None, None
+        ops.dwfilter(dout, dx, taps, k, mode, include_pad, backward=True)
+        return dx, None, None, None, None, None
 
 
 class GaussianFilter(nn.Module):
@@ -254,8 +269,9 @@ class GaussianFilter(nn.Module):
 
     def __init__(self, kernel_size=5, stride=1, padding=4):
         super().__init__()
-        if stride != 1 or padding != (kernel_size - 1) // 2:
-            raise NotImplementedError('GaussianFilter: only stride 1 / same padding is on the path')
+        if stride != 1 or padding not in (0, (kernel_size - 1) // 2) or kernel_size % 2 == 0:
+            raise NotImplementedError('GaussianFilter: stride 1, odd kernel, same or no padding')
+        self.valid = padding == 0 and kernel_size > 1
         m = (kernel_size - 1) / 2.0
         var = (kernel_size / 6.0) ** 2.0
         ax = torch.arange(kernel_size).float()
@@ -270,23 +286,24 @@ class GaussianFilter(nn.Module):
         return self.gaussian_filter.weight.detach()[0, 0].contiguous()
 
     def forward(self, x):
-        return _DWFilterFunction.apply(x, self.taps(), self.kernel_size, 0, True)
+        return _DWFilterFunction.apply(x, self.taps(), self.kernel_size, 0, True, self.valid)
 
 
 class FilterLow(nn.Module):
     def __init__(self, recursions=1, kernel_size=5, stride=1, padding=True, include_pad=True, gaussian=False):
         super().__init__()
-        if stride != 1 or not padding:
-            raise NotImplementedError('FilterLow: only stride 1 with padding is on the path')
+        if stride != 1 or kernel_size % 2 == 0:
+            raise NotImplementedError('FilterLow: only stride 1 with an odd kernel is on the path')
         self.kernel_size, self.include_pad, self.gaussian = kernel_size, include_pad, gaussian
-        pad = int((kernel_size - 1) / 2)
+        self.valid = (not padding) and kernel_size > 1
+        pad = int((kernel_size - 1) / 2) if padding else 0
         self.filter = GaussianFilter(kernel_size=kernel_size, stride=stride, padding=pad) if gaussian else \
             nn.AvgPool2d(kernel_size=kernel_size, stride=stride, padding=pad, count_include_pad=include_pad)
         self.recursions = recursions
 
     def _apply_once(self, img, mode):
         taps = self.filter.taps() if self.gaussian else None
-        return _DWFilterFunction.apply(img, taps, self.kernel_size, mode, self.include_pad)
+        return _DWFilterFunction.apply(img, taps, self.kernel_size, mode, self.include_pad, self.valid and mode == 0)
 
     def forward(self, img):
         for _ in range(self.recursions):

@@ -190,4 +190,46 @@ def test_dsn_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         Discriminator(filter_type='dct')
     with pytest.raises(NotImplementedError):
-        GeneratorLoss(per_type='LPIPS', filter='wavelet')
+        GeneratorLoss(per_type='SSIM', filter='wavelet')
+
+
+def test_generator_loss_with_auto_reproduce_options_vs_reference(golden):
+    """GeneratorLoss as codes/DSN/auto_reproduce_launcher_*.sh build it (--filter avg_pool, default --per_type LPIPS):
+    un-padded 5x5 box colour filter (DSN/loss.py:50-56) + LPIPS(alex) perceptual loss, against the reference's values."""
+    from dasr_b200.dsn.loss import GeneratorLoss
+    from oracle import lpips_oracle as LP
+    g = golden('dsn_autorepro.pt')
+    cfg = g['gloss_cfg']
+    full = dict(O.synth_state_dict(LP.alex_shapes(), cfg['alex_seed'], 1.0))
+    for i, w in enumerate(g['lins']):
+        full['lin%d.model.1.weight' % i] = w
+    for ft in ('avg_pool', 'gau'):
+        ref = g['gloss_' + ft]
+        gl = GeneratorLoss(per_type='LPIPS', filter=ft, kernel_size=5, w_col=1, w_tex=cfg['w_tex'], w_per=cfg['w_per'], wgan=False).cuda()
+        gl.perceptual_loss.loss.loss_network.net.load_state_dict(full, strict=False)
+        tex = O.synth_image((2, 1, 16, 16), cfg['tex_seed']).cuda().requires_grad_(True)
+        img = O.synth_image(cfg['shape'], cfg['img_seed']).cuda().requires_grad_(True)
+        tgt = O.synth_image(cfg['shape'], cfg['tgt_seed']).cuda()
+        total = gl(tex, img, tgt)
+        total.backward()
+        for name, mine in (('total', total), ('tex_loss', gl.last_tex_loss), ('per_loss', gl.last_per_loss), ('col_loss', gl.last_col_loss)):
+            assert abs(float(mine) - float(ref[name])) <= 1e-4 * max(1.0, abs(float(ref[name]))), (ft, name, float(mine), float(ref[name]))
+        assert rel_linf(tex.grad, ref['dtex']) < TOL
+        assert rel_linf(img.grad, ref['dimg']) < TOL, ft
+
+
+def test_fsd_avg_pool_highpass_vs_reference(golden):
+    """Discriminator(D_arch='FSD', filter_type='avg_pool') — the discriminator of the Auto-Reproduce DSN stage."""
+    from dasr_b200.dsn.model import Discriminator
+    g = golden('dsn_autorepro.pt')['fsd_avg']
+    net = Discriminator(kernel_size=5, wgan=False, highpass=True, D_arch='FSD', norm_layer='Instance', filter_type='avg_pool')
+    net.load_state_dict(O.synth_state_dict(D.fsd_shapes(3), g['w_seed'], 1.0), strict=False)
+    net.cuda()
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert rel_linf(out, g['out']) < TOL
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    assert rel_linf(x.grad, g['dx']) < TOL
+    named = dict(net.named_parameters())
+    for k, n in g['grad_norms'].items():
+        assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
