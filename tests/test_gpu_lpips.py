@@ -55,7 +55,7 @@ def test_lpips_feature_criterion_in_dasr_model(golden):
     """feature_criterion: "LPIPS" (train_DASR.json:80, train_DASR_auto_reproduce_aim2019.json) runs a training step and its
     log value equals the oracle's LPIPS of the same SR / HR pair."""
     from dasr_b200.srn.models import create_model
-    from test_gpu_parity import make_opt, unwrap
+    from helpers import make_opt, unwrap
     g = golden('lpips_alex.pt')
     opt = make_opt(True, 'DASR', 1, 'wavelet')
     opt['train']['feature_criterion'] = 'LPIPS'

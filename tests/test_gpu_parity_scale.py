@@ -111,10 +111,14 @@ def test_config1_bf16_nb23_16x256_vs_fp32_kernels():
         print('config1 %s nb23 16x256x256 vs fp32 kernels: rel-Linf %.3e rel-rms %.3e | 8-bit: %d of %d differ, max %d LSB | '
               '|dPSNR| %.5f dB |dSSIM| %.6f (PSNR ~31 dB)' % (prec, e, rms, nd, 3 * imgs[0].size, mx, dp, dq))
         res[prec] = (e, rms, mx, dp, dq)
-    e, rms, mx, dp, dq = res['bf16']
-    assert e < 2e-2 and rms < 3e-3
-    assert mx <= 3
-    assert dp < 2e-2 and dq < 2e-3
+    # measured on B200 (round 2): rel-Linf 6.8e-4, rel-rms 1.1e-4, 2.7 % of the 8-bit pixels differ by 1 LSB,
+    # |dPSNR| 0.0024 dB, |dSSIM| 0.0002 at PSNR ~31 dB — i.e. PSNR/SSIM agree to 2 decimals, not to the 3 the north star
+    # asks of the tensor-core path (the fp32 kernels above do).  Bounds = ~2x the measurement.
+    for prec in ('bf16', 'bf16_layer'):
+        e, rms, mx, dp, dq = res[prec]
+        assert e < 2e-3 and rms < 3e-4, prec
+        assert mx <= 1, prec
+        assert dp < 6e-3 and dq < 6e-4, prec
 
 
 def test_mixed_precision_dasr_steps_vs_reference_fixture(golden, monkeypatch):
@@ -125,7 +129,7 @@ def test_mixed_precision_dasr_steps_vs_reference_fixture(golden, monkeypatch):
     compared through the UPDATE direction (cosine > 0.8: signs of near-zero gradients flip under bf16)."""
     monkeypatch.setenv('DASR_B200_TRAIN_PRECISION', 'bf16')
     from dasr_b200.srn.models import create_model
-    from test_gpu_parity import make_opt, unwrap
+    from helpers import make_opt, unwrap
     g = golden('dasr_step_wavelet.pt')
     model = create_model(make_opt(True, 'DASR', g['nb'], g['fs']))
     sdG = O.synth_state_dict(O.rrdbnet_shapes(nb=g['nb']), g['wG_seed'], g['gain_G'])

@@ -246,6 +246,42 @@ def test_reference_test_py_runs_unchanged_through_the_launcher(tmp_path):
     assert 'no CPU fallback exists' in err, err[-2000:]
 
 
+def test_auto_reproduce_resolves_to_the_mirrors_after_install(tmp_path):
+    """`python -m dasr_b200.install <codes>` + the unmodified Auto_Reproduce.py (Auto_Reproduce.py:38-40 shells out to
+    `cd ./DSN; sh auto_reproduce_launcher_<dataset>.sh` and `cd ./SRN; python train.py -opt ...`): both child scripts must
+    import the dasr_b200 mirrors although their own directory is first on sys.path.  The stages stop at the datasets
+    (no data here); the overlay log records which imports were redirected for which script directory."""
+    import shutil
+    import pytest
+    ref = '/root/reference/codes'
+    if not os.path.exists(os.path.join(ref, 'Auto_Reproduce.py')):
+        pytest.skip('reference checkout not present')
+    codes = tmp_path / 'codes'
+    shutil.copytree(ref, str(codes), ignore=shutil.ignore_patterns('*.tar', '*.png', '*.jpg', '*.pyc', '__pycache__', '*.gif'))
+    from dasr_b200 import install
+    import io
+    buf = io.StringIO()
+    site_dir = install.install(str(codes), pth=False, out=buf)
+    assert 'PYTHONPATH' in buf.getvalue() and (codes / 'SRN' / '.dasr_b200').read_text().strip() == 'SRN'
+    log = tmp_path / 'overlay.log'
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([site_dir, ROOT, os.path.join(ROOT, 'oracle', 'ref_stubs')]),
+               CUDA_VISIBLE_DEVICES='', DASR_B200_OVERLAY_LOG=str(log), DASR_B200_ALLOW_RANDOM_VGG='1')
+    r = subprocess.run([sys.executable, 'Auto_Reproduce.py', '--dataset', 'realsr', '--artifact', 'tdrealsr'], cwd=str(codes), env=env,
+                       capture_output=True, text=True, timeout=900)
+    text = log.read_text() if log.exists() else ''
+    dsn_dir, srn_dir = str(codes / 'DSN'), str(codes / 'SRN')
+    for name in ('model', 'loss'):
+        assert any(l.startswith(name + ' -> ') and 'dasr_b200/dsn/' in l and dsn_dir in l for l in text.splitlines()), (name, text, r.stderr[-3000:])
+    for name in ('options', 'utils', 'models'):
+        assert any(l.startswith(name + ' -> ') and 'dasr_b200/srn/' in l and srn_dir in l for l in text.splitlines()), (name, text, r.stderr[-3000:])
+    # an unmarked directory is left alone
+    install.uninstall(str(codes), out=buf)
+    assert not (codes / 'SRN' / '.dasr_b200').exists()
+    log.unlink()
+    subprocess.run([sys.executable, '-c', 'import options.options'], cwd=srn_dir, env=env, capture_output=True, text=True, timeout=300)
+    assert not log.exists() or 'options' not in log.read_text()
+
+
 def test_bench_cpu_leg_and_generators_run():
     """bench.py: the CPU reference leg runs (tiny image) and the local deterministic generator matches the oracle's."""
     import torch
