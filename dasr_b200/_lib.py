@@ -74,7 +74,7 @@ SYMBOLS = {
     'dasr_pack_filter_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasr_conv_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
     'dasr_conv_tc2_supported': (_i, [C.POINTER(ConvTcParams)]),
-    'dasr_conv_tc2': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
+    'dasr_conv_tc2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvTcParams), _vp]),
     'dasr_conv_tc_setup': (_i, [C.POINTER(ConvTcParams), _i]),
     'dasr_pack_filter_tc_bytes': (_sz, [_i, _i, _i]),
     'dasr_pack_filter_tc': (_i, [_vp, _vp, _i, _i, _i, _vp]),

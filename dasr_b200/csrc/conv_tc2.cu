@@ -14,8 +14,10 @@
 // Layout per CTA: [filters: 9 taps x nchunks x (N/2 rows x 64 B)] [A stages: halo tile 18x10 px x 64 B, SWIZZLE_64B]
 // [output staging ring: 64-channel blocks of 128 px x 128 B, SWIZZLE_128B] [barriers, bias].
 // Warp roles (TC2_THREADS = 352): warp 0 TMA producer (filters once, A halo tiles) / warp 1 TMEM allocator + (leader
-// only) MMA issuer / warps 2..9 epilogue (TMEM -> registers -> bias, LeakyReLU on the first act_cols columns -> bf16
-// block in shared memory) / warp 10 TMA stores.
+// only) MMA issuer / warps 2..9 epilogue (TMEM -> registers -> +bias, +pre, activation on the first act_cols columns,
+// scale, +residuals -> bf16 block in shared memory) / warp 10 epilogue TMA (pre / residual blocks in, finished blocks out).
+// The epilogue works in 64-channel blocks (128 px x 128 B): v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2,
+// the same contract as dasr_conv_tc's staged epilogue, so every launch of the dense-block schedules can run on a pair.
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -26,6 +28,10 @@ constexpr int TC2_WARPS = 2 + TC2_EPI_WARPS + 1;
 constexpr int TC2_THREADS = 32 * TC2_WARPS;
 constexpr int TC2_MAX_STAGES = 6;
 constexpr int TC2_MAX_BLOCKS = 6;      // staging ring entries (64-channel output blocks)
+
+struct Tc2Maps {          // TMA descriptors of the 64-channel epilogue blocks: out, pre, res1, res2
+  CUtensorMap m[4];
+};
 
 struct Tc2Args {
   DasrConvTcParams p;
@@ -40,15 +46,19 @@ struct Tc2Args {
   int acc_stride;     // TMEM columns between the two accumulators
 };
 
+template <bool HAS_PRE, int NRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
-                const __grid_constant__ CUtensorMap tmap_out, const Tc2Args a) {
+                const __grid_constant__ Tc2Maps em, const Tc2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + a.w_bytes;
-  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;                  // [nblk] 64-channel output blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)a.nblk * EPI_BLK64_BYTES);
+  uint8_t* sS = sA + (size_t)a.stages * a.a_stage_bytes;                  // [nblk] 64-channel output blocks (pre addend in place)
+  uint8_t* sR1 = sS + (size_t)a.nblk * EPI_BLK64_BYTES;                   // [nblk] res1 blocks
+  uint8_t* sR2 = sR1 + (NRES >= 1 ? (size_t)a.nblk * EPI_BLK64_BYTES : 0);   // [nblk] res2 blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR2 + (NRES >= 2 ? (size_t)a.nblk * EPI_BLK64_BYTES : 0));
+  constexpr bool HAS_LOADS = HAS_PRE || NRES > 0;
   uint64_t* full_bar = bars;                              // [stages] LEADER: both CTAs' A chunks landed
   uint64_t* empty_bar = bars + TC2_MAX_STAGES;            // [stages] each CTA: A chunk consumed (multicast commit)
   uint64_t* w_bar = bars + 2 * TC2_MAX_STAGES;            // [1]      LEADER: both filter halves landed
@@ -56,8 +66,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;                   // [2]      LEADER: accumulator drained by BOTH CTAs' epilogues
   uint64_t* sfull_bar = tempty_bar + 2;                   // [nblk]   block written by the epilogue warps
   uint64_t* sfree_bar = sfull_bar + TC2_MAX_BLOCKS;       // [nblk]   block read by its TMA store
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + TC2_MAX_BLOCKS);
-  float* sBias = reinterpret_cast<float*>(bars + 32);     // [cout]  (16-byte aligned: read with ld.shared.v4)
+  uint64_t* pre_bar = sfree_bar + TC2_MAX_BLOCKS;         // [nblk]   pre / residual blocks landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pre_bar + TC2_MAX_BLOCKS);
+  float* sBias = reinterpret_cast<float*>(bars + 40);     // [cout]  (16-byte aligned: read with ld.shared.v4)
 
   const DasrConvTcParams& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,7 +79,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&em.m[0]);
     for (int s = 0; s < a.stages; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -81,6 +92,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     for (int b = 0; b < a.nblk; b++) {
       mbar_init(&sfull_bar[b], TC2_EPI_WARPS);
       mbar_init(&sfree_bar[b], 1);
+      mbar_init(&pre_bar[b], 1);
     }
     fence_barrier_init();
   }
@@ -177,21 +189,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       }
     }
   } else if (warp == TC2_WARPS - 1) {
-    // =========================== TMA store warp ===========================
+    // =========================== epilogue TMA warp ===========================
+    // blocks are numbered k = it * nb64 + i over this CTA's tiles; block k uses ring slot k % nblk
     if (lane == 0) {
-      pdl_wait();                       // the slots written here may still be read by the previous launch
-      uint32_t k = 0;                   // running block index
-      for (long it = 0; it < niter; it++) {
+      pdl_wait();                       // output slots / pre / residual tensors belong to earlier launches until now
+      const uint32_t nb = (uint32_t)a.nb64, nblk = (uint32_t)a.nblk;
+      const uint32_t total = (uint32_t)niter * nb;
+      const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * EPI_BLK64_BYTES);
+      auto issue_loads = [&](uint32_t k) {
+        const uint32_t b = k % nblk;
         int x0, y0, n;
-        const bool live = tile_of(it, x0, y0, n);
-        for (int i = 0; i < a.nb64; i++, k++) {
-          const int b = (int)(k % (uint32_t)a.nblk);
-          mbar_wait(&sfull_bar[b], (k / (uint32_t)a.nblk) & 1);
-          if (live) {
-            tma_store_4d(&tmap_out, sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + i * 64, x0, y0, n);
-            bulk_commit();
-            bulk_wait_read0();
-          }
+        tile_of((long)(k / nb), x0, y0, n);          // tail tile (n >= N): zero-filled boxes still complete the barrier
+        const int col = (int)(k % nb) * 64;
+        mbar_expect_tx(&pre_bar[b], load_bytes);
+        if constexpr (HAS_PRE) tma_load_4d(sS + (size_t)b * EPI_BLK64_BYTES, &em.m[1], &pre_bar[b], p.pre_coff + col, x0, y0, n);
+        if constexpr (NRES >= 1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[2], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+        if constexpr (NRES >= 2) tma_load_4d(sR2 + (size_t)b * EPI_BLK64_BYTES, &em.m[3], &pre_bar[b], p.res2_coff + col, x0, y0, n);
+      };
+      if constexpr (HAS_LOADS)
+        for (uint32_t k = 0; k < nblk && k < total; k++) issue_loads(k);
+      for (uint32_t k = 0; k < total; k++) {
+        const uint32_t b = k % nblk;
+        int x0, y0, n;
+        const bool live = tile_of((long)(k / nb), x0, y0, n);
+        mbar_wait(&sfull_bar[b], (k / nblk) & 1);
+        if (live) {
+          tma_store_4d(&em.m[0], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + (int)(k % nb) * 64, x0, y0, n);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+        if constexpr (HAS_LOADS) {
+          if (k + nblk < total) issue_loads(k + nblk);
+        } else {
           mbar_arrive(&sfree_bar[b]);
         }
       }
@@ -209,7 +238,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const int act = p.act;
     const float slope = p.slope, alpha = p.alpha;
     const bool scale = alpha != 1.f;
-    const uint32_t sS_u = smem_u32(sS), sBias_u = smem_u32(sBias);
+    const uint32_t sS_u = smem_u32(sS), sR1_u = smem_u32(sR1), sR2_u = smem_u32(sR2), sBias_u = smem_u32(sBias);
     const bool has_bias = a.bias != nullptr;
     uint32_t k = 0;
     for (long it = 0; it < niter; it++) {
@@ -219,8 +248,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.acc_stride);
       for (int i = 0; i < a.nb64; i++, k++) {
         const int b = (int)(k % (uint32_t)a.nblk);
-        if (k >= (uint32_t)a.nblk) mbar_wait(&sfree_bar[b], ((k / (uint32_t)a.nblk) & 1) ^ 1);
+        if constexpr (HAS_LOADS) {
+          mbar_wait(&pre_bar[b], (k / (uint32_t)a.nblk) & 1);                 // pre / residual blocks of this block landed
+        } else {
+          if (k >= (uint32_t)a.nblk) mbar_wait(&sfree_bar[b], ((k / (uint32_t)a.nblk) & 1) ^ 1);
+        }
         const uint32_t bS = sS_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
+        const uint32_t bR1 = sR1_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
+        const uint32_t bR2 = sR2_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
         uint32_t ra[16], rb[16];
         const int c0 = i * 64 + wg * 16, c1 = c0 + 32;        // this warp's two 16-column groups of the block
         tmem_ld16(t_addr + c0, ra);
@@ -249,6 +284,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
               v[4 * j4 + 3] += b4.w;
             }
           }
+          const int ch = (cg & 63) >> 3;                      // 16-byte chunk index inside the 128 B row
+          const uint32_t o0 = (uint32_t)(((ch) ^ sw128) << 4), o1 = (uint32_t)(((ch + 1) ^ sw128) << 4);
+          if constexpr (HAS_PRE) {
+            fma_bf16x8(v, lds128(bS + o0), 1.f);
+            fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
+          }
           if (do_act) {
             if (act == DASR_ACT_LRELU) {
 #pragma unroll
@@ -262,13 +303,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
+          if constexpr (NRES >= 1) {
+            fma_bf16x8(v, lds128(bR1 + o0), p.beta1);
+            fma_bf16x8(v + 8, lds128(bR1 + o1), p.beta1);
+          }
+          if constexpr (NRES >= 2) {
+            fma_bf16x8(v, lds128(bR2 + o0), p.beta2);
+            fma_bf16x8(v + 8, lds128(bR2 + o1), p.beta2);
+          }
           uint4 o[2];
           __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
           for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          const int ch = (cg & 63) >> 3;                      // 16-byte chunk index inside the 128 B row
-          sts128(bS + (((ch) ^ sw128) << 4), o[0]);
-          sts128(bS + (((ch + 1) ^ sw128) << 4), o[1]);
+          sts128(bS + o0, o[0]);
+          sts128(bS + o1, o[1]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -337,33 +385,64 @@ using namespace dasr;
 
 extern "C" {
 
-int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
-  // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 output in 64-channel blocks, no pre / residual tiles
-  if (!p) return 0;
-  if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
-  if (p->cout % 64 != 0 || p->cout < 64 || p->cout > 256 || p->cin % CHUNK != 0 || p->tile_rev) return 0;
+static int tc2_plan(const DasrConvTcParams* p, int has_pre, int nres, int* stages_out, int* nblk_out) {
   const int nchunks = p->cin / CHUNK;
-  const size_t w_bytes = (size_t)9 * nchunks * (p->cout / 2) * ROW_B;
-  const size_t need = w_bytes + 2 * 12288 + 3 * (size_t)EPI_BLK64_BYTES + 1024 + 2048;
-  return need <= (size_t)SMEM_LIMIT ? 1 : 0;
+  const long w_bytes = (long)9 * nchunks * (p->cout / 2) * ROW_B;
+  const int a_stage = (A_HALO_BYTES + 1023) / 1024 * 1024;
+  const int bar_bytes = 40 * 8 + 256 * 4 + 64;
+  const int per_blk = (1 + nres) * EPI_BLK64_BYTES;
+  (void)has_pre;
+  for (int nblk = TC2_MAX_BLOCKS; nblk >= 2; nblk--) {
+    const long avail = (long)SMEM_LIMIT - 1024 - w_bytes - (long)nblk * per_blk - bar_bytes;
+    int stages = (int)(avail / a_stage);
+    if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
+    // prefer >= 3 A stages; accept 2 only at the smallest ring
+    if (stages >= 3 || (nblk == 2 && stages >= 2)) {
+      *stages_out = stages;
+      *nblk_out = nblk;
+      return 1;
+    }
+  }
+  return 0;
 }
 
-int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, const DasrConvTcParams* p, void* stream) {
+int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
+  // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 epilogue in 64-channel blocks (this query assumes the
+  // worst case of a pre addend and two residual tensors)
+  if (!p) return 0;
+  if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
+  if (p->cout % 64 != 0 || p->cout < 64 || p->cout > 256 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
+  int st, nb;
+  return tc2_plan(p, 1, 2, &st, &nb);
+}
+
+int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
+                  void* out, const DasrConvTcParams* p, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc2: null argument");
-  DASR_REQUIRE(dasr_conv_tc2_supported(p), "conv_tc2: unsupported configuration (3x3, staged epilogue, cout %% 64 == 0, filters must fit)");
+  DASR_REQUIRE(p->nvar == 1 && p->ntaps == 9 && p->out_mul == 1 && p->epi_mode == 0 && p->a_mode == 0 && !p->tile_rev,
+               "conv_tc2: plain 3x3 geometry with the staged epilogue only");
+  DASR_REQUIRE(p->cout % 64 == 0 && p->cout >= 64 && p->cout <= 256, "conv_tc2: cout must be a multiple of 64 in [64, 256] (got %d)", p->cout);
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc2: bad dims");
+  DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc2: cin must be a multiple of 32 (got %d)", p->cin);
   if (p->nchunk_list > 0) {
     DASR_REQUIRE(p->nchunk_list <= 8 && p->nchunk_list * CHUNK == p->cin, "conv_tc2: chunk list must cover cin");
+    for (int i = 0; i < p->nchunk_list; i++)
+      DASR_REQUIRE(p->chunk_off[i] >= 0 && p->chunk_off[i] % 8 == 0 && p->chunk_off[i] + CHUNK <= p->in_cs, "conv_tc2: chunk_off[%d]", i);
   } else {
     DASR_REQUIRE(p->in_cs % 8 == 0 && p->in_coff % 8 == 0 && p->in_coff + p->cin <= p->in_cs, "conv_tc2: input slice");
   }
   DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc2: output slice");
   DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc2: act_cols must be a multiple of 16");
+  DASR_REQUIRE(!(res2 && !res1), "conv_tc2: res2 without res1");
+  if (pre) DASR_REQUIRE(p->pre_cs % 8 == 0 && p->pre_coff % 8 == 0 && p->pre_coff + p->cout <= p->pre_cs, "conv_tc2: pre slice");
+  if (res1) DASR_REQUIRE(p->res1_cs % 8 == 0 && p->res1_coff % 8 == 0 && p->res1_coff + p->cout <= p->res1_cs, "conv_tc2: res1 slice");
+  if (res2) DASR_REQUIRE(p->res2_cs % 8 == 0 && p->res2_coff % 8 == 0 && p->res2_coff + p->cout <= p->res2_cs, "conv_tc2: res2 slice");
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("conv_tc2: cuTensorMapEncodeTiled not available");
     return DASR_E_NODRIVER;
   }
+  const int has_pre = pre ? 1 : 0, nres = (res1 ? 1 : 0) + (res2 ? 1 : 0);
   Tc2Args a;
   a.p = *p;
   a.bias = bias;
@@ -376,24 +455,19 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, c
   a.a_stage_bytes = (A_HALO_BYTES + 1023) / 1024 * 1024;
   a.nb64 = p->cout / 64;
   a.acc_stride = 256;
-  const int bar_bytes = 32 * 8 + 256 * 4 + 64;
-  int nblk = TC2_MAX_BLOCKS, stages = 0;
-  for (;; nblk--) {
-    const long avail = (long)SMEM_LIMIT - 1024 - a.w_bytes - (long)nblk * EPI_BLK64_BYTES - bar_bytes;
-    stages = (int)(avail / a.a_stage_bytes);
-    if (stages >= 4 || nblk == 3) break;
-  }
-  if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
-  if (stages < 2) {
-    set_error("conv_tc2: filters (%d B per CTA) leave no room for 2 A stages", a.w_bytes);
+  const int bar_bytes = 40 * 8 + 256 * 4 + 64;
+  int stages = 0, nblk = 0;
+  if (!tc2_plan(p, has_pre, nres, &stages, &nblk)) {
+    set_error("conv_tc2: filters (%d B per CTA) + %d epilogue block arrays do not fit shared memory", a.w_bytes, 1 + nres);
     return DASR_E_SMEM;
   }
   a.stages = stages;
   a.nblk = nblk;
-  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + (size_t)nblk * EPI_BLK64_BYTES + bar_bytes;
+  size_t smem = 1024 + (size_t)a.w_bytes + (size_t)stages * a.a_stage_bytes + (size_t)nblk * (1 + nres) * EPI_BLK64_BYTES + bar_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM (the pair allocates all 512 TMEM columns)
 
-  CUtensorMap tm_in, tm_w, tm_out;
+  CUtensorMap tm_in, tm_w;
+  Tc2Maps em;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2, (cuuint64_t)p->H * p->W * p->in_cs * 2};
@@ -417,19 +491,30 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, c
     if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(filter) failed: %d", (int)r); return DASR_E_LAUNCH; }
   }
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)p->out_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-    cuuint64_t gstr[3] = {(cuuint64_t)p->out_cs * 2, (cuuint64_t)p->W * p->out_cs * 2, (cuuint64_t)p->H * p->W * p->out_cs * 2};
-    cuuint32_t box[4] = {64, TILE_W, TILE_H, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(output) failed: %d", (int)r); return DASR_E_LAUNCH; }
+    const void* bases[4] = {out, pre, res1, res2};
+    const int css[4] = {p->out_cs, p->pre_cs, p->res1_cs, p->res2_cs};
+    const char* names[4] = {"output", "pre", "res1", "res2"};
+    for (int t = 0; t < 4; t++) {
+      if (!bases[t]) { em.m[t] = tm_in; continue; }
+      cuuint64_t gdim[4] = {(cuuint64_t)css[t], (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+      cuuint64_t gstr[3] = {(cuuint64_t)css[t] * 2, (cuuint64_t)p->W * css[t] * 2, (cuuint64_t)p->H * p->W * css[t] * 2};
+      cuuint32_t box[4] = {64, TILE_W, TILE_H, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&em.m[t], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[t]), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(%s) failed: %d", names[t], (int)r); return DASR_E_LAUNCH; }
+    }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Tc2Maps, const Tc2Args);
+  static const KernelFn kernels[6] = {conv_tc2_kernel<false, 0>, conv_tc2_kernel<false, 1>, conv_tc2_kernel<false, 2>,
+                                      conv_tc2_kernel<true, 0>,  conv_tc2_kernel<true, 1>,  conv_tc2_kernel<true, 2>};
+  const int ki = has_pre * 3 + nres;
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  if (!attr_set[ki]) {
+    cudaError_t e = cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) { set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DASR_E_LAUNCH; }
-    attr_set = true;
+    attr_set[ki] = true;
   }
   long npairs = (a.ntiles + 1) / 2;
   int gx = num_sms() & ~1;
@@ -444,7 +529,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, void* out, c
   attrs[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, tm_in, tm_w, tm_out, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[ki], tm_in, tm_w, em, a);
   if (e != cudaSuccess) {
     set_error("conv_tc2: launch failed: %s", cudaGetErrorString(e));
     return DASR_E_LAUNCH;

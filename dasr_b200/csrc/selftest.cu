@@ -200,9 +200,9 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   for (auto& v : res1) v = rnd_q(8, 8.f);
   for (auto& v : msk) v = rnd_q(8, 8.f);
   const float slope = 0.25f, alpha = 0.5f, mslope = 0.25f;
-  const float beta1 = (epi == 2 && gn > 96) ? 0.f : 2.f;   // wide fused launches only carry the in-place pre addend
+  const float beta1 = ((epi == 2 || epi == 5) && gn > 96) ? 0.f : 2.f;   // wide fused launches only carry the in-place pre addend
   const int mc0 = gn >= 32 ? gn - 24 : 0, mc1 = gn;
-  const int act_cols = (epi == 2 || epi == 4) ? 16 * ((gn / 16 + 1) / 2) : gn;
+  const int act_cols = (epi == 2 || epi == 4 || epi == 5) ? 16 * ((gn / 16 + 1) / 2) : gn;
   const float beta2 = (gn > 96) ? 0.f : -0.5f;   // three staged tiles of a wide launch do not fit shared memory
   if (epi == 1)
     for (size_t i = 0; i < ref.size(); i++) {
@@ -213,7 +213,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
       if (c >= mc0 && c < mc1 && !(msk[i] > 0.f)) v *= mslope;
       ref[i] = v;
     }
-  if (epi == 2)
+  if (epi == 2 || epi == 5)
     for (size_t i = 0; i < ref.size(); i++) {
       int c = (int)(i % gn);
       double v = ref[i] + msk[i];                 // msk doubles as the pre-activation addend
@@ -244,7 +244,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   int rc = dasr_conv_tc_setup(&p, kind);
   p.N = N; p.H = H; p.W = W; p.cin = gk; p.in_cs = in_cs; p.in_coff = in_coff;
   p.cout = gn; p.out_cs = out_cs; p.out_coff = out_coff; p.nt = nt;
-  p.act = (epi == 1 || epi == 2 || epi == 4) ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = (epi == 1 || epi == 2 || epi == 4) ? alpha : 1.f;
+  p.act = (epi == 1 || epi == 2 || epi >= 4) ? DASR_ACT_LRELU : DASR_ACT_NONE; p.slope = slope; p.alpha = (epi == 1 || epi == 2 || epi >= 4) ? alpha : 1.f;
   p.act_cols = act_cols;
   p.beta1 = beta1; p.res1_cs = gn; p.res1_coff = 0;
   p.beta2 = beta2; p.res2_cs = gn; p.res2_coff = 0;
@@ -257,14 +257,16 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
   // res2 for epi 2 = res1 shifted by one pixel (same buffer, pointer offset of gn elements, wraps at the end -> use a copy)
   __nv_bfloat16* dres2 = nullptr;
-  if (epi == 2 && gn <= 96) {
+  if ((epi == 2 || epi == 5) && gn <= 96) {
     std::vector<__nv_bfloat16> r2(res_b.size());
     for (size_t i = 0; i < r2.size(); i++) r2[i] = res_b[(i + gn) % r2.size()];
     dres2 = dalloc<__nv_bfloat16>(r2.size());
     h2d(dres2, r2);
   }
   if (epi == 4)
-    rc |= dasr_conv_tc2(din, dwp, db, dout, &p, 0);
+    rc |= dasr_conv_tc2(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
+  else if (epi == 5)      // CTA-pair kernel with the full staged-epilogue contract of epi 2
+    rc |= dasr_conv_tc2(din, dwp, db, dmsk, gn <= 96 ? dres : nullptr, dres2, dout, &p, 0);
   else
     rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
                        epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
@@ -427,7 +429,7 @@ static void bench_tc_fused(int N, int H, int W, int cin, int cout, int nt, int w
   void* pre = with_pre ? (void*)obuf : nullptr;
   int rc = 0;
   auto run = [&]() {
-    return pair ? dasr_conv_tc2(buf, dwp, nullptr, obuf, &p, 0)
+    return pair ? dasr_conv_tc2(buf, dwp, nullptr, pre, nullptr, nullptr, obuf, &p, 0)
                 : dasr_conv_tc(buf, dwp, nullptr, pre, nullptr, nullptr, nullptr, obuf, &p, 0);
   };
   for (int i = 0; i < 3; i++) rc |= run();
@@ -542,6 +544,12 @@ int main(int argc, char** argv) {
       bench_tc_fused(16, 256, 256, 64, 192, 192, 0, 10, 0, 0, 1);
       bench_tc_fused(16, 256, 256, 64, 192, 192, 0, 10, 64, 192, 1);
       bench_tc_fused(16, 256, 256, 32, 128, 128, 0, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 32, 64, 64, 0, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 64, 64, 64, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 96, 64, 64, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 96, 128, 128, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 64, 128, 128, 1, 10, 0, 0, 1);
       return 0;
     }
     if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes
@@ -592,6 +600,11 @@ int main(int argc, char** argv) {
         test_tc(4, 96, 64, 64, 192, 192, 0, 0, 4);     // 192 tiles: pairs take a second iteration, ring wrap-around
         test_tc(1, 24, 16, 32, 128, 128, 0, 0, 4);     // one chunk, two 64-channel blocks
         test_tc(1, 16, 16, 192, 64, 192, 1, 0, 4);     // dgrad conv5-like: K=64 -> N=192
+        test_tc(1, 20, 13, 96, 64, 64, 0, 0, 5);       // pair kernel, staged epilogue with pre + res1 + res2, ragged, 3 chunks
+        test_tc(3, 48, 40, 64, 64, 64, 0, 0, 5);       // several iterations per pair (ring wrap with loads)
+        test_tc(2, 40, 24, 32, 128, 128, 0, 0, 5);     // pre only, two blocks per tile
+        test_tc(1, 32, 24, 64, 192, 192, 0, 0, 5);     // pre only, three blocks per tile
+        test_tc(4, 96, 64, 32, 64, 64, 0, 0, 5);       // 192 tiles, pre + two residuals
       }
       test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
       test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);

@@ -313,23 +313,46 @@ def _fused_rdb_filters(cache, params, L, r, nf):
     return out
 
 
-# Dense-block schedule 2 (inference): which (conv k, input chunk) products each of the five launches computes.
-# Launch j still completes conv j, but the later convs no longer take ALL their partial sums along from launch 1 on:
-#   1: x        -> x1 | p2 p3 p4 p5      2: x1 -> x2 | p3        3: x2 -> x3 | p4
-#   4: x1, x3   -> x4 | p5               5: x2, x4 -> out
-# Launches 2-5 of the column-strip schedule re-read and re-write 160/128/96/64 partial-sum channels per pixel and are HBM
-# bound (profiles/r1_summary.md); this assignment moves 1.9 KB instead of 2.7 KB per pixel and block at +23 % MMA cycles.
+# Dense-block schedules (inference): which (conv k, input chunk) products each of the five launches computes.  Launch j
+# always completes conv j (bias + LeakyReLU on its GC columns); the other columns of a launch extend partial sums of later
+# convs IN PLACE in the channel slots their activations will occupy (conv5: the extra 64-channel slot).  Launch 1 touches
+# every conv, so all later launches read their partial sums through the `pre` addend.
+#   SCHED2 (round 1):  1: x -> x1 | p2 p3 p4 p5   2: x1 -> x2 | p3   3: x2 -> x3 | p4   4: x1,x3 -> x4 | p5   5: x2,x4 -> out
+#                      34 x 64 B per pixel of DRAM traffic, 9 chunk-passes of MMAs
+#   SCHED3 (round 2):  1: x -> x1 | p2 p3 p4 p5   2: x1 -> x2        3: x1,x2 -> x3 | p4   4: x3 -> x4      5: x1..x4 -> out
+#                      30 x 64 B per pixel, 11 chunk-passes.  The launches are HBM-bound once they run on CTA pairs
+#                      (64 cycles per MMA K-step instead of 84: tools/sched_search.py, profiles/r2_summary.md), so trading
+#                      partial-sum bytes for MMA passes pays: every partial sum is now written once and read once.
 SCHED2 = ((('x',), (1, 2, 3, 4, 5)), ((1,), (2, 3)), ((2,), (3, 4)), ((1, 3), (4, 5)), ((2, 4), (5,)))
+SCHED3 = ((('x',), (1, 2, 3, 4, 5)), ((1,), (2,)), ((1, 2), (3, 4)), ((3,), (4,)), ((1, 2, 3, 4), (5,)))
+SCHEDULES = {'2': SCHED2, '3': SCHED3}
+
+
+def check_schedule(sched):
+    """Every (conv k, chunk c < k) product exactly once, launch j starts at conv j with contiguous convs, only reads
+    activations that exist, and launch 1 initialises every partial sum."""
+    seen = set()
+    for j, (chunks, ks) in enumerate(sched, start=1):
+        assert ks[0] == j and list(ks) == list(range(ks[0], ks[-1] + 1)), (j, ks)
+        for c in chunks:
+            ci = 0 if c == 'x' else c
+            assert ci <= j - 1, (j, c)
+            for k in ks:
+                assert ci < k and (k, ci) not in seen, (k, ci)
+                seen.add((k, ci))
+    assert seen == {(k, c) for k in range(1, 6) for c in range(0, k)}, 'schedule does not cover the dense block'
+    assert tuple(sched[0][1]) == (1, 2, 3, 4, 5), 'launch 1 must touch every conv (later launches read `pre`)'
+    return True
 
 
 def _sched2_chunk_offsets(nf, chunk):
     return [0, 32] if chunk == 'x' else [nf + (chunk - 1) * GC]
 
 
-def _sched2_rdb_filters(cache, params, L, r, nf):
-    """[(packed filters, bias, chunk channel offsets)] of the five launches of SCHED2 for dense block r."""
+def _sched_rdb_filters(cache, params, L, r, nf, sched, tag):
+    """[(packed filters, bias, chunk channel offsets)] of the five launches of schedule `sched` for dense block r."""
     out = []
-    for j, (chunks, ks) in enumerate(SCHED2, start=1):
+    for j, (chunks, ks) in enumerate(sched, start=1):
         offs = [o for c in chunks for o in _sched2_chunk_offsets(nf, c)]
         wj = params[2 * L.rdb_conv(r, j)]
 
@@ -345,8 +368,12 @@ def _sched2_rdb_filters(cache, params, L, r, nf):
             b[:bj.shape[0]] = bj
             return b
         wsrc = [params[2 * L.rdb_conv(r, k)] for k in ks]
-        out.append((cache.get(('s2w', r, j), wsrc, make_w), cache.get(('s2b', r, j), params[2 * L.rdb_conv(r, j) + 1], make_b), offs))
+        out.append((cache.get((tag + 'w', r, j), wsrc, make_w), cache.get((tag + 'b', r, j), params[2 * L.rdb_conv(r, j) + 1], make_b), offs))
     return out
+
+
+def _sched2_rdb_filters(cache, params, L, r, nf):
+    return _sched_rdb_filters(cache, params, L, r, nf, SCHED2, 's2')
 
 
 class _BatchPacker:
@@ -433,7 +460,8 @@ class _BatchPacker:
                   'pack_filter_tc_batch')
 
 
-PAIR_STAGE1 = os.environ.get('DASR_B200_PAIR', '1') != '0'    # dense-block launch 1 on the CTA-pair kernel (conv_tc2)
+PAIR_MODE = os.environ.get('DASR_B200_PAIR', '1') != '0'      # run eligible launches on the CTA-pair kernel (conv_tc2)
+PAIR_STAGE1 = PAIR_MODE
 
 
 def _rdb_stage1(b, w, bias, out, nf):
@@ -453,7 +481,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
                  and produces conv j's output plus partial sums of later convs of the block (a tcgen05.mma of
                  N <= 128 costs the same ~84 cycles as N = 32).  Partial sums live IN PLACE in the channel slots the
                  finished activations will occupy (bf16), so the only extra state is a 64-channel slot for conv5.
-                 DASR_B200_SCHED=2 (default): engine.SCHED2 assignment; =1: every launch carries all later partial sums.
+                 DASR_B200_SCHED=3 (default) / 2: engine.SCHED3 / SCHED2; =1: every launch carries all later partial sums.
     fused=False: one launch per conv over the growing concat (the straightforward restatement).
     """
     _need_cuda(x, 'RRDBNet')
@@ -466,7 +494,8 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
     bf = torch.bfloat16
     CS = nf + 4 * GC
     BW = CS + (nf if fused else 0)        # fused: extra slot for conv5's partial sums
-    sched2 = fused and nf == 64 and GC == 32 and os.environ.get('DASR_B200_SCHED', '2') == '2'
+    sched_id = os.environ.get('DASR_B200_SCHED', '3')
+    sched = SCHEDULES.get(sched_id) if (fused and nf == 64 and GC == 32) else None
     Wt = lambda i: params[2 * i]
 
     def wk(i, kind=TC_FPROP, cout_to=None, cin_to=None):
@@ -493,16 +522,19 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
             tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
         else:
             tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
-        if sched2:
-            fw = _sched2_rdb_filters(cache, params, L, r, nf)
+        if sched is not None:
+            fw = _sched_rdb_filters(cache, params, L, r, nf, sched, 's' + sched_id)
             _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
-            o = View(b, 2 * GC, nf + GC)                               # x2 | p3
-            ops.conv_tc(b, fw[1][0], fw[1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[1][2])
-            o = View(b, 2 * GC, nf + 2 * GC)                           # x3 | p4
-            ops.conv_tc(b, fw[2][0], fw[2][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[2][2])
-            o = View(b, GC + nf, nf + 3 * GC)                          # x4 | p5
-            ops.conv_tc(b, fw[3][0], fw[3][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o, chunks=fw[3][2])
-            ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], **tail)
+            for j in (2, 3, 4, 5):
+                ks = sched[j - 1][1]
+                width = sum(nf if k == 5 else GC for k in ks)
+                pair = PAIR_MODE and width % 64 == 0          # 64-channel epilogue blocks; other widths stay on one CTA
+                if j < 5:
+                    o = View(b, width, nf + (j - 1) * GC)                  # slots of conv j .. conv ks[-1], partial sums in place
+                    ops.conv_tc(b, fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o,
+                                chunks=fw[j - 1][2], pair=pair)
+                else:
+                    ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], pair=pair, **tail)
         elif fused:
             fw = _fused_rdb_filters(cache, params, L, r, nf)
             # launch 1: x -> x1 (complete) | partial conv2..5
@@ -510,15 +542,16 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
             for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
                 o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
                 ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
-                            act_cols=GC, pre=o)
-            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+                            act_cols=GC, pre=o, pair=PAIR_MODE and o.c % 64 == 0)
+            ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), pair=PAIR_MODE and nf % 64 == 0, **tail)
         else:
             for k in range(1, 5):
                 ci = L.rdb_conv(r, k)
                 ops.conv_tc(View(b, _rdb_cin(nf, k), 0), wk(ci), bk(ci), View(b, GC, nf + (k - 1) * GC), act=ACT_LRELU, slope=0.2)
             ci = L.rdb_conv(r, 5)
             ops.conv_tc(View(b, CS, 0), wk(ci), bk(ci), dst, nt=_pick_nt(nf, CS), **tail)
-    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
+    ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0,
+                pair=PAIR_MODE and nf % 64 == 0)
     del rot, bufs
     cur, h, w = lr, H, W
     for u in range(L.n_up):
@@ -529,7 +562,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
                     act=ACT_LRELU, slope=0.2)
         cur = nxt
     h0 = _empty((N, h, w, nf), x, bf)
-    ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2)
+    ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2, pair=PAIR_MODE and nf % 64 == 0)
     del cur
     out_nc = Wt(L.i_hr1).shape[0]
     out = _empty((N, out_nc, h, w), x)
@@ -579,8 +612,9 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
         _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
         for j in (2, 3, 4):
             o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
-            ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o)
-        ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), **tail)
+            ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o,
+                        pair=PAIR_MODE and o.c % 64 == 0)
+        ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), pair=PAIR_MODE and nf % 64 == 0, **tail)
     lr = _empty((N, H, W, nf), x, bf)
     ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)
     ups = [lr]

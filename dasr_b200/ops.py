@@ -196,8 +196,8 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     """tcgen05 3x3 conv on NHWC bf16 channel slices; chunks = optional list of 32-channel chunk offsets of `inp`'s buffer; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
     v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
     nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer).
-    pair: True = run on the CTA-pair kernel (dasr_conv_tc2: cta_group::2, filters split over two SMs; `nt` is ignored),
-          None = use it when the launch has no pre / residual tiles and its filter set does not fit one SM as one Cout tile."""
+    pair: True = run on the CTA-pair kernel (dasr_conv_tc2: cta_group::2, filters split over two SMs, 64-cycle MMAs;
+          plain 3x3 geometry, cout % 64 == 0, no mask; `nt` is ignored)."""
     inp = as_view(inp)
     N, H, W, _ = inp.t.shape
     if nchw_out is not None:
@@ -234,13 +234,12 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     if pair is None:
         pair = False
     if pair:
-        if pre is not None or res1 is not None or res2 is not None or mask is not None:
-            raise _lib.DasrError('conv_tc: the CTA-pair kernel has no pre / residual / mask inputs')
+        if mask is not None:
+            raise _lib.DasrError('conv_tc: the CTA-pair kernel has no mask input')
         p.nt = p.cout
         p.epi_mode = 0
-        if not lib.dasr_conv_tc2_supported(C.byref(p)):
-            raise _lib.DasrError('conv_tc: launch not supported by the CTA-pair kernel (cin=%d cout=%d)' % (p.cin, p.cout))
-        check(lib.dasr_conv_tc2(inp.ptr, _p(w_packed), _p(bias), out.ptr, C.byref(p), _stream()), 'conv_tc2')
+        check(lib.dasr_conv_tc2(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
+                                res2.ptr if res2 else None, out.ptr, C.byref(p), _stream()), 'conv_tc2')
         return
     check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
                            res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')

@@ -154,11 +154,13 @@ int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bi
 
 /* The same convolution on a CTA PAIR (tcgen05 cta_group::2, csrc/conv_tc2.cu): the two SMs of a TPC each keep half of
  * the filter rows resident and each load the A tile of their own pixel tile; one M=256 instruction feeds both tensor
- * cores.  For launches whose full filter set does not fit one SM (dense-block launch 1: K = 64, N = 192).
- * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 64 == 0, no pre / residual tiles. */
+ * cores (measured: 64 cycles per K step and pixel tile for N <= 128, N/2 above, against 84 / N/2+5 on one CTA), and a
+ * filter set twice as large fits (dense-block launch 1: K = 64, N = 192).
+ * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 64 == 0; pre / res1 / res2 as in
+ * dasr_conv_tc (nullable).  `nt` is ignored (one Cout tile = cout). */
 int dasr_conv_tc2_supported(const DasrConvTcParams* p);
-int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* bias, void* out_bf16,
-                  const DasrConvTcParams* p, void* stream);
+int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
+                  const void* res1_bf16, const void* res2_bf16, void* out_bf16, const DasrConvTcParams* p, void* stream);
 
 /* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
  *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)

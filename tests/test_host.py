@@ -292,20 +292,16 @@ def test_bench_cpu_leg_and_generators_run():
     assert torch.equal(bench.synth((2, 3, 5), 9, 0.5, 0.5), O.synth((2, 3, 5), 9, 0.5, 0.5))
 
 
-def test_dense_block_schedule2_covers_every_product_once():
-    """engine.SCHED2: every (conv k, input chunk c < k) product of the dense block is computed by exactly one launch,
-    launch j completes conv j (first of its column set) and only reads activations that already exist."""
+def test_dense_block_schedules_cover_every_product_once():
+    """engine.SCHED2 / SCHED3: every (conv k, input chunk c < k) product of the dense block is computed by exactly one
+    launch, launch j completes conv j (first of its contiguous column set), only reads activations that already exist and
+    launch 1 initialises every partial sum."""
     from dasr_b200 import engine
-    seen = {}
-    for j, (chunks, ks) in enumerate(engine.SCHED2, start=1):
-        assert ks[0] == j and list(ks) == list(range(ks[0], ks[-1] + 1))         # contiguous output columns
-        for c in chunks:
-            ci = 0 if c == 'x' else c
-            assert ci <= j - 1, (j, c)                                             # x_c exists before launch j
-            for k in ks:
-                assert ci < k
-                assert (k, ci) not in seen, (k, ci)
-                seen[(k, ci)] = j
-    assert set(seen) == {(k, c) for k in range(1, 6) for c in range(0, k)}
+    for sched in engine.SCHEDULES.values():
+        assert engine.check_schedule(sched)
+    bad = ((('x',), (1, 2, 3, 4, 5)), ((1,), (2,)), ((2,), (3, 4)), ((3,), (4,)), ((1, 2, 3, 4), (5,)))     # (3, x1) missing
+    import pytest
+    with pytest.raises(AssertionError):
+        engine.check_schedule(bad)
     # channel offsets of the chunks inside the [x | x1..x4 | p5] buffer
     assert engine._sched2_chunk_offsets(64, 'x') == [0, 32] and engine._sched2_chunk_offsets(64, 3) == [128]
