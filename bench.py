@@ -121,24 +121,10 @@ def synth_weights(net, seed=1, gain=0.1):
 
 
 def pick_threads():
-    """torch CPU convs on this path stop scaling (and regress badly) when oversubscribed on a shared many-core
-    host: time a small probe at a few thread counts and keep the fastest."""
-    import torch
-    from oracle import srn_oracle as O
-    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=1), 1, 0.1)
-    x = O.synth_image((1, 3, 96, 96), 3)
-    ncpu = os.cpu_count() or 1
-    best, best_t = 1, 1e30
-    for t in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
-        torch.set_num_threads(t)
-        with torch.no_grad():
-            O.rrdbnet_forward(x, sd, 1)
-            t0 = time.perf_counter()
-            O.rrdbnet_forward(x, sd, 1)
-            dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = t, dt
-    return best
+    """Fixed policy for the CPU arms: min(32, host CPUs) intra-op threads.  (torch's oneDNN convs on this path stop
+    scaling around 16-32 threads and regress when oversubscribed on a shared many-core host; round 1 probed per run and
+    landed on 16 / 32 / 64 from run to run, which made the baseline jumpy.)"""
+    return max(1, min(32, os.cpu_count() or 1))
 
 
 def cpu_reference_forward(n_images, lr, threads, steps, warmup):
@@ -158,20 +144,57 @@ def cpu_reference_forward(n_images, lr, threads, steps, warmup):
     return out_mp(n_images, lr) / dt, dt
 
 
+def cpu_reference_train_step(threads, B=8):
+    """configs[2] on CPU: the oracle's DASR train step (G + patch-D + VGG19 perceptual + weighted L1, both Adam steps) on a
+    bounded sample of B of the 32 crops per half-batch; returns (it/s scaled to batch 32, seconds of the sample)."""
+    import torch
+    from oracle import srn_oracle as O
+    torch.set_num_threads(threads)
+    sdG = O.synth_state_dict(O.rrdbnet_shapes(nb=NB), 1, 0.1)
+    sdD = O.synth_state_dict(O.nlayer_d_shapes(9, 64, 2), 2, 1.0)
+    sdF = O.synth_state_dict(O.vgg19_shapes(34), 3, 1.0)
+    h = 32
+    data = {'LR_real': O.synth_image((B, 3, h, h), 200), 'LR_fake': O.synth_image((B, 3, h, h), 300),
+            'HR': O.synth_image((B, 3, 4 * h, 4 * h), 400), 'HR_unpair': O.synth_image((B, 3, 4 * h, 4 * h), 500),
+            'fake_w': O.synth_image((B, 1, h, h), 600)}
+    t0 = time.perf_counter()
+    O.dasr_train_step(sdG, sdD, sdF, data, NB)
+    dt = time.perf_counter() - t0
+    return (B / 32.0) / dt, dt
+
+
+def cpu_reference_dsn_step(threads, B=4):
+    """configs[4] on CPU: the oracle's DSN iteration on B of the 8 crops; returns (it/s scaled to batch 8, seconds)."""
+    import torch
+    from oracle import dsn_oracle as D
+    from oracle import srn_oracle as O
+    torch.set_num_threads(threads)
+    sdG = D.synth_de_resnet(8, 4, 7, 0.7)
+    sdD = O.synth_state_dict(D.fsd_shapes(9), 8, 1.0)
+    sdV = O.synth_state_dict(D.vgg16_shapes(), 9, 1.0)
+    inp, bic, dis = O.synth_image((B, 3, 256, 256), 700), O.synth_image((B, 3, 64, 64), 800), O.synth_image((B, 3, 64, 64), 900)
+    t0 = time.perf_counter()
+    D.dsn_train_step(sdG, sdD, sdV, inp, bic, dis)
+    dt = time.perf_counter() - t0
+    return (B / 8.0) / dt, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = pick_threads()
-    steps, warm = max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0
-    mp_s, dt = cpu_reference_forward(1, LR, threads, steps, warm)
+    steps, warm = max(1, min(args.steps, 2)), 1 if args.warmup > 0 else 0
+    nimg = 4
+    mp_s, dt = cpu_reference_forward(nimg, LR, threads, steps, warm)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': mp_s, 'unit': 'MP/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'RRDBNet-23 x4 inference, batch 16 x 3x256x256 per GPU (configs[1]); CPU arm: one step = a '
-                               'bounded sample of 1 of the 16 images', 'inputs': 'host memory'},
+                               'bounded sample of 4 of the 16 images', 'inputs': 'host memory'},
         'cpu_baseline': {'value': mp_s, 'unit': 'MP/s', 'cores': threads, 'host_cpus': os.cpu_count(), 'kind': 'port',
-                         'sample': '1 x 3x256x256 image per step (1/16 of the batch), oracle/srn_oracle.py rrdbnet_forward, torch CPU fp32'},
+                         'threads_policy': 'min(32, host CPUs)',
+                         'sample': '4 x 3x256x256 images per step (1/4 of the batch), oracle/srn_oracle.py rrdbnet_forward, torch CPU fp32'},
         'e2e': {'value': mp_s, 'unit': 'MP/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -184,7 +207,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='dasr_b200')
-    ap.add_argument('--train-steps', type=int, default=3)
+    ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -290,29 +313,64 @@ def main():
         del xin, fea, buf, big
 
         # ---------------------------------------------------------------- end-to-end through the public API
-        for _ in range(2):
-            model.feed_data({'LR': x_host})
-            model.test()
-            y_host.copy_(model.fake_H, non_blocking=True)
-        barrier()
-        e0.record()
-        for _ in range(K):
+        # Every step: H2D of the input from pinned host memory (feed_data), the forward (test()), D2H of the result into
+        # pinned host memory.  The D2H of step k runs on a copy stream and overlaps the forward of step k+1 (two host
+        # buffers); the timed region ends when the last result has landed on the host.
+        y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
+        copy_stream = torch.cuda.Stream()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def e2e_step(k):
             model.feed_data({'LR': x_host})          # H2D of the step's input from pinned host memory
             model.test()                             # netG forward (public API call of test.py)
-            y_host.copy_(model.fake_H, non_blocking=True)   # D2H of the result
+            res = model.fake_H
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                y_hosts[k & 1].copy_(res, non_blocking=True)   # D2H of the result
+                res.record_stream(copy_stream)
+                done[k & 1].record(copy_stream)
+
+        for k in range(2):
+            e2e_step(k)
+        copy_stream.synchronize()
+        barrier()
+        e0.record()
+        for k in range(K):
+            if k >= 2:
+                done[k & 1].synchronize()            # host buffer k&1 was consumed two steps ago
+            e2e_step(k)
+        torch.cuda.current_stream().wait_stream(copy_stream)
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1) / K)
     model.fake_H = None
     torch.cuda.empty_cache()
 
-    # ---------------------------------------------------------------- train step (configs[2]), fp32 kernels
+    # ---------------------------------------------------------------- train step (configs[2]) and DSN iteration (configs[4])
     train = dsn = None
+    allreduce_ms = None
     if args.train_steps > 0:
         train = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'bf16')
-        train['fp32_mode'] = bench_train(args, dev, local_rank, world, barrier, max_over_ranks, 'fp32')
+        fp32_args = argparse.Namespace(**vars(args))
+        fp32_args.train_steps = min(args.train_steps, 3)            # the fp32 parity mode takes ~0.5 s per step
+        train['fp32_mode'] = bench_train(fp32_args, dev, local_rank, world, barrier, max_over_ranks, 'fp32')
         dsn = bench_dsn(args, dev, rank, world, barrier, max_over_ranks, 'bf16')
-        dsn['fp32_mode'] = bench_dsn(args, dev, rank, world, barrier, max_over_ranks, 'fp32')
+        dsn['fp32_mode'] = bench_dsn(fp32_args, dev, rank, world, barrier, max_over_ranks, 'fp32')
+        if world > 1:
+            # the gradient exchange in isolation: NCCL all-reduce (AVG) of the 69.5 MB [G | D] bucket, CUDA events, max over ranks
+            flat = torch.zeros(17366724, dtype=torch.float32, device=dev)
+            for _ in range(3):
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            barrier()
+            a0, a1 = _rec(), None
+            for _ in range(10):
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            a1 = _rec()
+            barrier()
+            allreduce_ms = max_over_ranks(a0.elapsed_time(a1) / 10)
+            del flat
 
     if rank != 0:
         if world > 1:
@@ -321,10 +379,13 @@ def main():
     peak, peak_src = peaks()
     flops_step = FLOP_PER_LR_PIXEL * BATCH * LR * LR
     ach = flops_step / (tc_ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get('dram_bytes_per_launch_avg')
+    traffic, traffic_src = None, None
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        tp = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch_avg')
+            traffic_src = 'static: ncu launch list of this command, profiles/%s (not re-measured in this run)' % name
+            break
     line = {
         'metric': METRIC, 'value': world * out_mp(BATCH, LR) / (ms * 1e-3), 'unit': 'MP/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
@@ -332,28 +393,39 @@ def main():
         'config': {'workload': 'RRDBNet-23 x4 inference, batch 16 x 3x256x256 per GPU, forward_chop off (BASELINE configs[1])',
                    'weights': 'random init (deterministic synthetic), reference architecture nb=23 nf=64 gc=32',
                    'parallelism': 'dp%d (independent replicas, no collective on the inference path)' % world,
-                   'l2': 'working set (3 x 403 MB concat buffers + 2.1 GB HR activations) >> 126 MB L2: no flush needed'},
+                   'l2': 'working set (3 x 537 MB dense-block buffers + 2.1 GB HR activations) >> 126 MB L2: no flush needed'},
         'e2e': {'value': world * out_mp(BATCH, LR) / (e2e_ms * 1e-3), 'unit': 'MP/s', 'ms_per_step': e2e_ms,
                 'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': y_host.numel() * 4,
-                'api': 'SRModel.feed_data(pinned host LR) -> SRModel.test() -> pinned host copy of fake_H'},
+                'api': 'SRModel.feed_data(pinned host LR) -> SRModel.test() -> pinned host copy of fake_H (copy stream, double buffered)'},
         'gpu_launches': launches,
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'dasr::conv_tc_kernel (tcgen05 implicit-GEMM 3x3 conv)',
+        'roofline': {'bound': 'tensor', 'kernel': 'dasr::conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM 3x3 conv)',
                      'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'peak_source': peak_src,
-                     'traffic': traffic, 'launches_per_step': n_tc, 'avg_launch_ms': tc_ms / n_tc,
-                     'algorithmic_flops_per_step': flops_step,
-                     'non_conv_ms_per_step': non_tc_ms,
-                     'note': 'achieved = algorithmic conv FLOPs of one forward / (CUDA-event step time - CUDA-event time of the non-conv kernels of a step)'},
+                     'traffic': traffic, 'traffic_source': traffic_src, 'launches_per_step': n_tc, 'avg_launch_ms': tc_ms / n_tc,
+                     'algorithmic_flops_per_step': flops_step, 'non_conv_ms_per_step': non_tc_ms},
     }
+    detail = {'roofline_note': 'achieved = algorithmic conv FLOPs of one forward / (CUDA-event step time - CUDA-event time of the non-conv kernels of a step)'}
     if train:
-        line['train'] = train
-    if dsn:
-        line['dsn'] = dsn
+        detail['train'], detail['dsn'] = train, dsn
+        line['train'] = {'value': train['value'], 'unit': 'it/s', 'ms_per_step': train['ms_per_step'], 'steps': train['steps'],
+                         'global_batch': 32 * world, 'dtype': 'bf16 mixed', 'fp32_mode_it_s': train['fp32_mode']['value'],
+                         'allreduce_ms': allreduce_ms, 'gpu_launches_per_step': train['gpu_launches_per_step']}
+        line['dsn'] = {'value': dsn['value'], 'unit': 'it/s', 'ms_per_step': dsn['ms_per_step'], 'global_batch': 8 * world,
+                       'fp32_mode_it_s': dsn['fp32_mode']['value']}
     if not args.no_cpu_baseline and world == 1:
         threads = pick_threads()
-        mp_s, dt = cpu_reference_forward(1, LR, threads, 1, 0)
+        mp_s, dt = cpu_reference_forward(4, LR, threads, 1, 0)
         line['cpu_baseline'] = {'value': mp_s, 'unit': 'MP/s', 'cores': threads, 'kind': 'port', 'seconds': dt,
-                                'sample': '1 x 3x256x256 image (1/16 of the batch), oracle port of RRDBNet-23 forward, torch CPU fp32'}
+                                'sample': '4 x 3x256x256 images (1/4 of the batch), oracle port of RRDBNet-23 forward, torch CPU fp32, min(32, host CPUs) threads'}
+        if train:
+            it_s, dt = cpu_reference_train_step(threads)
+            line['train']['cpu_baseline'] = {'value': it_s, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'seconds': dt,
+                                             'sample': 'oracle DASR train step on 8 of the 32 crops per half batch, scaled to batch 32'}
+            it_s, dt = cpu_reference_dsn_step(threads)
+            line['dsn']['cpu_baseline'] = {'value': it_s, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'seconds': dt,
+                                           'sample': 'oracle DSN iteration on 4 of the 8 crops, scaled to batch 8'}
+    # full detail (per-mode configs, dtypes, launch counts) on stderr; stdout carries ONE compact JSON line
+    sys.stderr.write('bench detail: ' + json.dumps(detail) + '\n')
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -16,7 +16,8 @@
 // Warp roles (TC2_THREADS = 352): warp 0 TMA producer (filters once, A halo tiles) / warp 1 TMEM allocator + (leader
 // only) MMA issuer / warps 2..9 epilogue (TMEM -> registers -> +bias, +pre, activation on the first act_cols columns,
 // scale, +residuals -> bf16 block in shared memory) / warp 10 epilogue TMA (pre / residual blocks in, finished blocks out).
-// The epilogue works in 64-channel blocks (128 px x 128 B): v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2,
+// The epilogue works in 64-channel blocks (128 px x 128 B) plus one 32-channel tail block when cout % 64 == 32:
+// v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2,
 // the same contract as dasr_conv_tc's staged epilogue, so every launch of the dense-block schedules can run on a pair.
 #include <stdlib.h>
 #include "tc_common.cuh"
@@ -29,8 +30,8 @@ constexpr int TC2_THREADS = 32 * TC2_WARPS;
 constexpr int TC2_MAX_STAGES = 6;
 constexpr int TC2_MAX_BLOCKS = 6;      // staging ring entries (64-channel output blocks)
 
-struct Tc2Maps {          // TMA descriptors of the 64-channel epilogue blocks: out, pre, res1, res2
-  CUtensorMap m[4];
+struct Tc2Maps {          // TMA descriptors of the epilogue blocks: [out, pre, res1, res2] x [64-channel box, 32-channel tail box]
+  CUtensorMap m[8];
 };
 
 struct Tc2Args {
@@ -43,6 +44,7 @@ struct Tc2Args {
   int stages, a_stage_bytes, w_bytes;
   int nblk;           // staging ring entries
   int nb64;           // 64-channel blocks per tile (cout / 64)
+  int nb;             // blocks per tile: nb64 + (cout % 64 == 32 ? one 32-channel tail block : 0)
   int acc_stride;     // TMEM columns between the two accumulators
 };
 
@@ -193,18 +195,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     // blocks are numbered k = it * nb64 + i over this CTA's tiles; block k uses ring slot k % nblk
     if (lane == 0) {
       pdl_wait();                       // output slots / pre / residual tensors belong to earlier launches until now
-      const uint32_t nb = (uint32_t)a.nb64, nblk = (uint32_t)a.nblk;
+      const uint32_t nb = (uint32_t)a.nb, nblk = (uint32_t)a.nblk;
       const uint32_t total = (uint32_t)niter * nb;
-      const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * EPI_BLK64_BYTES);
+      const uint32_t nld = (uint32_t)((HAS_PRE ? 1 : 0) + NRES);
       auto issue_loads = [&](uint32_t k) {
         const uint32_t b = k % nblk;
         int x0, y0, n;
         tile_of((long)(k / nb), x0, y0, n);          // tail tile (n >= N): zero-filled boxes still complete the barrier
-        const int col = (int)(k % nb) * 64;
-        mbar_expect_tx(&pre_bar[b], load_bytes);
-        if constexpr (HAS_PRE) tma_load_4d(sS + (size_t)b * EPI_BLK64_BYTES, &em.m[1], &pre_bar[b], p.pre_coff + col, x0, y0, n);
-        if constexpr (NRES >= 1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[2], &pre_bar[b], p.res1_coff + col, x0, y0, n);
-        if constexpr (NRES >= 2) tma_load_4d(sR2 + (size_t)b * EPI_BLK64_BYTES, &em.m[3], &pre_bar[b], p.res2_coff + col, x0, y0, n);
+        const int i = (int)(k % nb);
+        const int wide = i < a.nb64 ? 1 : 0;          // 64-channel block | 32-channel tail block
+        const int col = i * 64;
+        mbar_expect_tx(&pre_bar[b], nld * (uint32_t)(wide ? EPI_BLK64_BYTES : EPI_BLK32_BYTES));
+        if constexpr (HAS_PRE) tma_load_4d(sS + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
+        if constexpr (NRES >= 1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+        if constexpr (NRES >= 2) tma_load_4d(sR2 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 6 : 7], &pre_bar[b], p.res2_coff + col, x0, y0, n);
       };
       if constexpr (HAS_LOADS)
         for (uint32_t k = 0; k < nblk && k < total; k++) issue_loads(k);
@@ -212,9 +216,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         const uint32_t b = k % nblk;
         int x0, y0, n;
         const bool live = tile_of((long)(k / nb), x0, y0, n);
+        const int i = (int)(k % nb);
         mbar_wait(&sfull_bar[b], (k / nblk) & 1);
         if (live) {
-          tma_store_4d(&em.m[0], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + (int)(k % nb) * 64, x0, y0, n);
+          tma_store_4d(&em.m[i < a.nb64 ? 0 : 1], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + i * 64, x0, y0, n);
           bulk_commit();
           bulk_wait_read0();
         }
@@ -234,7 +239,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const int wg = ew >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int sw128 = m & 7;
+    const int sw128 = m & 7, sw64 = (m >> 1) & 3;
     const int act = p.act;
     const float slope = p.slope, alpha = p.alpha;
     const bool scale = alpha != 1.f;
@@ -246,28 +251,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       mbar_wait(&tfull_bar[acc], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.acc_stride);
-      for (int i = 0; i < a.nb64; i++, k++) {
+      for (int i = 0; i < a.nb; i++, k++) {
         const int b = (int)(k % (uint32_t)a.nblk);
         if constexpr (HAS_LOADS) {
           mbar_wait(&pre_bar[b], (k / (uint32_t)a.nblk) & 1);                 // pre / residual blocks of this block landed
         } else {
           if (k >= (uint32_t)a.nblk) mbar_wait(&sfree_bar[b], ((k / (uint32_t)a.nblk) & 1) ^ 1);
         }
-        const uint32_t bS = sS_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
-        const uint32_t bR1 = sR1_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
-        const uint32_t bR2 = sR2_u + (uint32_t)b * EPI_BLK64_BYTES + (uint32_t)m * 128;
+        const bool wide = i < a.nb64;                         // 64-channel block (128 B rows, SWIZZLE_128B) | 32-channel tail (64 B rows, SWIZZLE_64B)
+        const uint32_t rowoff = (uint32_t)m * (wide ? 128u : 64u);
+        const uint32_t bS = sS_u + (uint32_t)b * EPI_BLK64_BYTES + rowoff;
+        const uint32_t bR1 = sR1_u + (uint32_t)b * EPI_BLK64_BYTES + rowoff;
+        const uint32_t bR2 = sR2_u + (uint32_t)b * EPI_BLK64_BYTES + rowoff;
         uint32_t ra[16], rb[16];
-        const int c0 = i * 64 + wg * 16, c1 = c0 + 32;        // this warp's two 16-column groups of the block
+        const int c0 = i * 64 + wg * 16, c1 = c0 + 32;        // this warp's 16-column groups of the block (tail: one group)
         tmem_ld16(t_addr + c0, ra);
-        tmem_ld16(t_addr + c1, rb);
+        if (wide) tmem_ld16(t_addr + c1, rb);
         tmem_ld_wait();
-        if (i == a.nb64 - 1) {          // last TMEM read of this tile: hand the accumulator back to the leader's MMA warp
+        if (i == a.nb - 1) {            // last TMEM read of this tile: hand the accumulator back to the leader's MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+          if (h == 1 && !wide) break;
           const uint32_t* rr = h ? rb : ra;
           const int cg = h ? c1 : c0;
           const bool do_act = (act != DASR_ACT_NONE) && (cg + 16 <= p.act_cols);
@@ -284,8 +292,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
               v[4 * j4 + 3] += b4.w;
             }
           }
-          const int ch = (cg & 63) >> 3;                      // 16-byte chunk index inside the 128 B row
-          const uint32_t o0 = (uint32_t)(((ch) ^ sw128) << 4), o1 = (uint32_t)(((ch + 1) ^ sw128) << 4);
+          const int ch = (cg & (wide ? 63 : 31)) >> 3;        // 16-byte chunk index inside the 128 B (64 B) row
+          const int sw = wide ? sw128 : sw64;
+          const uint32_t o0 = (uint32_t)(((ch) ^ sw) << 4), o1 = (uint32_t)(((ch + 1) ^ sw) << 4);
           if constexpr (HAS_PRE) {
             fma_bf16x8(v, lds128(bS + o0), 1.f);
             fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
@@ -392,17 +401,25 @@ static int tc2_plan(const DasrConvTcParams* p, int has_pre, int nres, int* stage
   const int bar_bytes = 40 * 8 + 256 * 4 + 64;
   const int per_blk = (1 + nres) * EPI_BLK64_BYTES;
   (void)has_pre;
-  for (int nblk = TC2_MAX_BLOCKS; nblk >= 2; nblk--) {
-    const long avail = (long)SMEM_LIMIT - 1024 - w_bytes - (long)nblk * per_blk - bar_bytes;
-    int stages = (int)(avail / a_stage);
-    if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
-    // prefer >= 3 A stages; accept 2 only at the smallest ring
-    if (stages >= 3 || (nblk == 2 && stages >= 2)) {
-      *stages_out = stages;
-      *nblk_out = nblk;
-      return 1;
-    }
+  static int force_nblk = -1;
+  if (force_nblk < 0) {
+    const char* e = getenv("DASR_TC2_NBLK");       // experiments: force the epilogue ring depth
+    force_nblk = e ? atoi(e) : 0;
   }
+  // measured on B200 (selftest fused, K=64 N=192): 4 A stages + 4 blocks 0.137 ms, 3 A stages + 5 blocks 0.171 ms — the A
+  // ring matters more than the epilogue ring, so take the deepest epilogue ring that still leaves 4 A stages
+  for (int want = 4; want >= 2; want--)
+    for (int nblk = TC2_MAX_BLOCKS; nblk >= 2; nblk--) {
+      if (force_nblk > 0 && nblk != force_nblk) continue;
+      const long avail = (long)SMEM_LIMIT - 1024 - w_bytes - (long)nblk * per_blk - bar_bytes;
+      int stages = (int)(avail / a_stage);
+      if (stages > TC2_MAX_STAGES) stages = TC2_MAX_STAGES;
+      if (stages >= want) {
+        *stages_out = stages;
+        *nblk_out = nblk;
+        return 1;
+      }
+    }
   return 0;
 }
 
@@ -411,7 +428,7 @@ int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
   // worst case of a pre addend and two residual tensors)
   if (!p) return 0;
   if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
-  if (p->cout % 64 != 0 || p->cout < 64 || p->cout > 256 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
+  if (p->cout % 32 != 0 || p->cout < 32 || p->cout > 256 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
   int st, nb;
   return tc2_plan(p, 1, 2, &st, &nb);
 }
@@ -421,7 +438,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   DASR_REQUIRE(p && in && w && out, "conv_tc2: null argument");
   DASR_REQUIRE(p->nvar == 1 && p->ntaps == 9 && p->out_mul == 1 && p->epi_mode == 0 && p->a_mode == 0 && !p->tile_rev,
                "conv_tc2: plain 3x3 geometry with the staged epilogue only");
-  DASR_REQUIRE(p->cout % 64 == 0 && p->cout >= 64 && p->cout <= 256, "conv_tc2: cout must be a multiple of 64 in [64, 256] (got %d)", p->cout);
+  DASR_REQUIRE(p->cout % 32 == 0 && p->cout >= 32 && p->cout <= 256, "conv_tc2: cout must be a multiple of 32 in [32, 256] (got %d)", p->cout);
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc2: bad dims");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc2: cin must be a multiple of 32 (got %d)", p->cin);
   if (p->nchunk_list > 0) {
@@ -454,6 +471,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   a.w_bytes = 9 * a.nchunks * a.n_half * ROW_B;
   a.a_stage_bytes = (A_HALO_BYTES + 1023) / 1024 * 1024;
   a.nb64 = p->cout / 64;
+  a.nb = a.nb64 + ((p->cout & 32) ? 1 : 0);
   a.acc_stride = 256;
   const int bar_bytes = 40 * 8 + 256 * 4 + 64;
   int stages = 0, nblk = 0;
@@ -495,15 +513,21 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
     const int css[4] = {p->out_cs, p->pre_cs, p->res1_cs, p->res2_cs};
     const char* names[4] = {"output", "pre", "res1", "res2"};
     for (int t = 0; t < 4; t++) {
-      if (!bases[t]) { em.m[t] = tm_in; continue; }
-      cuuint64_t gdim[4] = {(cuuint64_t)css[t], (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
-      cuuint64_t gstr[3] = {(cuuint64_t)css[t] * 2, (cuuint64_t)p->W * css[t] * 2, (cuuint64_t)p->H * p->W * css[t] * 2};
-      cuuint32_t box[4] = {64, TILE_W, TILE_H, 1};
-      cuuint32_t estr[4] = {1, 1, 1, 1};
-      CUresult r = enc(&em.m[t], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[t]), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(%s) failed: %d", names[t], (int)r); return DASR_E_LAUNCH; }
+      em.m[2 * t] = em.m[2 * t + 1] = tm_in;      // placeholders when unused
+      if (!bases[t]) continue;
+      for (int narrow = 0; narrow < 2; narrow++) {
+        if (narrow ? !(p->cout & 32) : (a.nb64 == 0)) continue;
+        const int width = narrow ? 32 : 64;
+        cuuint64_t gdim[4] = {(cuuint64_t)css[t], (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+        cuuint64_t gstr[3] = {(cuuint64_t)css[t] * 2, (cuuint64_t)p->W * css[t] * 2, (cuuint64_t)p->H * p->W * css[t] * 2};
+        cuuint32_t box[4] = {(cuuint32_t)width, TILE_W, TILE_H, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&em.m[2 * t + narrow], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(bases[t]), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         (narrow && css[t] > 32) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc2: cuTensorMapEncodeTiled(%s) failed: %d", names[t], (int)r); return DASR_E_LAUNCH; }
+      }
     }
   }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Tc2Maps, const Tc2Args);

@@ -550,6 +550,9 @@ int main(int argc, char** argv) {
       bench_tc_fused(16, 256, 256, 96, 64, 64, 1, 10, 0, 0, 1);
       bench_tc_fused(16, 256, 256, 96, 128, 128, 1, 10, 0, 0, 1);
       bench_tc_fused(16, 256, 256, 64, 128, 128, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 32, 32, 32, 1, 10, 0, 0, 1);
+      bench_tc_fused(16, 256, 256, 32, 32, 32, 1, 10, 0, 0, 0);
+      bench_tc_fused(16, 256, 256, 128, 64, 64, 1, 10, 0, 0, 1);
       return 0;
     }
     if (!strcmp(argv[i], "prof")) {  // short run for ncu: a few launches of the hot shapes
@@ -605,6 +608,10 @@ int main(int argc, char** argv) {
         test_tc(2, 40, 24, 32, 128, 128, 0, 0, 5);     // pre only, two blocks per tile
         test_tc(1, 32, 24, 64, 192, 192, 0, 0, 5);     // pre only, three blocks per tile
         test_tc(4, 96, 64, 32, 64, 64, 0, 0, 5);       // 192 tiles, pre + two residuals
+        test_tc(2, 40, 24, 32, 32, 32, 0, 0, 5);       // N = 32: one 32-channel tail block, pre + residuals
+        test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);       // N = 96: 64-block + tail block, pre + residuals
+        test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);     // N = 160: two blocks + tail, pre only
+        test_tc(1, 19, 11, 64, 96, 96, 0, 0, 4);       // N = 96 without loads
       }
       test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
       test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);

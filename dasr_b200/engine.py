@@ -528,7 +528,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
             for j in (2, 3, 4, 5):
                 ks = sched[j - 1][1]
                 width = sum(nf if k == 5 else GC for k in ks)
-                pair = PAIR_MODE and width % 64 == 0          # 64-channel epilogue blocks; other widths stay on one CTA
+                pair = PAIR_MODE                              # every dense-block launch runs on a CTA pair
                 if j < 5:
                     o = View(b, width, nf + (j - 1) * GC)                  # slots of conv j .. conv ks[-1], partial sums in place
                     ops.conv_tc(b, fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o,
@@ -542,7 +542,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True):
             for j in (2, 3, 4):   # x_{j-1} -> x_j (complete) | partial conv_{j+1..5}, accumulated in place
                 o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
                 ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2,
-                            act_cols=GC, pre=o, pair=PAIR_MODE and o.c % 64 == 0)
+                            act_cols=GC, pre=o, pair=PAIR_MODE)
             ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), pair=PAIR_MODE and nf % 64 == 0, **tail)
         else:
             for k in range(1, 5):
@@ -613,7 +613,7 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
         for j in (2, 3, 4):
             o = View(b, BW - nf - (j - 1) * GC, nf + (j - 1) * GC)
             ops.conv_tc(View(b, GC, nf + (j - 2) * GC), fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o,
-                        pair=PAIR_MODE and o.c % 64 == 0)
+                        pair=PAIR_MODE)
         ops.conv_tc(View(b, GC, nf + 3 * GC), fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), pair=PAIR_MODE and nf % 64 == 0, **tail)
     lr = _empty((N, H, W, nf), x, bf)
     ops.conv_tc(View(bufs[n_rdb], nf, 0), wk(L.i_lr), bk(L.i_lr), lr, nt=_pick_nt(nf, nf), res1=fea, beta1=1.0)

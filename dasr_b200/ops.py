@@ -343,6 +343,18 @@ def lpips_layer_bwd(feats, lin_w, dval, dpred, eps, accumulate):
                                            _stream()), 'lpips_layer_bwd')
 
 
+def ddm(patch, H, W, ilo, ihi, jlo, jhi):
+    """Domain-distance map (dasr_ddm): patch [B,C,nfh,nfw] fp32 CUDA -> [B,C,H,W] fp64; ilo/ihi/jlo/jhi numpy int32 ranges."""
+    B, Cc, nfh, nfw = patch.shape
+    dev = patch.device
+    rng = [torch.as_tensor(a, dtype=torch.int32).contiguous().to(dev) for a in (ilo, ihi, jlo, jhi)]
+    out = torch.empty((B, Cc, H, W), dtype=torch.float64, device=dev)
+    scratch = torch.empty(B * Cc * nfh * W, dtype=torch.float64, device=dev)
+    check(_lib.load().dasr_ddm(_p(patch), _p(out), _p(scratch), _p(rng[0]), _p(rng[1]), _p(rng[2]), _p(rng[3]), B * Cc, nfh, nfw,
+                               H, W, _stream()), 'ddm', 2)
+    return out
+
+
 def instnorm_lrelu_fwd(x, stats, eps=1e-5, slope=0.2):
     N, H, W, Cc = x.shape
     check(_lib.load().dasr_instnorm_lrelu_fwd(_p(x), _p(stats), N, H * W, Cc, eps, slope, _stream()), 'instnorm_lrelu_fwd')

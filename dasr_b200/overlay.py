@@ -7,7 +7,7 @@ entry.  A `sys.meta_path` finder runs BEFORE the path-based import system: when 
 that `python -m dasr_b200.install` has marked (a `.dasr_b200` file naming the flavour, SRN or DSN), the top-level imports
 
     SRN:  models, options, utils        ->  dasr_b200/srn/{models,options,utils}
-    DSN:  model, loss                   ->  dasr_b200/dsn/{model,loss}.py
+    DSN:  model, loss, receptive_cal    ->  dasr_b200/dsn/{model,loss,receptive_cal}.py
 
 are served from this repository; everything else (data/, scripts/, utils/receptive_cal.py, DSN/utils.py, ...) keeps
 coming from the checkout (the mirror packages append the shadowed reference directory to their own __path__).
@@ -24,7 +24,8 @@ MARKER = '.dasr_b200'
 TABLE = {
     'SRN': {'models': os.path.join(HERE, 'srn', 'models'), 'options': os.path.join(HERE, 'srn', 'options'),
             'utils': os.path.join(HERE, 'srn', 'utils')},
-    'DSN': {'model': os.path.join(HERE, 'dsn', 'model.py'), 'loss': os.path.join(HERE, 'dsn', 'loss.py')},
+    'DSN': {'model': os.path.join(HERE, 'dsn', 'model.py'), 'loss': os.path.join(HERE, 'dsn', 'loss.py'),
+            'receptive_cal': os.path.join(HERE, 'dsn', 'receptive_cal.py')},
 }
 _NAMES = {n for t in TABLE.values() for n in t}
 

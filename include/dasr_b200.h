@@ -156,7 +156,7 @@ int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bi
  * the filter rows resident and each load the A tile of their own pixel tile; one M=256 instruction feeds both tensor
  * cores (measured: 64 cycles per K step and pixel tile for N <= 128, N/2 above, against 84 / N/2+5 on one CTA), and a
  * filter set twice as large fits (dense-block launch 1: K = 64, N = 192).
- * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 64 == 0; pre / res1 / res2 as in
+ * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 32 == 0; pre / res1 / res2 as in
  * dasr_conv_tc (nullable).  `nt` is ignored (one Cout tile = cout). */
 int dasr_conv_tc2_supported(const DasrConvTcParams* p);
 int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
@@ -239,6 +239,13 @@ int dasr_lpips_layer_fwd(const float* feats, const float* lin_w, float* val, flo
                          float eps, int accumulate, void* stream);
 int dasr_lpips_layer_bwd(const float* feats, const float* lin_w, const float* dval, float* dpred_feats, int N, int H, int W,
                          int C, float eps, int accumulate, void* stream);
+
+/* Domain-distance map: out[n,y,x] = mean of patch[n,i,j] over the patch positions whose receptive-field window covers
+ * (y,x) (codes/DSN/receptive_cal.py:34-60, create_dataset_modified.py:14-24).  ilo/ihi[H], jlo/jhi[W]: inclusive range
+ * of patch rows / columns covering each coordinate (device int arrays; empty range = lo > hi -> NaN like the
+ * reference's 0/0).  patch: [NC, nfh, nfw] fp32; out: [NC, H, W] fp64; scratch: NC*nfh*W doubles. */
+int dasr_ddm(const float* patch, double* out, double* scratch, const int* ilo, const int* ihi, const int* jlo, const int* jhi,
+             int NC, int nfh, int nfw, int H, int W, void* stream);
 
 /* 2x2 s2 max-pool NHWC fp32 fwd / bwd (VGG19 features, architecture.py:1076) */
 int dasr_maxpool2_fwd(const float* in, float* out, int N, int H, int W, int C, void* stream);
