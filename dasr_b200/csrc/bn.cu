@@ -1,0 +1,128 @@
+// BatchNorm2d + LeakyReLU for the BatchNorm variant of the DSN frequency-separation discriminator — sm_100a, fp32 NHWC,
+// HBM-bound (two passes over a tensor of a few MB).
+//
+// Replaces (reference, codes/DSN/model.py:173-190): nn.BatchNorm2d(C) (affine, eps 1e-5, momentum 0.1, running statistics)
+// followed by nn.LeakyReLU(0.2) inside DiscriminatorBasic(norm_layer='Batch') — the architecture of the only trained
+// checkpoint in the tree (codes/DSN/last_iteration.tar).  One block owns 32 channels and sweeps all N*H*W pixels.
+#include "common.cuh"
+
+namespace dasr {
+
+// training: batch statistics (biased variance for the normalisation, unbiased for the running estimate) -> stats[c] =
+// (mean, rstd); eval: statistics from running_mean / running_var.  y = lrelu(gamma * (x - mean) * rstd + beta).
+__global__ void bn_lrelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ running_mean,
+                                    float* __restrict__ running_var, float* __restrict__ stats, long M, int C, float eps,
+                                    float momentum, int training, float slope) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float mean = 0.f, rstd = 1.f;
+  if (training) {
+    double a = 0.0;
+    if (c < C)
+      for (long pp = threadIdx.y; pp < M; pp += 8) a += (double)x[pp * C + c];
+    s1[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    double mu = 0.0;
+    for (int k = 0; k < 8; k++) mu += s1[k][threadIdx.x];
+    mu /= (double)M;
+    double v = 0.0;
+    if (c < C)
+      for (long pp = threadIdx.y; pp < M; pp += 8) {
+        double d = (double)x[pp * C + c] - mu;
+        v += d * d;
+      }
+    s2[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    double var = 0.0;
+    for (int k = 0; k < 8; k++) var += s2[k][threadIdx.x];
+    mean = (float)mu;
+    rstd = (float)(1.0 / sqrt(var / (double)M + (double)eps));
+    if (c < C && threadIdx.y == 0 && running_mean != nullptr) {
+      const double unbiased = M > 1 ? var / (double)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else if (c < C) {
+    mean = running_mean[c];
+    rstd = rsqrtf(running_var[c] + eps);
+  }
+  if (c < C) {
+    if (threadIdx.y == 0) {
+      stats[2 * c] = mean;
+      stats[2 * c + 1] = rstd;
+    }
+    const float g = gamma[c] * rstd, b = beta[c];
+    for (long pp = threadIdx.y; pp < M; pp += 8) {
+      const float t = (x[pp * C + c] - mean) * g + b;
+      y[pp * C + c] = t > 0.f ? t : t * slope;
+    }
+  }
+}
+
+// dz = dy * lrelu'(y);  dbeta = sum dz;  dgamma = sum dz * xhat;
+// training: dx = gamma * rstd * (dz - dbeta / M - xhat * dgamma / M);   eval: dx = gamma * rstd * dz
+__global__ void bn_lrelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                                    const float* __restrict__ gamma, const float* __restrict__ stats, float* __restrict__ dx,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int C, int training,
+                                    float slope) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const float mean = c < C ? stats[2 * c] : 0.f, rstd = c < C ? stats[2 * c + 1] : 1.f;
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (long pp = threadIdx.y; pp < M; pp += 8) {
+      const float dz = dy[pp * C + c] * (y[pp * C + c] > 0.f ? 1.f : slope);
+      a += (double)dz;
+      b += (double)dz * (double)((x[pp * C + c] - mean) * rstd);
+    }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  double db = 0.0, dg = 0.0;
+  for (int k = 0; k < 8; k++) {
+    db += s1[k][threadIdx.x];
+    dg += s2[k][threadIdx.x];
+  }
+  if (c < C) {
+    if (threadIdx.y == 0) {
+      if (dgamma) dgamma[c] = (float)dg;
+      if (dbeta) dbeta[c] = (float)db;
+    }
+    if (dx) {
+      const float g = gamma[c] * rstd;
+      const float mb = training ? (float)(db / (double)M) : 0.f, mg = training ? (float)(dg / (double)M) : 0.f;
+      for (long pp = threadIdx.y; pp < M; pp += 8) {
+        const float dz = dy[pp * C + c] * (y[pp * C + c] > 0.f ? 1.f : slope);
+        const float xh = (x[pp * C + c] - mean) * rstd;
+        dx[pp * C + c] = g * (dz - mb - xh * mg);
+      }
+    }
+  }
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" {
+
+int dasr_bn_lrelu_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* stats, long M, int C, float eps, float momentum, int training, float slope, void* stream) {
+  DASR_REQUIRE(x && y && gamma && beta && stats && M > 0 && C > 0, "bn_lrelu_fwd: bad arguments");
+  DASR_REQUIRE(training || (running_mean && running_var), "bn_lrelu_fwd: eval mode needs running statistics");
+  dim3 grid(cdiv(C, 32)), block(32, 8);
+  bn_lrelu_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, running_mean, running_var, stats, M, C, eps,
+                                                               momentum, training, slope);
+  return check_launch("bn_lrelu_fwd");
+}
+
+int dasr_bn_lrelu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, float* dx,
+                      float* dgamma, float* dbeta, long M, int C, int training, float slope, void* stream) {
+  DASR_REQUIRE(x && y && dy && gamma && stats && M > 0 && C > 0, "bn_lrelu_bwd: bad arguments");
+  dim3 grid(cdiv(C, 32)), block(32, 8);
+  bn_lrelu_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, dy, gamma, stats, dx, dgamma, dbeta, M, C, training, slope);
+  return check_launch("bn_lrelu_bwd");
+}
+
+}  // extern "C"

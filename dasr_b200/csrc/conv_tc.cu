@@ -144,11 +144,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     if (lane == 0) pdl_wait();           // activations come from the previous launch (filters / bias above do not)
     __syncwarp();
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
-      int tx = (int)(te % a.tiles_x);
-      long r = te / a.tiles_x;
-      int ty = (int)(r % a.tiles_y);
-      int n = (int)(r / a.tiles_y);
+      const uint32_t te = (uint32_t)(p.tile_rev ? a.ntiles - 1 - tile : tile);   // 32-bit tile arithmetic (checked on the host)
+      const uint32_t r = te / (uint32_t)a.tiles_x;
+      const int tx = (int)(te - r * (uint32_t)a.tiles_x);
+      const int n = (int)(r / (uint32_t)a.tiles_y);
+      const int ty = (int)(r - (uint32_t)n * (uint32_t)a.tiles_y);
       int x0 = tx * TILE_W, y0 = ty * TILE_H;
       if (lane == 0) {
         for (int c = 0; c < a.nchunks; c++) {
@@ -236,11 +236,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * a.epi_bytes);
       pdl_wait();                      // pre / residual tiles and the output slots belong to earlier launches until now
       auto tile_xyz = [&](long tile, int& x0, int& y0, int& n) {
-        const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
-        int tx = (int)(te % a.tiles_x);
-        long r = te / a.tiles_x;
-        int ty = (int)(r % a.tiles_y);
-        n = (int)(r / a.tiles_y);
+        const uint32_t te = (uint32_t)(p.tile_rev ? a.ntiles - 1 - tile : tile);
+        const uint32_t r = te / (uint32_t)a.tiles_x;
+        const int tx = (int)(te - r * (uint32_t)a.tiles_x);
+        n = (int)(r / (uint32_t)a.tiles_y);
+        const int ty = (int)(r - (uint32_t)n * (uint32_t)a.tiles_y);
         x0 = tx * TILE_W;
         y0 = ty * TILE_H;
       };
@@ -313,11 +313,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       const int acc = (int)(it % nacc);
       const uint32_t acc_phase = (it / nacc) & 1;
-      const long te = p.tile_rev ? a.ntiles - 1 - tile : tile;   // alternate launches walk the tiles backwards (L2 reuse)
-      int tx = (int)(te % a.tiles_x);
-      long r = te / a.tiles_x;
-      int ty = (int)(r % a.tiles_y);
-      int n = (int)(r / a.tiles_y);
+      const uint32_t te = (uint32_t)(p.tile_rev ? a.ntiles - 1 - tile : tile);
+      const uint32_t r = te / (uint32_t)a.tiles_x;
+      const int tx = (int)(te - r * (uint32_t)a.tiles_x);
+      const int n = (int)(r / (uint32_t)a.tiles_y);
+      const int ty = (int)(r - (uint32_t)n * (uint32_t)a.tiles_y);
       const int y = ty * TILE_H + py, x = tx * TILE_W + px;
       const bool valid = (y < p.H) && (x < p.W);
       const int oy = y * p.out_mul + p.out_py[var], ox = x * p.out_mul + p.out_px[var];
@@ -758,6 +758,7 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
                  const void* mask_src, void* out, const DasrConvTcParams* p, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc: null argument");
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc: bad dims");
+  DASR_REQUIRE((long)p->N * cdiv(p->W, TILE_W) * cdiv(p->H, TILE_H) < (1L << 30), "conv_tc: too many tiles for 32-bit tile arithmetic");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc: cin must be a multiple of 32 (got %d)", p->cin);
   if (p->nchunk_list > 0) {
     DASR_REQUIRE(p->nchunk_list <= 8 && p->nchunk_list * CHUNK == p->cin && p->in_cs % 8 == 0, "conv_tc: chunk list must cover cin");

@@ -108,14 +108,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   pdl_launch_dependents();              // the next launch may start its prologue on SMs this grid has left
 
   auto tile_of = [&](long it, int& x0, int& y0, int& n) -> bool {     // tile of THIS CTA in pair-iteration `it`
-    const long t = 2 * (pair + it * npairs) + rank;
-    int tx = (int)(t % a.tiles_x);
-    long r = t / a.tiles_x;
-    int ty = (int)(r % a.tiles_y);
-    n = (int)(r / a.tiles_y);           // n >= N for the odd tail tile: TMA zero-fills, nothing is stored
-    x0 = tx * TILE_W;
-    y0 = ty * TILE_H;
-    return t < a.ntiles;
+    const uint32_t t = 2u * (uint32_t)(pair + it * npairs) + rank;     // tile counts fit 32 bits (checked on the host)
+    const uint32_t r = t / (uint32_t)a.tiles_x;
+    const uint32_t tx = t - r * (uint32_t)a.tiles_x;
+    n = (int)(r / (uint32_t)a.tiles_y); // n >= N for the odd tail tile: TMA zero-fills, nothing is stored
+    const uint32_t ty = r - (uint32_t)n * (uint32_t)a.tiles_y;
+    x0 = (int)tx * TILE_W;
+    y0 = (int)ty * TILE_H;
+    return (long)t < a.ntiles;
   };
   const long niter = (a.ntiles / 2 + (a.ntiles & 1) - pair + npairs - 1) / npairs;   // pair-iterations of this pair
 
@@ -201,8 +201,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       auto issue_loads = [&](uint32_t k) {
         const uint32_t b = k % nblk;
         int x0, y0, n;
-        tile_of((long)(k / nb), x0, y0, n);          // tail tile (n >= N): zero-filled boxes still complete the barrier
-        const int i = (int)(k % nb);
+        const uint32_t kt = k / nb;
+        tile_of((long)kt, x0, y0, n);                // tail tile (n >= N): zero-filled boxes still complete the barrier
+        const int i = (int)(k - kt * nb);
         const int wide = i < a.nb64 ? 1 : 0;          // 64-channel block | 32-channel tail block
         const int col = i * 64;
         mbar_expect_tx(&pre_bar[b], nld * (uint32_t)(wide ? EPI_BLK64_BYTES : EPI_BLK32_BYTES));
@@ -212,22 +213,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       };
       if constexpr (HAS_LOADS)
         for (uint32_t k = 0; k < nblk && k < total; k++) issue_loads(k);
-      for (uint32_t k = 0; k < total; k++) {
-        const uint32_t b = k % nblk;
-        int x0, y0, n;
-        const bool live = tile_of((long)(k / nb), x0, y0, n);
-        const int i = (int)(k % nb);
-        mbar_wait(&sfull_bar[b], (k / nblk) & 1);
-        if (live) {
-          tma_store_4d(&em.m[i < a.nb64 ? 0 : 1], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + i * 64, x0, y0, n);
-          bulk_commit();
-          bulk_wait_read0();
-        }
+      auto retire = [&](uint32_t k) {                // block k's store has finished reading its ring slot
         if constexpr (HAS_LOADS) {
           if (k + nblk < total) issue_loads(k + nblk);
         } else {
-          mbar_arrive(&sfree_bar[b]);
+          mbar_arrive(&sfree_bar[k % nblk]);
         }
+      };
+      int x0 = 0, y0 = 0, n = 0;
+      bool live = false;
+      uint32_t i = 0;                                 // block index inside the tile
+      for (uint32_t k = 0; k < total; k++) {
+        const uint32_t b = k % nblk;
+        if (i == 0) live = tile_of((long)(k / nb), x0, y0, n);
+        mbar_wait(&sfull_bar[b], (k / nblk) & 1);
+        if (live) tma_store_4d(&em.m[(int)i < a.nb64 ? 0 : 1], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + (int)i * 64, x0, y0, n);
+        bulk_commit();                                // (an empty group for the tail tile keeps the group count uniform)
+        if (k >= 1) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // everything but the newest store has been read
+          retire(k - 1);
+        }
+        if (++i == nb) i = 0;
+      }
+      if (total > 0) {
+        bulk_wait_read0();
+        retire(total - 1);
       }
       bulk_wait0();
     }
@@ -440,6 +450,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
                "conv_tc2: plain 3x3 geometry with the staged epilogue only");
   DASR_REQUIRE(p->cout % 32 == 0 && p->cout >= 32 && p->cout <= 256, "conv_tc2: cout must be a multiple of 32 in [32, 256] (got %d)", p->cout);
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc2: bad dims");
+  DASR_REQUIRE((long)p->N * cdiv(p->W, TILE_W) * cdiv(p->H, TILE_H) < (1L << 30), "conv_tc2: too many tiles for 32-bit tile arithmetic");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc2: cin must be a multiple of 32 (got %d)", p->cin);
   if (p->nchunk_list > 0) {
     DASR_REQUIRE(p->nchunk_list <= 8 && p->nchunk_list * CHUNK == p->cin, "conv_tc2: chunk list must cover cin");

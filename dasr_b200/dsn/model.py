@@ -3,7 +3,7 @@ arguments, state_dict keys and error behaviour; every forward/backward is C-ABI 
 
   De_resnet / Generator / ResidualBlock   model.py:7-55,213-224   3x3 convs + one-slope PReLU + sigmoid
   Discriminator (D_arch='FSD' | 'nld_s1' | 'nld_s2')   model.py:60-118
-  DiscriminatorBasic (InstanceNorm variant)            model.py:173-210
+  DiscriminatorBasic (Instance / Batch norm)          model.py:173-210
   FilterLow / FilterHigh / GaussianFilter              model.py:227-295 (shared with the SRN mirror)
 """
 import torch
@@ -131,8 +131,13 @@ class De_resnet(_SeqNet):
 class DiscriminatorBasic(_SeqNet):
     def __init__(self, n_input_channels=3, norm_layer='Batch'):
         super().__init__()
+        self.norm = norm_layer
         if norm_layer == 'Batch':
-            raise NotImplementedError('DiscriminatorBasic with BatchNorm is not on the B200 path (use norm_layer="Instance")')
+            self.net = nn.Sequential(
+                nn.Conv2d(n_input_channels, 64, kernel_size=5, padding=2), nn.LeakyReLU(0.2),
+                nn.Conv2d(64, 128, kernel_size=5, padding=2), nn.BatchNorm2d(128), nn.LeakyReLU(0.2),
+                nn.Conv2d(128, 256, kernel_size=5, padding=2), nn.BatchNorm2d(256), nn.LeakyReLU(0.2),
+                nn.Conv2d(256, 1, kernel_size=1))
         elif norm_layer == 'Instance':
             self.net = nn.Sequential(
                 nn.Conv2d(n_input_channels, 64, kernel_size=5, padding=2), nn.LeakyReLU(0.2),
@@ -142,12 +147,19 @@ class DiscriminatorBasic(_SeqNet):
         else:
             raise NotImplementedError('{} norm layer is not recognized'.format(norm_layer))
 
+    def _norm(self, i):
+        if self.norm == 'Instance':
+            return {'op': 'in_lrelu'}
+        bn = self.net[i]      # running statistics are module buffers: handed to the layer list by reference
+        return {'op': 'bn_lrelu', 'w': 'net.%d.weight' % i, 'b': 'net.%d.bias' % i, 'rm': bn.running_mean, 'rv': bn.running_var,
+                'nbt': bn.num_batches_tracked, 'training': self.training}
+
     def _spec(self):
         return [{'op': 'conv', 'k': 5, 's': 1, 'p': 2, 'w': 'net.0.weight', 'b': 'net.0.bias', 'act': ACT_LRELU},
                 {'op': 'conv', 'k': 5, 's': 1, 'p': 2, 'w': 'net.2.weight', 'b': 'net.2.bias', 'act': ACT_NONE},
-                {'op': 'in_lrelu'},
+                self._norm(3),
                 {'op': 'conv', 'k': 5, 's': 1, 'p': 2, 'w': 'net.5.weight', 'b': 'net.5.bias', 'act': ACT_NONE},
-                {'op': 'in_lrelu'},
+                self._norm(6),
                 {'op': 'conv', 'k': 1, 's': 1, 'p': 0, 'w': 'net.8.weight', 'b': 'net.8.bias', 'act': ACT_NONE}]
 
 

@@ -343,6 +343,18 @@ def lpips_layer_bwd(feats, lin_w, dval, dpred, eps, accumulate):
                                            _stream()), 'lpips_layer_bwd')
 
 
+def bn_lrelu_fwd(x, y, gamma, beta, running_mean, running_var, stats, eps, momentum, training, slope=0.2):
+    M, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    check(_lib.load().dasr_bn_lrelu_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(stats), M, Cc,
+                                        eps, momentum, int(bool(training)), slope, _stream()), 'bn_lrelu_fwd')
+
+
+def bn_lrelu_bwd(x, y, dy, gamma, stats, dx, dgamma, dbeta, training, slope=0.2):
+    M, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    check(_lib.load().dasr_bn_lrelu_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(stats), _p(dx), _p(dgamma), _p(dbeta), M, Cc,
+                                        int(bool(training)), slope, _stream()), 'bn_lrelu_bwd')
+
+
 def ddm(patch, H, W, ilo, ihi, jlo, jhi):
     """Domain-distance map (dasr_ddm): patch [B,C,nfh,nfw] fp32 CUDA -> [B,C,H,W] fp64; ilo/ihi/jlo/jhi numpy int32 ranges."""
     B, Cc, nfh, nfw = patch.shape

@@ -5,6 +5,8 @@ A net is a list of layer dicts:
   {'op': 'conv', 'k', 's', 'p', 'w': param index, 'b': param index | None, 'act': ACT_NONE | ACT_LRELU}
   {'op': 'prelu', 'a': param index}            nn.PReLU() with one slope
   {'op': 'in_lrelu'}                           InstanceNorm2d(affine=False, eps=1e-5) + LeakyReLU(0.2), in place
+  {'op': 'bn_lrelu', 'w', 'b': param indices, 'rm', 'rv', 'nbt': running_mean / running_var / num_batches_tracked buffers,
+   'training': bool}                           BatchNorm2d(affine, eps=1e-5, momentum=0.1) + LeakyReLU(0.2)
   {'op': 'sigmoid'}                            in place
   {'op': 'res_begin'} ... {'op': 'res_end'}    y = x_at_begin + y
 """
@@ -59,6 +61,13 @@ def forward_nhwc(a, layers, params, save=True):
             st = torch.empty((cur.shape[0], cur.shape[3], 2), dtype=torch.float32, device=x.device)
             ops.instnorm_lrelu_fwd(cur, st, 1e-5, 0.2)
             o = cur
+            aux.append(st)
+        elif op == 'bn_lrelu':
+            st = torch.empty((cur.shape[3], 2), dtype=torch.float32, device=x.device)
+            o = torch.empty_like(cur)
+            ops.bn_lrelu_fwd(cur, o, params[L['w']], params[L['b']], L['rm'], L['rv'], st, 1e-5, 0.1, L['training'], 0.2)
+            if L['training'] and L.get('nbt') is not None:
+                L['nbt'].add_(1)
             aux.append(st)
         elif op == 'sigmoid':
             ops.sigmoid_fwd(cur, cur)
@@ -130,6 +139,14 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
         elif op == 'in_lrelu':
             gz = torch.empty_like(g)
             ops.instnorm_lrelu_bwd(acts[li + 1], aux[li], g, gz, 0.2)
+            g = gz
+        elif op == 'bn_lrelu':
+            gz = torch.empty_like(g)
+            dgm = torch.empty_like(params[L['w']], dtype=torch.float32) if need_dw else None
+            dbt = torch.empty_like(params[L['b']], dtype=torch.float32) if need_dw else None
+            ops.bn_lrelu_bwd(acts[li], acts[li + 1], g, params[L['w']], aux[li], gz, dgm, dbt, L['training'], 0.2)
+            if need_dw:
+                grads[L['w']], grads[L['b']] = dgm, dbt
             g = gz
         elif op == 'sigmoid':
             gz = torch.empty_like(g)

@@ -240,6 +240,15 @@ int dasr_lpips_layer_fwd(const float* feats, const float* lin_w, float* val, flo
 int dasr_lpips_layer_bwd(const float* feats, const float* lin_w, const float* dval, float* dpred_feats, int N, int H, int W,
                          int C, float eps, int accumulate, void* stream);
 
+/* BatchNorm2d(affine, eps, momentum, running statistics) + LeakyReLU on NHWC fp32 [M = N*H*W pixels, C] — the BatchNorm
+ * variant of DSN's DiscriminatorBasic (codes/DSN/model.py:173-190).  training = 1: batch statistics (and the running
+ * estimates are updated in place, unbiased variance); 0: running statistics.  stats: 2*C floats (mean, rstd) kept for bwd.
+ * bwd: dx / dgamma / dbeta (each nullable). */
+int dasr_bn_lrelu_fwd(const float* x, float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* stats, long M, int C, float eps, float momentum, int training, float slope, void* stream);
+int dasr_bn_lrelu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, float* dx,
+                      float* dgamma, float* dbeta, long M, int C, int training, float slope, void* stream);
+
 /* Domain-distance map: out[n,y,x] = mean of patch[n,i,j] over the patch positions whose receptive-field window covers
  * (y,x) (codes/DSN/receptive_cal.py:34-60, create_dataset_modified.py:14-24).  ilo/ihi[H], jlo/jhi[W]: inclusive range
  * of patch rows / columns covering each coordinate (device int arrays; empty range = lo > hi -> NaN like the

@@ -184,7 +184,7 @@ def test_dsn_unsupported_options_raise():
     from dasr_b200.dsn.loss import GeneratorLoss
     from dasr_b200.dsn.model import Discriminator, DiscriminatorBasic
     with pytest.raises(NotImplementedError):
-        DiscriminatorBasic(9, 'Batch')
+        DiscriminatorBasic(9, 'Group')
     with pytest.raises(NotImplementedError):
         Discriminator(D_arch='unknown')
     with pytest.raises(NotImplementedError):
@@ -236,3 +236,65 @@ def test_fsd_avg_pool_highpass_vs_reference(golden):
         if n < 1e-4 * big:
             continue          # bias of a conv feeding InstanceNorm: mathematically zero gradient, pure rounding noise
         assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+
+
+def test_domain_distance_map_vs_reference(golden):
+    """receptive_cal.getWeights / domain_distance_map_handler (dasr_ddm kernels, fp64) against the arrays the reference's
+    numpy scatter produced (tests/golden/ddm.pt): same [1,1,h,w] float64 array that create_dataset_modified.py np.save()s."""
+    import numpy as np
+    from dasr_b200.dsn import receptive_cal as R
+    for c in golden('ddm.pt'):
+        H, W = c['hw']
+        lh, lw = R.receptive_cal(H, c['convnet']), R.receptive_cal(W, c['convnet'])
+        patch = O.synth_image(c['patch_shape'], c['patch_seed']).numpy()
+        out = R.getWeights(patch, torch.zeros((1, 1, H, W)), lh, lw)
+        assert out.dtype == np.float64 and out.shape == (1, 1, H, W)
+        assert np.allclose(out, c['ddm'].numpy(), rtol=1e-12, atol=1e-12, equal_nan=True), c['name']
+    # handler: gau / avg_pool keep the image size, wavelet halves it (create_dataset_modified.py:14-24)
+    fake = torch.zeros((1, 3, 40, 33))
+    d_out = O.synth_image((1, 1, 36, 29), 7).numpy()
+    assert R.domain_distance_map_handler(fake, d_out, [[4, 1, 1]] * 4, 'avg_pool').shape == (1, 1, 40, 33)
+
+
+def test_fsd_batchnorm_discriminator_vs_reference(golden):
+    """Discriminator(D_arch='FSD', norm_layer='Batch') — the architecture of the shipped checkpoint codes/DSN/last_iteration.tar
+    (DSN/model.py:173-190): train-mode forward / gradients / running statistics and the eval-mode forward against the reference."""
+    from collections import OrderedDict
+    from dasr_b200.dsn.model import Discriminator
+    g = golden('dsn_autorepro.pt')['fsd_bn']
+    net = Discriminator(kernel_size=5, wgan=False, highpass=True, D_arch='FSD', norm_layer='Batch', filter_type='gau')
+    sd = OrderedDict()
+    for i, (k, shp) in enumerate(g['shapes'].items()):
+        if len(shp) == 4:
+            sd[k] = O.synth(shp, 171000 + i, (2.0 / (shp[1] * shp[2] * shp[3])) ** 0.5 * 3 ** 0.5)
+        elif k.endswith('weight'):
+            sd[k] = O.synth(shp, 171000 + i, 0.3, 1.0)
+        else:
+            sd[k] = O.synth(shp, 171000 + i, 0.05)
+    missing = net.load_state_dict(sd, strict=False)
+    assert all('running' in k or 'num_batches' in k or k.startswith('filter') for k in missing.missing_keys), missing
+    net.cuda().train()
+    x = O.synth_image(g['x_shape'], g['x_seed']).cuda().requires_grad_(True)
+    out = net(x)
+    assert rel_linf(out, g['out']) < TOL
+    (out * O.synth(tuple(out.shape), g['pat_seed']).cuda()).sum().backward()
+    assert rel_linf(x.grad, g['dx']) < TOL
+    named = dict(net.named_parameters())
+    for k, ref in g['grads'].items():
+        if float(ref.abs().max()) < 1e-4 * max(g['grad_norms'].values()):
+            continue                      # bias of a conv feeding BatchNorm: mathematically zero gradient
+        assert rel_linf(named[k].grad, ref) < TOL, k
+    big = max(g['grad_norms'].values())
+    for k, n in g['grad_norms'].items():
+        if n >= 1e-4 * big:
+            assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+    state = net.state_dict()
+    for k, v in g['running'].items():
+        if 'num_batches' in k:
+            assert int(state[k]) == int(v), k
+        else:
+            assert rel_linf(state[k], v) < TOL, k
+    net.eval()
+    with torch.no_grad():
+        oe = net(O.synth_image((2, 3, 20, 12), g['x_eval_seed']).cuda())
+    assert rel_linf(oe, g['out_eval']) < TOL

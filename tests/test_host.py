@@ -305,3 +305,26 @@ def test_dense_block_schedules_cover_every_product_once():
         engine.check_schedule(bad)
     # channel offsets of the chunks inside the [x | x1..x4 | p5] buffer
     assert engine._sched2_chunk_offsets(64, 'x') == [0, 32] and engine._sched2_chunk_offsets(64, 3) == [128]
+
+
+def test_ddm_window_ranges_reproduce_the_reference_scatter(golden):
+    """dasr_b200/dsn/receptive_cal.py: the per-coordinate ranges of covering patch rows / columns (host logic feeding the
+    dasr_ddm gather kernels), evaluated here with numpy, reproduce the reference's scatter-add / count
+    (codes/DSN/receptive_cal.py:34-60) for the three discriminator geometries of create_dataset_modified.py:113-119 —
+    including the quirk that the W axis' (jump, rf, start) are used for both axes."""
+    from dasr_b200.dsn import receptive_cal as R
+    for c in golden('ddm.pt'):
+        H, W = c['hw']
+        lh, lw = R.receptive_cal(H, c['convnet']), R.receptive_cal(W, c['convnet'])
+        assert tuple(lh) == c['layer_h'] and tuple(lw) == c['layer_w']
+        patch = O.synth_image(c['patch_shape'], c['patch_seed']).double().numpy()[0, 0]
+        jump, rf, start = lw[1], lw[2], lw[3]
+        ilo, ihi = R._windows(lh[0], H, jump, rf, start)
+        jlo, jhi = R._windows(lw[0], W, jump, rf, start)
+        out = np.empty((H, W))
+        for y in range(H):
+            for x in range(W):
+                blk = patch[ilo[y]:ihi[y] + 1, jlo[x]:jhi[x] + 1]
+                out[y, x] = blk.sum() / blk.size if blk.size else np.nan
+        ref = c['ddm'].numpy()[0, 0]
+        assert np.allclose(out, ref, rtol=1e-12, atol=1e-12, equal_nan=True), c['name']

@@ -32,10 +32,10 @@ def main(path, out_json=None):
         print('%-60s %8d %12.1f %6.1f%% %14.1f' % (k[:60], a['launches'], a['us'], 100 * a['us'] / tot, a['dram'] / a['launches'] / 1e6))
     print('total us: %.1f' % tot)
     if out_json:
-        tcs = [v for k, v in agg.items() if 'conv_tc_kernel' in k]
+        tcs = [v for k, v in agg.items() if 'conv_tc_kernel' in k or 'conv_tc2_kernel' in k]
         tc = {'launches': sum(v['launches'] for v in tcs), 'us': sum(v['us'] for v in tcs), 'dram': sum(v['dram'] for v in tcs)} if tcs else None
         if tc:
-            json.dump({'kernel': 'dasr::conv_tc_kernel', 'launches': tc['launches'],
+            json.dump({'kernel': 'dasr::conv_tc2_kernel + conv_tc_kernel', 'launches': tc['launches'],
                        'dram_bytes_per_launch_avg': tc['dram'] / tc['launches'], 'time_share': tc['us'] / tot,
                        'us_per_launch_avg_cold': tc['us'] / tc['launches'],
                        'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum (tools/profile_forward.py)'},
