@@ -107,6 +107,7 @@ SYMBOLS = {
     'dasr_lpips_layer_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'dasr_bn_lrelu_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _f, _f, _i, _f, _vp]),
     'dasr_bn_lrelu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _f, _vp]),
+    'dasr_pixel_shuffle': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'dasr_ddm': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasr_log_loss': (_i, [_vp, _i, _f, _vp, _vp, _f, _l, _vp, _vp]),
     'dasr_prelu_fwd': (_i, [_vp, _vp, _vp, _l, _vp]),

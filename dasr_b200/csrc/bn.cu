@@ -126,3 +126,33 @@ int dasr_bn_lrelu_bwd(const float* x, const float* y, const float* dy, const flo
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// nn.PixelShuffle(r) on NHWC fp32 (codes/SRN/models/modules/block.py:838-851, the sr_resnet upsampler):
+//   out[n, y*r + i, x*r + j, c] = in[n, y, x, c*r*r + i*r + j];  the backward is the inverse gather.
+// ---------------------------------------------------------------------------------------------
+namespace dasr {
+__global__ void pixel_shuffle_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C, int r,
+                                     int inverse) {
+  // C = output channels; input has C*r*r channels at HxW, output C channels at (H*r)x(W*r)
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)N * H * r * W * r * C;
+  if (idx >= total) return;
+  int c = (int)(idx % C);
+  long pp = idx / C;
+  int ox = (int)(pp % (W * r));
+  long rr = pp / (W * r);
+  int oy = (int)(rr % (H * r));
+  int n = (int)(rr / (H * r));
+  const int y = oy / r, i = oy - y * r, x = ox / r, j = ox - x * r;
+  const long lo = (((long)n * H + y) * W + x) * ((long)C * r * r) + (long)c * r * r + i * r + j;
+  if (inverse) out[lo] = in[idx]; else out[idx] = in[lo];
+}
+}  // namespace dasr
+
+extern "C" int dasr_pixel_shuffle(const float* in, float* out, int N, int H, int W, int C, int r, int inverse, void* stream) {
+  DASR_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && r >= 1, "pixel_shuffle: bad arguments");
+  long total = (long)N * H * r * W * r * C;
+  dasr::pixel_shuffle_kernel<<<dasr::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C, r, inverse);
+  return dasr::check_launch("pixel_shuffle");
+}

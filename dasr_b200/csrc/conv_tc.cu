@@ -266,7 +266,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         for (int k = 0; k < nbuf; k++)
           if ((long)blockIdx.x + k * G < a.ntiles) issue_loads(blockIdx.x + k * G, k);
       }
+      // The store of tile i is retired (its staging buffer handed back: next pre/residual loads, or sfree) only after
+      // the store of tile i+1 has been issued: `wait_group.read 1` then covers tile i while tile i+1 is still being read,
+      // so the shared-memory read of one tile overlaps the wait for the next (measured on the pair kernel: the
+      // serialised issue -> wait_read -> retire loop was the bottleneck of the small launches).
       uint32_t it = 0;
+      long prev_tile = -1;
+      int prev_b = 0;
+      auto retire = [&](long t, int bb) {           // whole warp
+        if (has_loads) {
+          if (t + (long)nbuf * G < a.ntiles) issue_loads(t + (long)nbuf * G, bb);
+        } else if (lane == 0) {
+          mbar_arrive(&sfree_bar[bb]);
+        }
+        __syncwarp();
+      };
       for (long tile = blockIdx.x; tile < a.ntiles; tile += G, it++) {
         const int b = (int)(it % (uint32_t)nbuf);
         if (lane == 0) {
@@ -279,11 +293,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             tma_store_4d(&em.m[wide ? 0 : 1], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
           }
           bulk_commit();
-          bulk_wait_read0();                       // buffer b has been read by the stores
-          if (!has_loads) mbar_arrive(&sfree_bar[b]);
+          if (prev_tile >= 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous tile's stores have read their buffer
         }
         __syncwarp();
-        if (has_loads && tile + (long)nbuf * G < a.ntiles) issue_loads(tile + (long)nbuf * G, b);
+        if (prev_tile >= 0) retire(prev_tile, prev_b);
+        prev_tile = tile;
+        prev_b = b;
+      }
+      if (prev_tile >= 0) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        retire(prev_tile, prev_b);
       }
       if (lane == 0) bulk_wait0();                 // all stores complete before the CTA (and its smem) goes away
     }

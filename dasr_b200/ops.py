@@ -355,6 +355,13 @@ def bn_lrelu_bwd(x, y, dy, gamma, stats, dx, dgamma, dbeta, training, slope=0.2)
                                         int(bool(training)), slope, _stream()), 'bn_lrelu_bwd')
 
 
+def pixel_shuffle(src, dst, r, inverse=False):
+    """nn.PixelShuffle(r) on NHWC fp32: src [N,H,W,C*r*r] -> dst [N,H*r,W*r,C]; inverse: dst [N,H,W,C*r*r] <- src [N,H*r,W*r,C]."""
+    lo = dst if inverse else src
+    N, H, W, CC = lo.shape
+    check(_lib.load().dasr_pixel_shuffle(_p(src), _p(dst), N, H, W, CC // (r * r), r, int(bool(inverse)), _stream()), 'pixel_shuffle')
+
+
 def ddm(patch, H, W, ilo, ihi, jlo, jhi):
     """Domain-distance map (dasr_ddm): patch [B,C,nfh,nfw] fp32 CUDA -> [B,C,H,W] fp64; ilo/ihi/jlo/jhi numpy int32 ranges."""
     B, Cc, nfh, nfw = patch.shape

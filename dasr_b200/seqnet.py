@@ -8,6 +8,9 @@ A net is a list of layer dicts:
   {'op': 'bn_lrelu', 'w', 'b': param indices, 'rm', 'rv', 'nbt': running_mean / running_var / num_batches_tracked buffers,
    'training': bool}                           BatchNorm2d(affine, eps=1e-5, momentum=0.1) + LeakyReLU(0.2)
   {'op': 'sigmoid'}                            in place
+  {'op': 'pixel_shuffle', 'r': 2}              nn.PixelShuffle(r)
+  conv layers may carry 'view': (cout, cin, k, k) — an nn.Linear weight [out, in] used as a k x k valid conv over the
+  NHWC feature map it flattens (Linear(512*4*4, 100) after .view(N, -1) == conv k=4 with the weight viewed [100,512,4,4])
   {'op': 'res_begin'} ... {'op': 'res_end'}    y = x_at_begin + y
 """
 import torch
@@ -45,6 +48,8 @@ def forward_nhwc(a, layers, params, save=True):
         op = L['op']
         if op == 'conv':
             wt = params[L['w']]
+            if L.get('view') is not None:
+                wt = wt.view(*L['view'])
             bs = params[L['b']] if L['b'] is not None else None
             n, h, w, _ = cur.shape
             oh, ow = _out_hw(h, L['k'], L['s'], L['p']), _out_hw(w, L['k'], L['s'], L['p'])
@@ -72,6 +77,12 @@ def forward_nhwc(a, layers, params, save=True):
         elif op == 'sigmoid':
             ops.sigmoid_fwd(cur, cur)
             o = cur
+            aux.append(None)
+        elif op == 'pixel_shuffle':
+            r = L['r']
+            n, h, w, cc = cur.shape
+            o = torch.empty((n, h * r, w * r, cc // (r * r)), dtype=torch.float32, device=x.device)
+            ops.pixel_shuffle(cur, o, r)
             aux.append(None)
         elif op == 'res_begin':
             res_stack.append(cur)
@@ -119,12 +130,20 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
                     g = g.clone()
                 ops.act_bwd(g, acts[li + 1], 0.2)
             wt = params[L['w']]
+            if L.get('view') is not None:
+                wt = wt.view(*L['view'])
+            act_kind = L.get('act', ACT_NONE)
+            if act_kind == ops.ACT_RELU:
+                if skip_stack and skip_stack[-1] is g:
+                    g = g.clone()
+                ops.act_bwd(g, acts[li + 1], 0.0)
             if need_dw:
-                grads[L['w']] = torch.empty_like(wt, dtype=torch.float32)
+                gw = torch.empty_like(wt, dtype=torch.float32)
+                grads[L['w']] = gw.view_as(params[L['w']])
                 db = None
                 if L['b'] is not None:
                     db = grads[L['b']] = torch.empty_like(params[L['b']], dtype=torch.float32)
-                ops.conv2d_wgrad_f32(acts[li], g, grads[L['w']], db, L['k'], L['s'], L['p'])
+                ops.conv2d_wgrad_f32(acts[li], g, gw, db, L['k'], L['s'], L['p'])
             if li > first_conv or need_dx:
                 gin = torch.empty(tuple(acts[li].shape), dtype=torch.float32, device=dout.device)
                 ops.conv2d_f32(g, ops.pack_filter_f32(wt, for_dgrad=True), None, gin, L['k'], L['s'], L['p'], mode=DGRAD)
@@ -151,6 +170,10 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
         elif op == 'sigmoid':
             gz = torch.empty_like(g)
             ops.sigmoid_bwd(acts[li + 1], g, gz)
+            g = gz
+        elif op == 'pixel_shuffle':
+            gz = torch.empty(tuple(acts[li].shape), dtype=torch.float32, device=dout.device)
+            ops.pixel_shuffle(g, gz, L['r'], inverse=True)
             g = gz
         elif op == 'res_end':
             skip_stack.append(g)            # the same gradient feeds the skip connection and the residual branch

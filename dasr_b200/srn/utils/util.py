@@ -125,7 +125,11 @@ def forward_chop(img, scale, model, shave=20, min_size=160000):
     left, right = slice(0, w // 2 + shave), slice(w - w // 2 - shave, w)
     chops = [img[..., top, left], img[..., top, right], img[..., bottom, left], img[..., bottom, right]]
     if h * w < 4 * min_size:
-        outs = [model(c) for c in chops]
+        # the four quadrants have the same shape: ONE batched forward on the device (the reference runs them one at a time
+        # through P.data_parallel(model, x, range(1)), utils/util.py:104-113)
+        n = chops[0].shape[0]
+        y = model(torch.cat([c.contiguous() for c in chops], 0))
+        outs = [y[i * n:(i + 1) * n] for i in range(4)]
     else:
         outs = [forward_chop(c, scale, model, shave=shave, min_size=min_size) for c in chops]
     h, w = scale * h, scale * w

@@ -249,6 +249,10 @@ int dasr_bn_lrelu_fwd(const float* x, float* y, const float* gamma, const float*
 int dasr_bn_lrelu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, float* dx,
                       float* dgamma, float* dbeta, long M, int C, int training, float slope, void* stream);
 
+/* nn.PixelShuffle(r) on NHWC fp32: in [N,H,W,C*r*r] -> out [N,H*r,W*r,C] (block.py:838-851, sr_resnet upsampler);
+ * inverse = 1: the backward gather (in [N,H*r,W*r,C] -> out [N,H,W,C*r*r]).  H, W are the LOW-resolution dims. */
+int dasr_pixel_shuffle(const float* in, float* out, int N, int H, int W, int C, int r, int inverse, void* stream);
+
 /* Domain-distance map: out[n,y,x] = mean of patch[n,i,j] over the patch positions whose receptive-field window covers
  * (y,x) (codes/DSN/receptive_cal.py:34-60, create_dataset_modified.py:14-24).  ilo/ihi[H], jlo/jhi[W]: inclusive range
  * of patch rows / columns covering each coordinate (device int arrays; empty range = lo > hi -> NaN like the

@@ -403,3 +403,68 @@ def test_ops_refuse_cpu_tensors():
     net = RRDBNet(3, 3, 64, 1)
     with pytest.raises(DasrError):
         net(torch.rand(1, 3, 8, 8))
+
+
+@pytest.mark.parametrize('min_size', [160000, 300])
+def test_forward_chop_matches_stitched_oracle_quadrants(min_size):
+    """utils/util.py:87-147 forward_chop (4 overlapping quadrants, `shave` px, recursive above min_size) with the quadrants
+    batched into one device forward: equals the stitching of the oracle's per-quadrant forwards."""
+    from dasr_b200.srn.utils.util import forward_chop
+    nb, scale, shave = 1, 4, 6
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 141, 0.3)
+    net = build_G(nb, sd).eval()
+    net.precision = 'fp32'
+    x = O.synth_image((1, 3, 44, 36), 142)
+
+    def ref_chop(img):
+        h, w = img.shape[-2:]
+        tb = (slice(0, h // 2 + shave), slice(h - h // 2 - shave, h))
+        lr = (slice(0, w // 2 + shave), slice(w - w // 2 - shave, w))
+        parts = [img[..., a, b] for a in tb for b in lr]
+        outs = [O.rrdbnet_forward(c, sd, nb) if h * w < 4 * min_size else ref_chop(c) for c in parts]
+        H, W = scale * h, scale * w
+        y = torch.empty((img.shape[0], 3, H, W))
+        y[..., :H // 2, :W // 2] = outs[0][..., :H // 2, :W // 2]
+        y[..., :H // 2, W - W // 2:] = outs[1][..., :H // 2, W // 2 - W:]
+        y[..., H - H // 2:, :W // 2] = outs[2][..., H // 2 - H:, :W // 2]
+        y[..., H - H // 2:, W - W // 2:] = outs[3][..., H // 2 - H:, W // 2 - W:]
+        return y
+    with torch.no_grad():
+        got = forward_chop(x.cuda(), scale, net, shave=shave, min_size=min_size)
+        ref = ref_chop(x)
+    assert got.shape == ref.shape == (1, 3, 176, 144)
+    assert rel_linf(got, ref) < FP32_TOL
+
+
+def test_sr_model_test_x8_self_ensemble_vs_oracle():
+    """SRModel.test_x8 (SR_model.py:102-140): mean over the 8 dihedral views, each mapped back."""
+    from dasr_b200.srn.models import create_model
+    nb = 1
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 151, 0.3)
+    model = create_model(make_opt(False, 'sr', nb))
+    unwrap(model.netG).load_state_dict(sd)
+    unwrap(model.netG).precision = 'fp32'
+    x = O.synth_image((1, 3, 12, 20), 152)
+    model.feed_data({'LR': x})
+    model.test_x8()
+    outs = []
+    for t in (False, True):
+        for hf in (False, True):
+            for vf in (False, True):
+                v = x
+                if vf:
+                    v = v.flip(3)
+                if hf:
+                    v = v.flip(2)
+                if t:
+                    v = v.transpose(2, 3)
+                o = O.rrdbnet_forward(v.contiguous(), sd, nb)
+                if t:
+                    o = o.transpose(2, 3)
+                if hf:
+                    o = o.flip(2)
+                if vf:
+                    o = o.flip(3)
+                outs.append(o)
+    ref = torch.stack(outs, 0).mean(0)
+    assert rel_linf(model.fake_H, ref) < FP32_TOL
