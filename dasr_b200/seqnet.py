@@ -52,11 +52,12 @@ def forward_nhwc(a, layers, params, save=True):
                 wt = wt.view(*L['view'])
             bs = params[L['b']] if L['b'] is not None else None
             n, h, w, _ = cur.shape
-            oh, ow = _out_hw(h, L['k'], L['s'], L['p']), _out_hw(w, L['k'], L['s'], L['p'])
+            ups = L.get('ups', 1)
+            oh, ow = _out_hw(h * ups, L['k'], L['s'], L['p']), _out_hw(w * ups, L['k'], L['s'], L['p'])
             if oh <= 0 or ow <= 0:
                 raise ops._lib.DasrError('input %dx%d too small for the network' % (H, W))
             o = torch.empty((n, oh, ow, wt.shape[0]), dtype=torch.float32, device=x.device)
-            ops.conv2d_f32(cur, ops.pack_filter_f32(wt), bs, o, L['k'], L['s'], L['p'], act=L.get('act', ACT_NONE), slope=0.2)
+            ops.conv2d_f32(cur, ops.pack_filter_f32(wt), bs, o, L['k'], L['s'], L['p'], ups=ups, act=L.get('act', ACT_NONE), slope=0.2)
             aux.append(None)
         elif op == 'prelu':
             o = torch.empty_like(cur)
@@ -70,7 +71,8 @@ def forward_nhwc(a, layers, params, save=True):
         elif op == 'bn_lrelu':
             st = torch.empty((cur.shape[3], 2), dtype=torch.float32, device=x.device)
             o = torch.empty_like(cur)
-            ops.bn_lrelu_fwd(cur, o, params[L['w']], params[L['b']], L['rm'], L['rv'], st, 1e-5, 0.1, L['training'], 0.2)
+            ops.bn_lrelu_fwd(cur, o, params[L['w']], params[L['b']], L['rm'], L['rv'], st, L.get('eps', 1e-5), L.get('momentum', 0.1),
+                             L['training'], L.get('slope', 0.2))
             if L['training'] and L.get('nbt') is not None:
                 L['nbt'].add_(1)
             aux.append(st)
@@ -90,7 +92,7 @@ def forward_nhwc(a, layers, params, save=True):
             aux.append(None)
         elif op == 'res_end':
             skip = res_stack.pop()
-            ops.axpby(cur, 1.0, skip, 1.0, cur)
+            ops.axpby(cur, L.get('scale', 1.0), skip, 1.0, cur)
             o = cur
             aux.append(None)
         else:
@@ -143,10 +145,17 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
                 db = None
                 if L['b'] is not None:
                     db = grads[L['b']] = torch.empty_like(params[L['b']], dtype=torch.float32)
-                ops.conv2d_wgrad_f32(acts[li], g, gw, db, L['k'], L['s'], L['p'])
+                ops.conv2d_wgrad_f32(acts[li], g, gw, db, L['k'], L['s'], L['p'], ups=L.get('ups', 1))
             if li > first_conv or need_dx:
-                gin = torch.empty(tuple(acts[li].shape), dtype=torch.float32, device=dout.device)
-                ops.conv2d_f32(g, ops.pack_filter_f32(wt, for_dgrad=True), None, gin, L['k'], L['s'], L['p'], mode=DGRAD)
+                if L.get('ups', 1) == 2:            # gradient w.r.t. the (virtual) nearest-upsampled tensor, then the 2x2 block sums
+                    n_, h_, w_, c_ = acts[li].shape
+                    gup = torch.empty((n_, 2 * h_, 2 * w_, c_), dtype=torch.float32, device=dout.device)
+                    ops.conv2d_f32(g, ops.pack_filter_f32(wt, for_dgrad=True), None, gup, L['k'], L['s'], L['p'], mode=DGRAD)
+                    gin = torch.empty((n_, h_, w_, c_), dtype=torch.float32, device=dout.device)
+                    ops.upsample2x_bwd(gup, gin)
+                else:
+                    gin = torch.empty(tuple(acts[li].shape), dtype=torch.float32, device=dout.device)
+                    ops.conv2d_f32(g, ops.pack_filter_f32(wt, for_dgrad=True), None, gin, L['k'], L['s'], L['p'], mode=DGRAD)
                 g = gin
         elif op == 'prelu':
             gz = torch.empty_like(g)
@@ -163,7 +172,7 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
             gz = torch.empty_like(g)
             dgm = torch.empty_like(params[L['w']], dtype=torch.float32) if need_dw else None
             dbt = torch.empty_like(params[L['b']], dtype=torch.float32) if need_dw else None
-            ops.bn_lrelu_bwd(acts[li], acts[li + 1], g, params[L['w']], aux[li], gz, dgm, dbt, L['training'], 0.2)
+            ops.bn_lrelu_bwd(acts[li], acts[li + 1], g, params[L['w']], aux[li], gz, dgm, dbt, L['training'], L.get('slope', 0.2))
             if need_dw:
                 grads[L['w']], grads[L['b']] = dgm, dbt
             g = gz
@@ -177,6 +186,10 @@ def backward_nhwc(ctx, layers, params, g, need_dx=True, need_dw=True):
             g = gz
         elif op == 'res_end':
             skip_stack.append(g)            # the same gradient feeds the skip connection and the residual branch
+            if L.get('scale', 1.0) != 1.0:
+                gb = torch.empty_like(g)
+                ops.axpby(g, L['scale'], None, 0.0, gb)
+                g = gb
         elif op == 'res_begin':
             gs = skip_stack.pop()
             ops.axpby(g, 1.0, gs, 1.0, g)
@@ -199,3 +212,121 @@ class SeqFunction(torch.autograd.Function):
         # ctx.saved is kept: the DSN iteration back-propagates through D(fake) twice (D loss, then G loss)
         dx, grads = backward(ctx.saved, ctx.layers, [p.detach() for p in ctx.params], dout, ctx.need_dx, ctx.need_dw)
         return (dx, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# module tree -> layer list
+# --------------------------------------------------------------------------------------------------
+
+def compile_sequence(mods, prefix, training, out_channels=None):
+    """Layer list for a flat list of (name, module) pairs as the reference's B.sequential / nn.Sequential produce them:
+    Conv2d [+ BatchNorm2d] [+ LeakyReLU(0.2) | ReLU], nn.Upsample(2, nearest) + Conv2d, nn.PixelShuffle, nn.Linear
+    (as a k x k valid conv over the feature map it flattens), ShortcutBlock / ResNetBlock (residual), nested Sequentials.
+    Parameter references are NAMES relative to the root module (`prefix` + child name); run() resolves them."""
+    import torch.nn as nn
+    layers = []
+    state = {'c': out_channels}
+    i, n = 0, len(mods)
+
+    def act_of(j):
+        """(act kind | None, modules consumed) for the activation at position j"""
+        if j < n and isinstance(mods[j][1], nn.LeakyReLU):
+            if abs(mods[j][1].negative_slope - 0.2) > 1e-12:
+                raise NotImplementedError('LeakyReLU slope %r' % mods[j][1].negative_slope)
+            return ACT_LRELU, 1
+        if j < n and isinstance(mods[j][1], nn.ReLU):
+            return ops.ACT_RELU, 1
+        return ACT_NONE, 0
+
+    pending_ups = 1
+    while i < n:
+        name, m = mods[i]
+        full = prefix + name
+        if isinstance(m, nn.Upsample):
+            if m.mode != 'nearest' or float(m.scale_factor) != 2.0:
+                raise NotImplementedError('only nearest x2 upsampling is on the path')
+            pending_ups = 2
+            i += 1
+        elif isinstance(m, nn.Conv2d):
+            if m.groups != 1 or m.dilation != (1, 1) or m.kernel_size[0] != m.kernel_size[1]:
+                raise NotImplementedError('grouped / dilated / non-square convs are not on the path')
+            L = {'op': 'conv', 'k': m.kernel_size[0], 's': m.stride[0], 'p': m.padding[0], 'w': full + '.weight',
+                 'b': (full + '.bias') if m.bias is not None else None, 'act': ACT_NONE}
+            if pending_ups != 1:
+                L['ups'] = pending_ups
+                pending_ups = 1
+            state['c'] = m.out_channels
+            j = i + 1
+            if j < n and isinstance(mods[j][1], nn.BatchNorm2d):
+                bn, bname = mods[j][1], prefix + mods[j][0]
+                a, used = act_of(j + 1)
+                slope = 0.2 if a == ACT_LRELU else (0.0 if a == ops.ACT_RELU else 1.0)
+                layers.append(L)
+                layers.append({'op': 'bn_lrelu', 'w': bname + '.weight', 'b': bname + '.bias', 'rm': bn.running_mean, 'rv': bn.running_var,
+                               'nbt': bn.num_batches_tracked, 'training': training, 'slope': slope, 'eps': bn.eps,
+                               'momentum': bn.momentum if bn.momentum is not None else 0.1})
+                i = j + 1 + used
+            else:
+                a, used = act_of(j)
+                L['act'] = a
+                layers.append(L)
+                i = j + used
+        elif isinstance(m, nn.BatchNorm2d):          # 'NAC' order: norm -> act -> conv
+            a, used = act_of(i + 1)
+            slope = 0.2 if a == ACT_LRELU else (0.0 if a == ops.ACT_RELU else 1.0)
+            layers.append({'op': 'bn_lrelu', 'w': full + '.weight', 'b': full + '.bias', 'rm': m.running_mean, 'rv': m.running_var,
+                           'nbt': m.num_batches_tracked, 'training': training, 'slope': slope, 'eps': m.eps,
+                           'momentum': m.momentum if m.momentum is not None else 0.1})
+            i += 1 + used
+        elif isinstance(m, nn.PixelShuffle):
+            a, used = act_of(i + 1)
+            if used:      # conv -> PixelShuffle -> act (block.py:838-851): the activation commutes with the shuffle -> conv epilogue
+                if not layers or layers[-1]['op'] != 'conv' or layers[-1]['act'] != ACT_NONE:
+                    raise NotImplementedError('activation after PixelShuffle without a preceding plain conv')
+                layers[-1]['act'] = a
+            layers.append({'op': 'pixel_shuffle', 'r': m.upscale_factor})
+            state['c'] = state['c'] // (m.upscale_factor ** 2) if state['c'] else None
+            i += 1 + used
+        elif isinstance(m, nn.Linear):
+            c = state['c']
+            k = int(round((m.in_features / c) ** 0.5)) if c else 1
+            if c is None or c * k * k != m.in_features:
+                c, k = m.in_features, 1
+            a, used = act_of(i + 1)
+            layers.append({'op': 'conv', 'k': k, 's': 1, 'p': 0, 'w': full + '.weight', 'b': (full + '.bias') if m.bias is not None else None,
+                           'act': a, 'view': (m.out_features, c, k, k)})
+            state['c'] = m.out_features
+            i += 1 + used
+        elif isinstance(m, nn.Sequential):
+            sub = compile_sequence(list(m.named_children()), full + '.', training, state['c'])
+            layers += sub
+            i += 1
+        elif m.__class__.__name__ == 'ShortcutBlock':
+            inner = m.sub
+            kids = list(inner.named_children()) if isinstance(inner, nn.Sequential) else [('', inner)]
+            pre = full + '.sub.' if isinstance(inner, nn.Sequential) else full + '.sub'
+            layers += [{'op': 'res_begin'}] + compile_sequence(kids, pre, training, state['c']) + [{'op': 'res_end'}]
+            i += 1
+        elif m.__class__.__name__ == 'ResNetBlock':
+            kids = list(m.res.named_children())
+            layers += [{'op': 'res_begin'}] + compile_sequence(kids, full + '.res.', training, state['c']) + [{'op': 'res_end', 'scale': float(m.res_scale)}]
+            i += 1
+        elif isinstance(m, (nn.LeakyReLU, nn.ReLU)):
+            raise NotImplementedError('a free-standing activation (not after a conv / norm / linear) is not on the path')
+        else:
+            raise NotImplementedError('module %s (%s) is not on the B200 path' % (full, m.__class__.__name__))
+    return layers
+
+
+def run_module(root, x, layers_by_name):
+    """Resolve parameter names against root.named_parameters() and run the layer list as ONE autograd node."""
+    named = list(root.named_parameters())
+    idx = {k: i for i, (k, _) in enumerate(named)}
+    layers = []
+    for L in layers_by_name:
+        L = dict(L)
+        for key in ('w', 'b', 'a'):
+            if isinstance(L.get(key), str):
+                L[key] = idx[L[key]]
+        layers.append(L)
+    return SeqFunction.apply(x, layers, *[p for _, p in named])

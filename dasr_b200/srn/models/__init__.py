@@ -10,6 +10,10 @@ def create_model(opt):
     model = opt['model']
     if model == 'sr':
         from .SR_model import SRModel as M
+    elif model == 'srgan':
+        from .SRGAN_model import SRGANModel as M
+    elif model == 'srragan':
+        from .SRRaGAN_model import SRRaGANModel as M
     elif model in ('DASR', 'DASR_FS_ESRGAN_patchGAN'):
         from .DASR_model import DASR_Model as M
     else:

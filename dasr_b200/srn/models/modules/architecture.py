@@ -327,6 +327,9 @@ class FilterHigh(nn.Module):
         return img - self.filter_low(img)
 
 
+from .sr_nets import Discriminator_VGG_128, Discriminator_VGG_192, SRResNet  # noqa: E402,F401
+
+
 def __getattr__(name):
     """FS_Discriminator / DiscriminatorBasic (architecture.py:833-870,922-980) live in the DSN drop-in, which imports the
     filters from this module — resolved lazily to avoid the import cycle."""

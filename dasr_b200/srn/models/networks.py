@@ -81,6 +81,10 @@ def define_G(opt):
         netG = arch.RRDBNet(in_nc=opt_net['in_nc'], out_nc=opt_net['out_nc'], nf=opt_net['nf'], nb=opt_net['nb'],
                             gc=opt_net['gc'], upscale=opt_net['scale'], norm_type=opt_net['norm_type'],
                             act_type='leakyrelu', mode=opt_net['mode'], upsample_mode='upconv')
+    elif which == 'sr_resnet':      # networks.py:88-91
+        netG = arch.SRResNet(in_nc=opt_net['in_nc'], out_nc=opt_net['out_nc'], nf=opt_net['nf'], nb=opt_net['nb'],
+                             upscale=opt_net['scale'], norm_type=opt_net['norm_type'], act_type='relu', mode=opt_net['mode'],
+                             upsample_mode='pixelshuffle')
     else:
         raise NotImplementedError('Generator model [{:s}] not recognized'.format(str(which)))
     if opt['is_train']:
@@ -92,6 +96,11 @@ def _patch_discriminator(opt_net, key):
     which = opt_net[key]
     if which == 'discriminator_patch':
         return arch.NLayerDiscriminator(opt_net['in_nc'], n_layers=opt_net['n_layers'])
+    if which == 'discriminator_vgg_128':      # networks.py:156-159
+        return arch.Discriminator_VGG_128(in_nc=opt_net['in_nc'], nf=opt_net['nf'])
+    if which == 'discriminator_vgg_192':      # networks.py:170-172
+        return arch.Discriminator_VGG_192(in_nc=opt_net['in_nc'], base_nf=opt_net['nf'], norm_type=opt_net['norm_type'],
+                                          mode=opt_net['mode'], act_type=opt_net['act_type'])
     raise NotImplementedError('Discriminator model [{:s}] not recognized'.format(str(which)))
 
 
