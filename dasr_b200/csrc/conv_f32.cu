@@ -318,11 +318,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   long total = (long)K * cout;
   if (i >= total) return;
   int k = (int)(i / cout), co = (int)(i - (long)k * cout);
-  float s = 0.f;
-  for (int sp = 0; sp < splits; sp++) s += part[(long)sp * total + i];
+  // the per-split partials (<= 256 pixels each, fp32) are combined in double: a filter gradient is a sum of P signed
+  // products whose magnitude is ~sqrt(P) of the sum of their absolute values, so fp32 rounding of a 128-term running sum
+  // shows up ~sqrt(P) times larger in the result (first-layer gradients of the 128^2 / 192^2 discriminators: 1e-3 -> 1e-5)
+  double s = 0.0;
+  for (int sp = 0; sp < splits; sp++) s += (double)part[(long)sp * total + i];
   int tap = k / cin, ci = k - tap * cin;
   long o = ((long)co * cin + ci) * ntaps + tap;
-  dw[o] = accumulate ? dw[o] + s : s;
+  dw[o] = accumulate ? dw[o] + (float)s : (float)s;
 }
 
 // bias gradient: column sums of dout, two-stage deterministic
@@ -340,9 +343,9 @@ __global__ void bgrad_reduce_kernel(const float* __restrict__ part, float* __res
                                     int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cout) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; b++) s += part[(long)b * cout + c];
-  db[c] = accumulate ? db[c] + s : s;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; b++) s += (double)part[(long)b * cout + c];
+  db[c] = accumulate ? db[c] + (float)s : (float)s;
 }
 
 __global__ void pack_filter_f32_kernel(const float* __restrict__ w, float* __restrict__ o, int cout, int cin,
