@@ -62,7 +62,7 @@ def test_create_model_state_dict_contract_and_cpu_refusal():
         model.feed_data(data, True)
         model.optimize_parameters(1)
     with pytest.raises(NotImplementedError):
-        create_model(make_opt(True, 'srgan', gpu=False))
+        create_model(make_opt(True, 'De_Resnet', gpu=False))      # dead duplicate of codes/DSN in the reference
 
 
 def test_save_load_checkpoint_roundtrip(tmp_path):
