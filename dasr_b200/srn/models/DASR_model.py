@@ -43,6 +43,14 @@ def _params_frozen(net):
             p.requires_grad_(True)
 
 
+def _ragan_pair(cri_gan, pred_real, pred_fake, for_G):
+    """Relativistic average GAN term of the generator (DASR_model.py:242-246): each set's scores relative to the batch
+    mean (dim 0, per patch position) of the other set; the real scores carry no gradient."""
+    pred_real = pred_real.detach()
+    return (cri_gan(pred_fake - pred_real.mean(0, keepdim=True), True) +
+            cri_gan(pred_real - pred_fake.mean(0, keepdim=True), False)) / 2
+
+
 class DASR_Model(BaseModel):
     def __init__(self, opt):
         super().__init__(opt)
@@ -58,8 +66,6 @@ class DASR_Model(BaseModel):
         self.l_gan_H_source_w = train_opt.get('gan_H_source') or 0
         if self.is_train:
             self.cri_gan = L.GANLoss(train_opt['gan_type'], 1.0, 0.0).to(self.device)
-            if self.ragan:
-                raise NotImplementedError('ragan: true needs cross-batch means (not in any shipped SRN config; SURVEY §8e)')
             if train_opt['gan_type'] == 'wgan-gp':
                 raise NotImplementedError('wgan-gp gradient penalty (double backward) is not on the B200 path')
 
@@ -199,12 +205,28 @@ class DASR_Model(BaseModel):
             if self.l_gan_H_target_w > 0:
                 with _params_frozen(self.netD_target):
                     pred_g_Hf_target_fake = self.netD_target(self.fake_SR_Hf_target)
-                l_g_gan_target_Hf = self.cri_gan(pred_g_Hf_target_fake, True)
+                    if self.ragan:
+                        with torch.no_grad():
+                            pred_g_Hf_target_real = self.netD_target(self.real_HR_Hf_target)
+                if self.ragan:
+                    # relativistic average: scores relative to the other set's batch mean (DASR_model.py:242-246; the weight
+                    # is applied here AND below, as the reference does)
+                    l_g_gan_target_Hf = self.l_gan_H_target_w * _ragan_pair(self.cri_gan, pred_g_Hf_target_real,
+                                                                             pred_g_Hf_target_fake, True)
+                else:
+                    l_g_gan_target_Hf = self.cri_gan(pred_g_Hf_target_fake, True)
                 l_g_total += self.l_gan_H_target_w * l_g_gan_target_Hf
             if self.l_gan_H_source_w > 0:
                 with _params_frozen(self.netD_source):
                     pred_g_Hf_source_fake = self.netD_source(self.fake_SR_Hf_source)
-                l_g_gan_source_Hf = self.l_gan_H_source_w * self.cri_gan(pred_g_Hf_source_fake, True)
+                    if self.ragan:
+                        with torch.no_grad():
+                            pred_g_Hf_source_real = self.netD_source(self.real_HR_Hf_source)
+                if self.ragan:
+                    l_g_gan_source_Hf = self.l_gan_H_source_w * _ragan_pair(self.cri_gan, pred_g_Hf_source_real,
+                                                                             pred_g_Hf_source_fake, True)
+                else:
+                    l_g_gan_source_Hf = self.l_gan_H_source_w * self.cri_gan(pred_g_Hf_source_fake, True)
                 l_g_total += l_g_gan_source_Hf
             self.optimizer_G.zero_grad()
             l_g_total.backward()
@@ -220,8 +242,12 @@ class DASR_Model(BaseModel):
                 nreal = self.real_HR_Hf_target.shape[0]
                 pred_d = self.netD_target(torch.cat([self.real_HR_Hf_target.detach(), self.fake_SR_Hf_target.detach()], 0))
                 pred_d_target_real, pred_d_target_fake = pred_d[:nreal], pred_d[nreal:]
-                l_d_target_real = self.cri_gan(pred_d_target_real, True)
-                l_d_target_fake = self.cri_gan(pred_d_target_fake, False)
+                if self.ragan:
+                    l_d_target_real = self.cri_gan(pred_d_target_real - pred_d_target_fake.mean(0, keepdim=True), True)
+                    l_d_target_fake = self.cri_gan(pred_d_target_fake - pred_d_target_real.mean(0, keepdim=True), False)
+                else:
+                    l_d_target_real = self.cri_gan(pred_d_target_real, True)
+                    l_d_target_fake = self.cri_gan(pred_d_target_fake, False)
                 l_d_target_total = (l_d_target_real + l_d_target_fake) / 2
                 self.optimizer_D_target.zero_grad()
                 l_d_target_total.backward()
@@ -230,8 +256,12 @@ class DASR_Model(BaseModel):
             if self.l_gan_H_source_w > 0:
                 pred_d_source_real = self.netD_source(self.real_HR_Hf_source.detach())
                 pred_d_source_fake = self.netD_source(self.fake_SR_Hf_source.detach())
-                l_d_source_real = self.cri_gan(pred_d_source_real, True)
-                l_d_source_fake = self.cri_gan(pred_d_source_fake, False)
+                if self.ragan:
+                    l_d_source_real = self.cri_gan(pred_d_source_real - pred_d_source_fake.mean(0, keepdim=True), True)
+                    l_d_source_fake = self.cri_gan(pred_d_source_fake - pred_d_source_real.mean(0, keepdim=True), False)
+                else:
+                    l_d_source_real = self.cri_gan(pred_d_source_real, True)
+                    l_d_source_fake = self.cri_gan(pred_d_source_fake, False)
                 l_d_source_total = (l_d_source_fake + l_d_source_real) / 2
                 self.optimizer_D_source.zero_grad()
                 l_d_source_total.backward()

@@ -139,7 +139,7 @@ def gen_misc():
 
 
 # ---------------------------------------------------------------- G5: DASR_Model train steps, G6: SRModel test
-def make_opt(is_train, model, nb=1, fs='wavelet'):
+def make_opt(is_train, model, nb=1, fs='wavelet', ragan=False):
     opt = {
         'name': 'golden', 'model': model, 'scale': 4, 'gpu_ids': None, 'is_train': is_train, 'chop': False,
         'val_lpips': False, 'multiweights': True,
@@ -153,7 +153,7 @@ def make_opt(is_train, model, nb=1, fs='wavelet'):
         'train': {'lr_G': 5e-5, 'weight_decay_G': 0, 'beta1_G': 0.9, 'lr_D': 5e-5, 'weight_decay_D': 0, 'beta1_D': 0.9,
                   'lr_scheme': 'MultiStepLR', 'lr_steps': [50000, 80000], 'lr_gamma': 0.5, 'fs': fs, 'norm': True,
                   'sup_LL': True, 'fs_kernel_size': 5, 'pixel_criterion': 'l1', 'pixel_weight': 1, 'pixel_LL_weight': 1,
-                  'feature_criterion': 'l1', 'feature_weight': 1e-2, 'gan_type': 'vanilla', 'ragan': False,
+                  'feature_criterion': 'l1', 'feature_weight': 1e-2, 'gan_type': 'vanilla', 'ragan': ragan,
                   'gan_H_target': 1e-4, 'gan_H_source': 0, 'G_update_inter': 1, 'D_update_inter': 1,
                   'D_update_ratio': 1, 'D_init_iters': 0, 'manual_seed': 0, 'niter': 10, 'val_freq': 10},
     }
@@ -166,9 +166,9 @@ def synth_batch(B, h, w, seed):
             'fake_w': O.synth_image((B, 1, h, w), seed + 4)}
 
 
-def gen_dasr_step(fs, name):
+def gen_dasr_step(fs, name, ragan=False):
     nb = 1
-    model = create_model(make_opt(True, 'DASR', nb, fs))
+    model = create_model(make_opt(True, 'DASR', nb, fs, ragan))
     in_nc_d = 9 if fs == 'wavelet' else 3
     sdG = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), seed=5, gain=0.3)
     sdD = O.synth_state_dict(O.nlayer_d_shapes(in_nc_d, 64, 2), seed=6, gain=1.0)
@@ -179,7 +179,7 @@ def gen_dasr_step(fs, name):
     B, h, w = 2, 8, 8
     keepG = ['model.0.weight', 'model.1.sub.0.RDB1.conv1.0.bias', 'model.1.sub.0.RDB2.conv5.0.weight', 'model.10.weight']
     keepD = ['model.0.weight', 'model.8.weight', 'model.8.bias']
-    rec = dict(nb=nb, B=B, h=h, w=w, fs=fs, data_seeds=[51, 61], wG_seed=5, wD_seed=6, wF_seed=7, gain_G=0.3, steps=[])
+    rec = dict(nb=nb, B=B, h=h, w=w, fs=fs, data_seeds=[51, 61], wG_seed=5, wD_seed=6, wF_seed=7, gain_G=0.3, ragan=ragan, steps=[])
     for step, seed in enumerate(rec['data_seeds'], 1):
         model.update_learning_rate() if False else None  # train.py:105 steps schedulers first; LR unchanged before 50k iters
         model.feed_data(synth_batch(B, h, w, seed), True)
@@ -196,6 +196,11 @@ def gen_dasr_step(fs, name):
             D_delta_norm=float(sum(((D[k] - sdD[k]).double() ** 2).sum() for k in D) ** 0.5)))
         print('  step', step, {k: round(v, 6) for k, v in log.items()})
     save(name, rec)
+
+
+def gen_dasr_ragan():
+    """`ragan: true` (DASR_model.py:242-247,273-275): relativistic average terms in the G and D losses."""
+    gen_dasr_step('gau', 'dasr_step_ragan.pt', ragan=True)
 
 
 def gen_sr_test():
@@ -228,4 +233,5 @@ if __name__ == '__main__':
     gen_misc()
     gen_dasr_step('wavelet', 'dasr_step_wavelet.pt')
     gen_dasr_step('gau', 'dasr_step_gau.pt')
+    gen_dasr_ragan()
     gen_sr_test()

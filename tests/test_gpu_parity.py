@@ -341,14 +341,16 @@ def test_weighted_l1_and_l1_grad():
 from helpers import make_opt, unwrap  # noqa: E402
 
 
-@pytest.mark.parametrize('name', ['dasr_step_wavelet.pt', 'dasr_step_gau.pt'])
+@pytest.mark.parametrize('name', ['dasr_step_wavelet.pt', 'dasr_step_gau.pt', 'dasr_step_ragan.pt'])
 def test_dasr_model_train_steps_vs_golden(golden, name):
     """create_model -> feed_data -> optimize_parameters x2 through the public API, against the log values
     and post-step weights the reference produced for the same inputs (oracle/gen_golden.py)."""
     from dasr_b200.srn.models import create_model
     g = golden(name)
     fs = g['fs']
-    model = create_model(make_opt(True, 'DASR', g['nb'], fs))
+    opt = make_opt(True, 'DASR', g['nb'], fs)
+    opt['train']['ragan'] = bool(g.get('ragan', False))        # dasr_step_ragan.pt: relativistic average GAN terms
+    model = create_model(opt)
     unwrap(model.netG).load_state_dict(O.synth_state_dict(O.rrdbnet_shapes(nb=g['nb']), g['wG_seed'], g['gain_G']))
     unwrap(model.netD_target).load_state_dict(O.synth_state_dict(O.nlayer_d_shapes(9 if fs == 'wavelet' else 3, 64, 2), g['wD_seed'], 1.0))
     unwrap(model.netF).load_state_dict(O.synth_state_dict(O.vgg19_shapes(34), g['wF_seed'], 1.0), strict=False)
