@@ -47,7 +47,7 @@ class ConvTcParams(C.Structure):
         ('mask_slope', C.c_float),
         ('a_mode', C.c_int), ('epi_mode', C.c_int), ('act_cols', C.c_int),
         ('pre_cs', C.c_int), ('pre_coff', C.c_int), ('out_nc', C.c_int), ('tile_rev', C.c_int),
-        ('nchunk_list', C.c_int), ('chunk_off', C.c_int * 8),
+        ('nchunk_list', C.c_int), ('chunk_off', C.c_int * 8), ('f16', C.c_int),
     ]
 
 

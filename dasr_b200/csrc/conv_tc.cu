@@ -173,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const uint32_t mi = (warp == 1) ? 0u : 1u;
     // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the tcgen05.mma
     // instructions, so descriptors live in uniform registers and no per-lane serialisation is emitted.
-    const uint32_t idesc = make_idesc_bf16(128, nt);
+    const uint32_t idesc = make_idesc_16(128, nt, p.f16);
     const uint32_t a_sbo = (p.a_mode == 0) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
     const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
     const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
@@ -322,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int co_base = ntile * nt;
     const int OW = p.W * p.out_mul, OH = p.H * p.out_mul;
     const int ngroups = nt >> 4;
-    const int act = p.act;
+    const int act = p.act, f16 = p.f16;
     const float slope = p.slope, alpha = p.alpha;
     const bool scale = alpha != 1.f;
     const int sw64 = (m >> 1) & 3, sw128 = m & 7;
@@ -385,8 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             o1 = base + (((c0 + 1) ^ sw64) << 4);
           }
           if constexpr (HAS_PRE) {
-            fma_bf16x8(v, lds128(bS + o0), 1.f);
-            fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
+            fma_h16x8(v, lds128(bS + o0), 1.f, f16);
+            fma_h16x8(v + 8, lds128(bS + o1), 1.f, f16);
           }
           if (do_act) {
             if (act == DASR_ACT_LRELU) {
@@ -402,17 +402,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
           if constexpr (NRES >= 1) {
-            fma_bf16x8(v, lds128(bR1 + o0), p.beta1);
-            fma_bf16x8(v + 8, lds128(bR1 + o1), p.beta1);
+            fma_h16x8(v, lds128(bR1 + o0), p.beta1, f16);
+            fma_h16x8(v + 8, lds128(bR1 + o1), p.beta1, f16);
           }
           if constexpr (NRES >= 2) {
-            fma_bf16x8(v, lds128(bR2 + o0), p.beta2);
-            fma_bf16x8(v + 8, lds128(bR2 + o1), p.beta2);
+            fma_h16x8(v, lds128(bR2 + o0), p.beta2, f16);
+            fma_h16x8(v + 8, lds128(bR2 + o1), p.beta2, f16);
           }
           uint4 o[2];
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pack_h16x16(v, o, f16);
           sts128(bS + o0, o[0]);
           sts128(bS + o1, o[1]);
         } else if (valid) {
@@ -433,13 +431,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             __nv_bfloat16* ob16 = reinterpret_cast<__nv_bfloat16*>(a.out);
             if (a.res1) {
               const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + opix * p.res1_cs + p.res1_coff + co);
-              fma_bf16x8(v, __ldg(rp), p.beta1);
-              fma_bf16x8(v + 8, __ldg(rp + 1), p.beta1);
+              fma_h16x8(v, __ldg(rp), p.beta1, f16);
+              fma_h16x8(v + 8, __ldg(rp + 1), p.beta1, f16);
             }
             if (a.res2) {
               const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + opix * p.res2_cs + p.res2_coff + co);
-              fma_bf16x8(v, __ldg(rp), p.beta2);
-              fma_bf16x8(v + 8, __ldg(rp + 1), p.beta2);
+              fma_h16x8(v, __ldg(rp), p.beta2, f16);
+              fma_h16x8(v + 8, __ldg(rp + 1), p.beta2, f16);
             }
             if (a.mask_src && co + 16 > p.mask_c0 && co < p.mask_c1) {
               const __nv_bfloat16* mp = a.mask_src + opix * p.mask_cs + p.mask_coff + (co - p.mask_c0);
@@ -453,9 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               }
             }
             uint4 o[2];
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-            for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pack_h16x16(v, o, f16);
             uint4* op = reinterpret_cast<uint4*>(ob16 + opix * p.out_cs + p.out_coff + co);
             op[0] = o[0];
             op[1] = o[1];
@@ -511,8 +507,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 //                                  tap (dy,dx) uses w[kco][nci][2-dy][2-dx]
 // kind 2: nearest-x2 + 3x3       : 4 variants (py,px), taps (a,b) in {0,1}^2; halo row = py + a,
 //                                  filter rows summed:  py=0: a=0 -> {0}, a=1 -> {1,2};  py=1: a=0 -> {0,1}, a=1 -> {2}
-__global__ void pack_filter_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int cout, int cin,
-                                      int kind) {
+__global__ void pack_filter_tc_kernel(const float* __restrict__ w, unsigned short* __restrict__ o, int cout, int cin,
+                                      int kind, int f16) {
   const int gn = (kind == 1) ? cin : cout;   // GEMM N (output channels of this conv)
   const int gk = (kind == 1) ? cout : cin;   // GEMM K channels
   const int nvar = (kind == 2) ? 4 : 1, ntaps = (kind == 2) ? 4 : 9, nchunks = gk / CHUNK;
@@ -540,7 +536,7 @@ __global__ void pack_filter_tc_kernel(const float* __restrict__ w, __nv_bfloat16
     for (int rr = r0; rr <= r1; rr++)
       for (int cc = c0; cc <= c1; cc++) v += w[((long)nn * cin + kk) * 9 + rr * 3 + cc];
   }
-  o[i] = __float2bfloat16(v);
+  o[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
 }
 
 // Batched form: one launch re-packs every filter of a network from a device-resident job table (training re-packs
@@ -707,6 +703,7 @@ extern "C" {
 int dasr_conv_tc_setup(DasrConvTcParams* p, int kind) {
   if (!p) return DASR_E_BADARG;
   p->nchunk_list = 0;
+  p->f16 = 0;
   if (kind == 0 || kind == 1) {
     p->nvar = 1;
     p->ntaps = 9;
@@ -742,11 +739,13 @@ size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind) {
 }
 
 int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, void* stream) {
+  const int f16 = (kind & DASR_TC_PACK_F16) != 0;      // IEEE half instead of bf16 (inference precision 'fp16')
+  kind &= ~DASR_TC_PACK_F16;
   DASR_REQUIRE(kind >= 0 && kind <= 2, "pack_filter_tc: kind");
   int gk = (kind == 1) ? cout : cin;
   DASR_REQUIRE(gk % CHUNK == 0, "pack_filter_tc: contraction channels (%d) must be a multiple of 32", gk);
   long total = (long)dasr_pack_filter_tc_bytes(cout, cin, kind) / 2;
-  pack_filter_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)o, cout, cin, kind);
+  pack_filter_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (unsigned short*)o, cout, cin, kind, f16);
   return check_launch("pack_filter_tc");
 }
 
@@ -792,6 +791,7 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   DASR_REQUIRE(p->nvar >= 1 && p->nvar <= 4 && p->ntaps >= 1 && p->ntaps <= 9, "conv_tc: variants/taps");
   DASR_REQUIRE(p->out_mul == 1 || p->out_mul == 2, "conv_tc: out_mul");
   DASR_REQUIRE(p->epi_mode >= 0 && p->epi_mode <= 2, "conv_tc: epi_mode");
+  DASR_REQUIRE(p->f16 == 0 || (p->f16 == 1 && !mask_src), "conv_tc: f16 must be 0/1; the dgrad mask input is bf16 only");
   DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc: act_cols must be a multiple of 16");
   if (p->epi_mode == 2) {
     DASR_REQUIRE(p->out_nc >= 1 && p->out_nc <= 16 && p->nt == p->cout && !res1 && !res2 && !pre && !mask_src,

@@ -148,7 +148,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_bf16(256, cout);
+      const uint32_t idesc = make_idesc_16(256, cout, p.f16);
       const uint32_t a_sbo = (uint32_t)(HALO_W * ROW_B);
       const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
       const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
@@ -250,7 +250,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int sw128 = m & 7, sw64 = (m >> 1) & 3;
-    const int act = p.act;
+    const int act = p.act, f16 = p.f16;
     const float slope = p.slope, alpha = p.alpha;
     const bool scale = alpha != 1.f;
     const uint32_t sS_u = smem_u32(sS), sR1_u = smem_u32(sR1), sR2_u = smem_u32(sR2), sBias_u = smem_u32(sBias);
@@ -306,8 +306,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
           const int sw = wide ? sw128 : sw64;
           const uint32_t o0 = (uint32_t)(((ch) ^ sw) << 4), o1 = (uint32_t)(((ch + 1) ^ sw) << 4);
           if constexpr (HAS_PRE) {
-            fma_bf16x8(v, lds128(bS + o0), 1.f);
-            fma_bf16x8(v + 8, lds128(bS + o1), 1.f);
+            fma_h16x8(v, lds128(bS + o0), 1.f, f16);
+            fma_h16x8(v + 8, lds128(bS + o1), 1.f, f16);
           }
           if (do_act) {
             if (act == DASR_ACT_LRELU) {
@@ -323,17 +323,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
           if constexpr (NRES >= 1) {
-            fma_bf16x8(v, lds128(bR1 + o0), p.beta1);
-            fma_bf16x8(v + 8, lds128(bR1 + o1), p.beta1);
+            fma_h16x8(v, lds128(bR1 + o0), p.beta1, f16);
+            fma_h16x8(v + 8, lds128(bR1 + o1), p.beta1, f16);
           }
           if constexpr (NRES >= 2) {
-            fma_bf16x8(v, lds128(bR2 + o0), p.beta2);
-            fma_bf16x8(v + 8, lds128(bR2 + o1), p.beta2);
+            fma_h16x8(v, lds128(bR2 + o0), p.beta2, f16);
+            fma_h16x8(v + 8, lds128(bR2 + o1), p.beta2, f16);
           }
           uint4 o[2];
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pack_h16x16(v, o, f16);
           sts128(bS + o0, o[0]);
           sts128(bS + o1, o[1]);
         }

@@ -11,6 +11,8 @@ template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat
 template <typename T> __device__ __forceinline__ void st(T* p, float v);
 template <> __device__ __forceinline__ void st<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+template <> __device__ __forceinline__ float ld<__half>(const __half* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ void st<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
 // ---- NCHW fp32 <-> NHWC (tile transpose through shared memory: coalesced on both sides) --------
 // one block handles 32 pixels x up to 32 channels
@@ -708,7 +710,9 @@ int dasr_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, i
   DASR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && dst_cs >= dst_coff + C, "nchw_to_nhwc: bad dims");
   long HW = (long)H * W;
   dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
-  if (dst_is_bf16)
+  if (dst_is_bf16 == 2)
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(src, (__half*)dst, C, HW, dst_cs, dst_coff, mean, stdv);
+  else if (dst_is_bf16)
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, HW, dst_cs,
                                                                                 dst_coff, mean, stdv);
   else
@@ -778,6 +782,11 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
                int d_cs, int d_coff, float a, float b, int is_bf16, void* stream) {
   DASR_REQUIRE(npix > 0 && C > 0 && x && dst, "axpby: bad arguments");
   long total = npix * C;
+  if (is_bf16 == 2) {
+    axpby_kernel<__half><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, (const __half*)y, (__half*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs, d_coff, a, b);
+    return check_launch("axpby");
+  }
   const bool vec = is_bf16 && C % 8 == 0 && x_cs % 8 == 0 && x_coff % 8 == 0 && d_cs % 8 == 0 && d_coff % 8 == 0 &&
                    (!y || (y_cs % 8 == 0 && y_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)) &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;

@@ -5,6 +5,7 @@
 // Test infrastructure only — nothing here is on the product path.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -169,6 +170,23 @@ static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
   for (size_t i = 0; i < v.size(); i++) o[i] = __float2bfloat16(v[i]);
   return o;
 }
+// 16-bit storage of the tensor-core conv tests: bf16, or IEEE half bits carried in the same 2-byte slots (g_f16)
+static int g_f16 = 0;
+static std::vector<__nv_bfloat16> to_h16(const std::vector<float>& v) {
+  if (!g_f16) return to_bf16(v);
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    __half h = __float2half_rn(v[i]);
+    memcpy(&o[i], &h, 2);
+  }
+  return o;
+}
+static inline float h16_to_float(__nv_bfloat16 x) {
+  if (!g_f16) return __bfloat162float(x);
+  __half h;
+  memcpy(&h, &x, 2);
+  return __half2float(h);
+}
 
 // tcgen05 conv vs CPU reference. kind 0 fprop, 1 dgrad, 2 upsample-fused
 // epi: 0 none, 1 = act+res1+mask (direct-store epilogue), 2 = staged epilogue with pre + act_cols + res1 + res2, 3 = NCHW fp32 out
@@ -228,9 +246,9 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
       if (c < ac) v = v > 0 ? v : v * slope;
       ref[i] = alpha * v;
     }
-  auto in_b = to_bf16(in);
-  auto res_b = to_bf16(res1);
-  auto msk_b = to_bf16(msk);
+  auto in_b = to_h16(in);
+  auto res_b = to_h16(res1);
+  auto msk_b = to_h16(msk);
   __nv_bfloat16* din = dalloc<__nv_bfloat16>(in_b.size());
   __nv_bfloat16* dres = dalloc<__nv_bfloat16>(res_b.size());
   __nv_bfloat16* dmsk = dalloc<__nv_bfloat16>(msk_b.size());
@@ -251,10 +269,11 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   p.pre_cs = gn; p.pre_coff = 0;
   p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
   p.a_mode = a_mode;
+  p.f16 = g_f16;
   p.epi_mode = (kind == 2 || epi == 1 || nt % 32) ? 1 : 0;
   float* dnchw = nullptr;
   if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
-  rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind, 0);
+  rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind | (g_f16 ? DASR_TC_PACK_F16 : 0), 0);
   // res2 for epi 2 = res1 shifted by one pixel (same buffer, pointer offset of gn elements, wraps at the end -> use a copy)
   __nv_bfloat16* dres2 = nullptr;
   if ((epi == 2 || epi == 5) && gn <= 96) {
@@ -271,7 +290,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
                        epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
-  snprintf(name, sizeof(name), "conv_tc kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
+  snprintf(name, sizeof(name), "conv_tc%s kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", g_f16 ? " f16" : "", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
   if (rc == DASR_E_SMEM && e == cudaSuccess) {
     printf("[SKIP] %s (does not fit shared memory in this A mode)\n", name);
     return;
@@ -298,16 +317,16 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     auto got = d2h(dout, (size_t)N * OH * OW * out_cs);
     // guard channels around the slice must be untouched (zero)
     for (size_t pix = 0; pix < (size_t)N * OH * OW; pix++) {
-      for (int c = 0; c < out_coff; c++) me = fmax(me, fabs(__bfloat162float(got[pix * out_cs + c])));
-      for (int c = out_coff + gn; c < out_cs; c++) me = fmax(me, fabs(__bfloat162float(got[pix * out_cs + c])));
+      for (int c = 0; c < out_coff; c++) me = fmax(me, fabs(h16_to_float(got[pix * out_cs + c])));
+      for (int c = out_coff + gn; c < out_cs; c++) me = fmax(me, fabs(h16_to_float(got[pix * out_cs + c])));
       for (int c = 0; c < gn; c++) {
         double r = ref[pix * gn + c];
-        double g = __bfloat162float(got[pix * out_cs + out_coff + c]);
+        double g = h16_to_float(got[pix * out_cs + out_coff + c]);
         me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
         mref = fmax(mref, fabs(r));
       }
     }
-    report(name, me, 8e-3);
+    report(name, me, g_f16 ? 1e-3 : 8e-3);      // output rounding: bf16 2^-8, half 2^-11 (relative to 1 + |ref|)
   }
   if (dres2) cudaFree(dres2);
   cudaFree(din); cudaFree(dres); cudaFree(dmsk); cudaFree(dout); cudaFree(dw); cudaFree(db); cudaFree(dwp);
@@ -612,6 +631,15 @@ int main(int argc, char** argv) {
         test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);       // N = 96: 64-block + tail block, pre + residuals
         test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);     // N = 160: two blocks + tail, pre only
         test_tc(1, 19, 11, 64, 96, 96, 0, 0, 4);       // N = 96 without loads
+        g_f16 = 1;                                     // IEEE half operands / activations (inference precision 'fp16')
+        test_tc(2, 32, 16, 64, 192, 192, 0, 0, 4);
+        test_tc(1, 20, 13, 96, 64, 64, 0, 0, 5);
+        test_tc(2, 40, 24, 32, 32, 32, 0, 0, 5);
+        test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);
+        test_tc(1, 20, 13, 96, 32, 32, 0, 0, 2);       // single-CTA kernel, staged epilogue
+        test_tc(1, 16, 16, 64, 64, 64, 2, 0, 0);       // upsample-fused (direct-store epilogue)
+        test_tc(1, 21, 10, 64, 16, 16, 0, 0, 3);       // NCHW fp32 tail
+        g_f16 = 0;
       }
       test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
       test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace dasr {
 
@@ -199,6 +200,12 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr, uint32_t 
 __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with the 16-bit operand type selectable: f16 != 0 -> a/b format F16 (0) (IEEE half operands, fp32 accumulate:
+// three more mantissa bits than bf16 at the same tensor-core rate)
+__host__ __device__ inline uint32_t make_idesc_16(int M, int N, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // TMA store / bulk-group helpers (epilogue)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
@@ -260,6 +267,33 @@ __device__ __forceinline__ void fma_bf16x8(float* v, const uint4& u, float s) {
     float2 f = __bfloat1622float2(b2[j]);
     v[2 * j] = fmaf(s, f.x, v[2 * j]);
     v[2 * j + 1] = fmaf(s, f.y, v[2 * j + 1]);
+  }
+}
+
+// v[0..8) += s * (8 packed 16-bit values of u), bf16 or IEEE half
+__device__ __forceinline__ void fma_h16x8(float* v, const uint4& u, float s, int f16) {
+  if (f16) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float2 f = __half22float2(h2[j]);
+      v[2 * j] = fmaf(s, f.x, v[2 * j]);
+      v[2 * j + 1] = fmaf(s, f.y, v[2 * j + 1]);
+    }
+  } else {
+    fma_bf16x8(v, u, s);
+  }
+}
+// 16 floats -> 16 packed 16-bit values (round to nearest even)
+__device__ __forceinline__ void pack_h16x16(const float* v, uint4* o, int f16) {
+  if (f16) {
+    __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; j++) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  } else {
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
   }
 }
 

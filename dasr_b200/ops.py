@@ -179,14 +179,23 @@ def pack_filter_f32(w, for_dgrad=False):
 # tcgen05 bf16 conv
 # --------------------------------------------------------------------------------------------------
 
-def pack_filter_tc(w, kind):
-    """OIHW fp32 3x3 filter -> bf16 [variant][tap][chunk][cout][32] (dasr_pack_filter_tc)."""
+TC_PACK_F16 = 0x100        # DASR_TC_PACK_F16
+
+
+def _dt16(t):
+    """dtype code of the layout kernels: 0 = fp32, 1 = bf16, 2 = IEEE half."""
+    return 1 if t.dtype == torch.bfloat16 else 2 if t.dtype == torch.float16 else 0
+
+
+def pack_filter_tc(w, kind, dtype=torch.bfloat16):
+    """OIHW fp32 3x3 filter -> bf16 (or IEEE half) [variant][tap][chunk][cout][32] (dasr_pack_filter_tc)."""
     cout, cin, kh, kw = w.shape
-    assert kh == 3 and kw == 3
+    assert kh == 3 and kw == 3 and dtype in (torch.bfloat16, torch.float16)
     lib = _lib.load()
     nbytes = lib.dasr_pack_filter_tc_bytes(cout, cin, kind)
-    o = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-    check(lib.dasr_pack_filter_tc(_p(w.detach()), _p(o), cout, cin, kind, _stream()), 'pack_filter_tc')
+    o = torch.empty(nbytes // 2, dtype=dtype, device=w.device)
+    flag = TC_PACK_F16 if dtype == torch.float16 else 0
+    check(lib.dasr_pack_filter_tc(_p(w.detach()), _p(o), cout, cin, kind | flag, _stream()), 'pack_filter_tc')
     return o
 
 
@@ -207,6 +216,10 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     lib = _lib.load()
     check(lib.dasr_conv_tc_setup(C.byref(p), kind), 'conv_tc_setup', 0)
     p.N, p.H, p.W = N, H, W
+    p.f16 = int(inp.t.dtype == torch.float16)
+    for t in (w_packed, out.t):
+        if t.dtype != inp.t.dtype:
+            raise _lib.DasrError('conv_tc: operands of different 16-bit types (%s vs %s)' % (t.dtype, inp.t.dtype))
     p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
     if chunks is not None:
         p.cin, p.in_coff, p.nchunk_list = 32 * len(chunks), 0, len(chunks)
@@ -251,6 +264,9 @@ def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode
     lib = _lib.load()
     check(lib.dasr_conv_tc_setup(C.byref(p), TC_FPROP), 'conv_tc_setup', 0)
     p.N, p.H, p.W = N, H, W
+    p.f16 = int(inp.t.dtype == torch.float16)
+    if w_packed.dtype != inp.t.dtype:
+        raise _lib.DasrError('conv_tc: operands of different 16-bit types (%s vs %s)' % (w_packed.dtype, inp.t.dtype))
     p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
     p.cout, p.out_cs, p.out_coff, p.nt = cout, cout, 0, cout
     p.act, p.slope, p.alpha, p.act_cols = act, slope, alpha, (cout if act != ACT_NONE else 0)
@@ -267,7 +283,7 @@ def nchw_to_nhwc(src, dst, mean=None, std=None):
     dst = as_view(dst)
     N, Cc, H, W = src.shape
     check(_lib.load().dasr_nchw_to_nhwc(_p(src), dst.ptr, N, Cc, H, W, dst.cs, dst.coff,
-                                        int(dst.t.dtype == torch.bfloat16), _p(mean), _p(std), _stream()), 'nchw_to_nhwc')
+                                        _dt16(dst.t), _p(mean), _p(std), _stream()), 'nchw_to_nhwc')
 
 
 def nhwc_to_nchw(src, dst, inv_std=None):
@@ -298,7 +314,7 @@ def axpby(x, a, y, b, dst):
     npix = dst.t.numel() // dst.cs
     check(_lib.load().dasr_axpby(x.ptr, y.ptr if y else None, dst.ptr, npix, dst.c, x.cs, x.coff,
                                  y.cs if y else 0, y.coff if y else 0, dst.cs, dst.coff, a, b,
-                                 int(dst.t.dtype == torch.bfloat16), _stream()), 'axpby')
+                                 _dt16(dst.t), _stream()), 'axpby')
 
 
 def maxpool2_fwd(x, out):

@@ -75,7 +75,7 @@ class RRDBNet(nn.Module):
         ups = upsampler if isinstance(upsampler, list) else [upsampler]
         self.model = B.sequential(fea_conv, B.ShortcutBlock(B.sequential(*rb_blocks, LR_conv)), *ups, HR_conv0, HR_conv1)
         self.nb, self.nf, self.upscale = nb, nf, upscale
-        self.precision = None          # inference: None -> DASR_B200_PRECISION or 'bf16' ('bf16' | 'bf16_layer' | 'fp32')
+        self.precision = None          # inference: None -> DASR_B200_PRECISION or 'bf16' ('bf16' | 'bf16_layer' | 'fp16' | 'fp16_layer' | 'fp32')
         self.train_precision = None    # training:  None -> DASR_B200_TRAIN_PRECISION or 'fp32' ('fp32' | 'bf16')
         self._pack_cache = engine._PackCache()
         self._graphs = {}
@@ -109,9 +109,11 @@ class RRDBNet(nn.Module):
                 return engine.RRDBNetFunctionBF16.apply(x, self.nb, self.upscale, self._pack_cache, graphs, arena, *params)
             return engine.RRDBNetFunction.apply(x, self.nb, self.upscale, *params)
         prec = self.precision or _precision('bf16')
-        if prec in ('bf16', 'bf16_layer'):
-            # 'bf16' = dense-block N-fused launches (default); 'bf16_layer' = one launch per conv
-            fn = lambda t: engine.rrdb_forward_bf16(t, params, self.nb, self.upscale, self._pack_cache, fused=(prec == 'bf16'))
+        if prec in ('bf16', 'bf16_layer', 'fp16', 'fp16_layer'):
+            # 'bf16' / 'fp16' = dense-block N-fused launches (bf16 is the default); '*_layer' = one launch per conv;
+            # fp16 = IEEE half operands on the same tcgen05 kernels (3 more significand bits, same speed)
+            fn = lambda t: engine.rrdb_forward_bf16(t, params, self.nb, self.upscale, self._pack_cache,
+                                                    fused=not prec.endswith('_layer'), half=prec.startswith('fp16'))
             if os.environ.get('DASR_B200_GRAPH', '1') == '0' or not x.is_cuda or engine.PROFILE is not None:
                 return fn(x)
             key = (tuple(x.shape), x.dtype, x.device.index, prec, tuple(p._version for p in params),

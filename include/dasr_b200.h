@@ -146,6 +146,9 @@ typedef struct {
                                   contiguous slice [in_coff, in_coff + cin) — dense-block schedules that feed
                                   non-adjacent activations (e.g. x1 and x3) to one launch */
   int chunk_off[8];
+  int f16;                     /* 0: operands / activations / partial sums are bf16;  1: IEEE half (kind::f16 F16 operands, fp32
+                                  accumulate; same rate, 3 more mantissa bits — the inference precision 'fp16').  Filters must be
+                                  packed with DASR_TC_PACK_F16. */
 } DasrConvTcParams;
 
 int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
@@ -176,6 +179,9 @@ int dasr_pack_filter_tc(const float* w_oihw, void* w_packed_bf16, int cout, int 
  *             input channels [ci_lo, ci_lo + ci_n) of src (OIHW [cout][cin][3][3]); reads beyond cout/cin give 0.
  *   kind 1  : dgrad pack; GEMM-N rows = input channels [ci_lo, ci_lo + ci_n), GEMM-K = k_pad >= cout channels.
  *   kind 3  : copy `cout` fp32 values src -> dst (bias prefix). */
+/* OR into `kind` of dasr_pack_filter_tc: write IEEE half instead of bf16 */
+#define DASR_TC_PACK_F16 0x100
+
 typedef struct {
   const float* src;
   void* dst;
@@ -194,6 +200,7 @@ int dasr_pack_filter_tc_batch(const DasrPackJob* jobs, int njobs, int blocks_per
  * ---------------------------------------------------------------------------------------------- */
 /* NCHW fp32 <-> NHWC (fp32 or bf16) with channel stride/offset; optional per-channel (x-mean)/std
  * (VGGFeatureExtractor input norm, architecture.py:1073-1086).  mean/std may be NULL. */
+/* dst_is_bf16 / is_bf16 of nchw_to_nhwc and axpby: 0 = fp32, 1 = bf16, 2 = IEEE half */
 int dasr_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_cs,
                       int dst_coff, int dst_is_bf16, const float* mean, const float* std, void* stream);
 int dasr_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_cs,

@@ -369,12 +369,17 @@ def test_dasr_model_train_steps_vs_golden(golden, name):
         G, D = unwrap(model.netG).state_dict(), unwrap(model.netD_target).state_dict()
         for k, v in ref['G_keep'].items():
             assert rel_linf(G[k], v) < FP32_TOL, k
+        # relativistic losses only see score DIFFERENCES: the gradient of D's last bias is mathematically zero, what
+        # backward leaves there is rounding noise and Adam turns noise into a +-lr step -> not comparable
+        skip = {'model.8.bias'} if g.get('ragan') else set()
         for k, v in ref['D_keep'].items():
-            assert rel_linf(D[k], v) < FP32_TOL, k
+            if k not in skip:
+                assert rel_linf(D[k], v) < FP32_TOL, k
         for k, n in ref['G_norms'].items():
             assert abs(float(G[k].double().norm()) - n) <= 1e-4 * max(n, 1e-9), k
         for k, n in ref['D_norms'].items():
-            assert abs(float(D[k].double().norm()) - n) <= 1e-4 * max(n, 1e-9), k
+            if k not in skip:
+                assert abs(float(D[k].double().norm()) - n) <= 1e-4 * max(n, 1e-9), k
 
 
 def test_sr_model_test_path_vs_golden(golden):

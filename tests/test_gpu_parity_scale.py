@@ -3,7 +3,8 @@
   * configs[0] ("PR1 ref"): RRDBNet-23, kaiming x0.1-like gain, 1x3x256x256, fp32 kernels against the CPU oracle:
     rel-Linf <= 1e-3 (north_star), 8-bit images equal, PSNR/SSIM to 3 decimals.
   * configs[1]: 16x3x256x256 through the benchmarked bf16 tcgen05 dense-block schedule against the fp32 kernels on
-    the same weights: rel-Linf reported + bounded, 8-bit image difference and PSNR/SSIM deltas reported + bounded.
+    the same weights: rel-Linf reported + bounded, 8-bit image difference and PSNR/SSIM deltas reported + bounded;
+    the same launches with IEEE half operands (precision 'fp16'): PSNR/SSIM to 3 decimals.
   * mixed-precision DASR_Model train steps against the reference's own two-step fixture with stated tolerances.
 
 "rel-Linf" = max|a-b| / max|b|.  The raw output of a x0.1-initialised net spans only +-3e-4, so images
@@ -91,7 +92,7 @@ def test_config1_bf16_nb23_16x256_vs_fp32_kernels():
         net.precision = 'fp32'
         ref = torch.cat([net(x[i:i + 4]).cpu() for i in range(0, 16, 4)], 0)
         res = {}
-        for prec in ('bf16', 'bf16_layer'):
+        for prec in ('bf16', 'bf16_layer', 'fp16'):
             net.precision = prec
             res[prec] = net(x).cpu()
     s, t = _affine(ref)
@@ -119,6 +120,12 @@ def test_config1_bf16_nb23_16x256_vs_fp32_kernels():
         assert e < 2e-3 and rms < 3e-4, prec
         assert mx <= 1, prec
         assert dp < 6e-3 and dq < 6e-4, prec
+    # IEEE half operands on the same kernels (precision 'fp16', same speed): 3 more significand bits ->
+    # PSNR / SSIM equal to the fp32 path to the 3 decimals the north star asks of the tensor-core path.
+    e, rms, mx, dp, dq = res['fp16']
+    assert e < 3e-4 and rms < 5e-5
+    assert mx <= 1
+    assert dp < 5e-4 and dq < 5e-4
 
 
 def test_mixed_precision_dasr_steps_vs_reference_fixture(golden, monkeypatch):
