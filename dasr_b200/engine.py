@@ -746,7 +746,7 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
             ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True)
         else:
             ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)    # ... or as 2 x 96
-        ops.axpby(View(GB, nf, 0), 1.0, g_y, b1, View(GB, nf, 0))
+        g_new = _empty((N, H, W, nf), dev, bf)
         for k in (4, 3, 2, 1):
             ci = L.rdb_conv(r, k)
             cin = _rdb_cin(nf, k)
@@ -755,18 +755,20 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
             if not fused_wgrad:
                 wgrad(View(b, cin, 0), gk, ci, bias=False)
             o = View(GB, cin, 0)
-            ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                          # accumulate in place
+            if k > 1:
+                ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                      # accumulate in place
+            elif r % 3 == 0 and g_rrdb is not None:
+                # conv1's dgrad completes the block's input gradient: + what conv2..5 left in the x slot + the block skip
+                # (b1 * g_y) + the RRDB skip, written straight to the next gradient buffer (no separate add kernels)
+                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1, res2=g_rrdb, beta2=1.0)
+                g_rrdb = None
+            else:
+                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1)
         # bias gradients of conv1..4 in one reduction: their masked output gradients are the final x1..x4 slices of GB
         c1 = L.rdb_conv(r, 1)
         ops.bias_grad(View(GB, 4 * GC, nf), flat[b_off[c1]:b_off[c1] + 4 * GC])
         if fused_wgrad:     # all five filter gradients of the block: one tcgen05 launch + one reduction
             ops.rdb_wgrad_tc(b, GB, nf, g_x5, 0, [gW(L.rdb_conv(r, k)) for k in range(1, 6)])
-        g_new = _empty((N, H, W, nf), dev, bf)
-        if r % 3 == 0 and g_rrdb is not None:
-            ops.axpby(View(GB, nf, 0), 1.0, g_rrdb, 1.0, g_new)
-            g_rrdb = None
-        else:
-            ops.axpby(View(GB, nf, 0), 1.0, None, 0.0, g_new)
         g_y = g_new
     g_fea = _empty((N, H, W, nf), dev, bf)
     ops.axpby(g_y, 1.0, g_lr, 1.0, g_fea)
