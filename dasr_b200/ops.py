@@ -4,6 +4,7 @@ torch is used here only as the owner of device memory and of the current CUDA st
 computes anything on this path.  Every wrapper requires CUDA tensors and raises otherwise.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -27,6 +28,27 @@ def _p(t):
     if not t.is_contiguous():
         raise _lib.DasrError('dasr_b200 kernels need contiguous tensors')
     return C.c_void_p(t.data_ptr())
+
+
+NVTX = os.environ.get('DASR_B200_NVTX', '0') == '1'
+
+
+class nvtx:
+    """NVTX range (nsys / ncu --nvtx timelines) around a phase of a step: `with ops.nvtx('G/backward'): ...`.
+    Off unless DASR_B200_NVTX=1 (a push/pop pair costs ~1 us of host time per range)."""
+    __slots__ = ('name',)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class View:

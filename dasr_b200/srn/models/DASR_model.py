@@ -169,9 +169,11 @@ class DASR_Model(BaseModel):
 
     # ------------------------------------------------------------------------------------------ step
     def optimize_parameters(self, step):
-        self.fake_H = self.netG(self.var_L)
-        self.fake_LL, self.fake_Hc = self.fs(self.fake_H, norm=self.norm)
-        self.real_LL, self.real_Hc = self.fs(self.var_H, norm=self.norm)
+        with ops.nvtx('G/forward'):
+            self.fake_H = self.netG(self.var_L)
+        with ops.nvtx('frequency_separation'):
+            self.fake_LL, self.fake_Hc = self.fs(self.fake_H, norm=self.norm)
+            self.real_LL, self.real_Hc = self.fs(self.var_H, norm=self.norm)
 
         self.fake_SR_source, _ = b_split(self.fake_H, self.mask)
         self.fake_SR_LL_source, _ = b_split(self.fake_LL, self.mask)
@@ -229,7 +231,8 @@ class DASR_Model(BaseModel):
                     l_g_gan_source_Hf = self.l_gan_H_source_w * self.cri_gan(pred_g_Hf_source_fake, True)
                 l_g_total += l_g_gan_source_Hf
             self.optimizer_G.zero_grad()
-            l_g_total.backward()
+            with ops.nvtx('G/backward'):
+                l_g_total.backward()
             if not self.grad_sync.active:
                 self.optimizer_G.step()
             else:
@@ -237,6 +240,7 @@ class DASR_Model(BaseModel):
 
         if do_D:
             if self.l_gan_H_target_w > 0:
+                # (NVTX: the D step is everything between 'G/backward' and 'dp/finish+optimizers')
                 # one discriminator pass over [real | fake] (DASR_model.py:271-272 runs two): InstanceNorm statistics are
                 # per sample, so the scores and the parameter gradients are the same sums
                 nreal = self.real_HR_Hf_target.shape[0]
@@ -271,13 +275,14 @@ class DASR_Model(BaseModel):
         if self.grad_sync.active:
             # gradient exchange over NCCL (G's segment already in flight, D's now; DASR_B200_DP_OVERLAP=0: one all-reduce of
             # the whole [G | D] bucket here), then the deferred optimiser steps
-            self.grad_sync.finish()
-            if do_G:
-                self.optimizer_G.step()
-            if do_D and self.l_gan_H_target_w > 0:
-                self.optimizer_D_target.step()
-            if do_D and self.l_gan_H_source_w > 0:
-                self.optimizer_D_source.step()
+            with ops.nvtx('dp/finish+optimizers'):
+                self.grad_sync.finish()
+                if do_G:
+                    self.optimizer_G.step()
+                if do_D and self.l_gan_H_target_w > 0:
+                    self.optimizer_D_target.step()
+                if do_D and self.l_gan_H_source_w > 0:
+                    self.optimizer_D_source.step()
 
         if do_G:
             if self.cri_pix:
