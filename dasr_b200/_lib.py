@@ -29,6 +29,7 @@ class ConvF32Params(C.Structure):
         ('alpha', C.c_float),
         ('beta1', C.c_float), ('res1_cs', C.c_int), ('res1_coff', C.c_int),
         ('beta2', C.c_float), ('res2_cs', C.c_int), ('res2_coff', C.c_int),
+        ('math', C.c_int),
     ]
 
 

@@ -7,6 +7,7 @@
 // (NLayerDiscriminator), architecture.py:1076 (VGG19 features); autograd's conv backward for them.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace dasr {
@@ -64,18 +65,107 @@ __device__ __forceinline__ bool gather_coord(const DasrConvF32Params& p, int oy,
   }
 }
 
-constexpr int BM = 64, BN = 64, BK = 16, BMP = 68;
+constexpr int BM = 64, BN = 64, BK = 16;
+
+// Arithmetic of the 64x64x16 tile product (DasrConvF32Params.math, DASR_F32_MATH_*):
+//   FMA    : fp32 FMA on CUDA cores, 4x4 outputs per thread                      (exact mode, default)
+//   TF32   : mma.sync m16n8k8 tf32, fp32 accumulate (10-bit significand operands) (mixed-precision training: the fp32 side
+//            nets — discriminators, stride-2 / 5x5 layers — whose shapes do not fit the tcgen05 tiles)
+//   TF32X3 : a = hi + lo, b = hi + lo in tf32; lo*hi + hi*lo + hi*hi              (fp32-level error on tensor cores)
+// The odd shapes of these layers (Cin 3/9, 4x4 stride 2, 5x5, Cout 1) rule out the tcgen05 halo-tile kernel; warp-level
+// MMA on the gathered tile keeps the generic gather and still leaves the FMA pipe.
+constexpr int MATH_FMA = 1, MATH_TF32 = 2, MATH_TF32X3 = 3;
+template <int MATH> struct Pad {       // row strides of the two shared-memory tiles: conflict-free for each access pattern
+  static constexpr int A = (MATH == MATH_FMA) ? 68 : 72;
+  static constexpr int B = (MATH == MATH_FMA) ? 64 : 72;
+};
+
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// acc (16 floats per thread) += As[BK][64] (k-major) * Bs[BK][64].
+//   FMA : thread (ty, tx) owns rows ty*4 + i, cols tx*4 + j              -> acc[i*4 + j]
+//   MMA : warp (wm = warp & 3, wn = warp >> 2) owns rows wm*16.., cols wn*32..; lane (g = lane >> 2, t = lane & 3) owns
+//         rows wm*16 + g + 8*h, cols wn*32 + nt*8 + 2*t + e              -> acc[nt*4 + h*2 + e]
+template <int MATH>
+__device__ __forceinline__ void tile_product(const float (*As)[Pad<MATH>::A], const float (*Bs)[Pad<MATH>::B], float* acc,
+                                             int t) {
+  if constexpr (MATH == MATH_FMA) {
+    const int ty = t >> 4, tx = t & 15;
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i * 4 + j] = fmaf(av[i], bv[j], acc[i * 4 + j]);
+    }
+  } else {
+    const int warp = t >> 5, lane = t & 31;
+    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int k0 = 0; k0 < BK; k0 += 8) {
+      const float af[4] = {As[k0 + q][m0 + g], As[k0 + q][m0 + g + 8], As[k0 + q + 4][m0 + g], As[k0 + q + 4][m0 + g + 8]};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ah[i] = cvt_tf32(af[i]);
+        if constexpr (MATH == MATH_TF32X3) al[i] = cvt_tf32(af[i] - __uint_as_float(ah[i]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const float bf[2] = {Bs[k0 + q][n0 + nt * 8 + g], Bs[k0 + q + 4][n0 + nt * 8 + g]};
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          bh[i] = cvt_tf32(bf[i]);
+          if constexpr (MATH == MATH_TF32X3) bl[i] = cvt_tf32(bf[i] - __uint_as_float(bh[i]));
+        }
+        if constexpr (MATH == MATH_TF32X3) {      // small terms first
+          mma_tf32(acc + nt * 4, al, bh);
+          mma_tf32(acc + nt * 4, ah, bl);
+        }
+        mma_tf32(acc + nt * 4, ah, bh);
+      }
+    }
+  }
+}
+// tile-local (row, col) of accumulator element e of thread t
+template <int MATH>
+__device__ __forceinline__ void acc_coord(int t, int e, int& row, int& col) {
+  if constexpr (MATH == MATH_FMA) {
+    row = (t >> 4) * 4 + (e >> 2);
+    col = (t & 15) * 4 + (e & 3);
+  } else {
+    const int warp = t >> 5, lane = t & 31;
+    row = (warp & 3) * 16 + (lane >> 2) + 8 * ((e >> 1) & 1);
+    col = (warp >> 2) * 32 + (e >> 2) * 8 + 2 * (lane & 3) + (e & 1);
+  }
+}
 
 // out[P x Cout] = gather(in)[P x K] * w[K x Cout],  K = taps*cin flattened tap-major.
-template <bool VEC>
+template <bool VEC, int MATH>
 __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict__ in,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          const float* __restrict__ res1,
                                                          const float* __restrict__ res2,
                                                          float* __restrict__ out, DasrConvF32Params p) {
-  __shared__ __align__(16) float As[BK][BMP];
-  __shared__ __align__(16) float Bs[BK][BN];
+  __shared__ __align__(16) float As[BK][Pad<MATH>::A];
+  __shared__ __align__(16) float Bs[BK][Pad<MATH>::B];
   const int t = threadIdx.x;
   const long P = (long)p.N * p.OH * p.OW;
   const int K = p.kh * p.kw * p.cin;
@@ -96,12 +186,9 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
   // B-load role: k row b_k, cout-quad b_cq
   const int b_k = t >> 4, b_cq = t & 15;
 
-  const int ty = t >> 4, tx = t & 15;
-  float acc[4][4];
+  float acc[16];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int e = 0; e < 16; e++) acc[e] = 0.f;
 
   for (int kk = 0; kk < K; kk += BK) {
     // ---- load A tile (gathered activations) ----
@@ -152,36 +239,24 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
       *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = q;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; k++) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
+    tile_product<MATH>(As, Bs, acc, t);
     __syncthreads();
   }
 
   // ---- epilogue ----
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    long pm = pm0 + ty * 4 + i;
-    if (pm >= P) continue;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int co = co0 + tx * 4 + j;
-      if (co >= p.cout) continue;
-      float v = acc[i][j] + (bias ? bias[co] : 0.f);
-      v = apply_act(v, p.act, p.slope);
-      v *= p.alpha;
-      if (res1) v = fmaf(p.beta1, res1[pm * p.res1_cs + p.res1_coff + co], v);
-      if (res2) v = fmaf(p.beta2, res2[pm * p.res2_cs + p.res2_coff + co], v);
-      out[pm * p.out_cs + p.out_coff + co] = v;
-    }
+  for (int e = 0; e < 16; e++) {
+    int row, col;
+    acc_coord<MATH>(t, e, row, col);
+    const long pm = pm0 + row;
+    const int co = co0 + col;
+    if (pm >= P || co >= p.cout) continue;
+    float v = acc[e] + (bias ? bias[co] : 0.f);
+    v = apply_act(v, p.act, p.slope);
+    v *= p.alpha;
+    if (res1) v = fmaf(p.beta1, res1[pm * p.res1_cs + p.res1_coff + co], v);
+    if (res2) v = fmaf(p.beta2, res2[pm * p.res2_cs + p.res2_coff + co], v);
+    out[pm * p.out_cs + p.out_coff + co] = v;
   }
 }
 
@@ -198,13 +273,13 @@ template <> __device__ __forceinline__ float load1<float>(const float* p) { retu
 template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // part[split][K x Cout] = gather(in)^T[K x Pslice] * dout[Pslice x Cout]      (T = fp32 or bf16 inputs, fp32 accumulate)
-template <bool VEC, typename T>
+template <bool VEC, typename T, int MATH>
 __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restrict__ in,
                                                                const T* __restrict__ dout,
                                                                float* __restrict__ part,
                                                                DasrConvF32Params p, long pix_per_split) {
-  __shared__ __align__(16) float As[BK][BMP];  // [pixel][k]
-  __shared__ __align__(16) float Bs[BK][BN];   // [pixel][co]
+  __shared__ __align__(16) float As[BK][Pad<MATH>::A];  // [pixel][k]
+  __shared__ __align__(16) float Bs[BK][Pad<MATH>::B];  // [pixel][co]
   const int t = threadIdx.x;
   const long P = (long)p.N * p.OH * p.OW;
   const int K = p.kh * p.kw * p.cin;
@@ -227,12 +302,9 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restri
       kci[j] = 0;
     }
   }
-  const int ty = t >> 4, tx = t & 15;
-  float acc[4][4];
+  float acc[16];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int e = 0; e < 16; e++) acc[e] = 0.f;
 
   for (long pp = pbeg; pp < pend; pp += BK) {
     long pix = pp + l_p;
@@ -285,29 +357,16 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restri
       *reinterpret_cast<float4*>(&Bs[l_p][l_q * 4]) = q;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; k++) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
+    tile_product<MATH>(As, Bs, acc, t);
     __syncthreads();
   }
   float* dst = part + (long)blockIdx.z * K * p.cout;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    int k = k0 + ty * 4 + i;
-    if (k >= K) continue;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int co = co0 + tx * 4 + j;
-      if (co < p.cout) dst[(long)k * p.cout + co] = acc[i][j];
-    }
+  for (int e = 0; e < 16; e++) {
+    int row, col;
+    acc_coord<MATH>(t, e, row, col);
+    const int k = k0 + row, co = co0 + col;
+    if (k < K && co < p.cout) dst[(long)k * p.cout + co] = acc[e];
   }
 }
 
@@ -362,6 +421,19 @@ __global__ void pack_filter_f32_kernel(const float* __restrict__ w, float* __res
   o[dst] = w[i];
 }
 
+// math field of the params: 0 = library default (DASR_B200_F32_MATH = fma | tf32 | tf32x3, else FMA)
+static int resolve_math(int m) {
+  if (m != 0) return m;
+  static int dflt = 0;
+  if (dflt == 0) {
+    const char* e = getenv("DASR_B200_F32_MATH");
+    dflt = MATH_FMA;
+    if (e && !strcmp(e, "tf32")) dflt = MATH_TF32;
+    if (e && !strcmp(e, "tf32x3")) dflt = MATH_TF32X3;
+  }
+  return dflt;
+}
+
 static int wgrad_splits(const DasrConvF32Params* p) {
   long P = (long)p->N * p->OH * p->OW;
   int K = p->kh * p->kw * p->cin;
@@ -412,10 +484,19 @@ static int wgrad_impl(const T* in, const T* dout, float* dw, float* db, const Da
   bool vec = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
              (p->out_cs % 4 == 0) && (p->out_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & amask) == 0) &&
              ((reinterpret_cast<uintptr_t>(dout) & amask) == 0);
-  if (vec)
-    conv2d_wgrad_f32_kernel<true, T><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
-  else
-    conv2d_wgrad_f32_kernel<false, T><<<grid, 256, 0, st>>>(in, dout, part, *p, pps);
+  const int math = resolve_math(p->math);
+  DASR_REQUIRE(math >= MATH_FMA && math <= MATH_TF32X3, "wgrad: math=%d", p->math);
+#define DASR_WGRAD_LAUNCH(V, M) conv2d_wgrad_f32_kernel<V, T, M><<<grid, 256, 0, st>>>(in, dout, part, *p, pps)
+  if (vec) {
+    if (math == MATH_FMA) DASR_WGRAD_LAUNCH(true, MATH_FMA);
+    else if (math == MATH_TF32) DASR_WGRAD_LAUNCH(true, MATH_TF32);
+    else DASR_WGRAD_LAUNCH(true, MATH_TF32X3);
+  } else {
+    if (math == MATH_FMA) DASR_WGRAD_LAUNCH(false, MATH_FMA);
+    else if (math == MATH_TF32) DASR_WGRAD_LAUNCH(false, MATH_TF32);
+    else DASR_WGRAD_LAUNCH(false, MATH_TF32X3);
+  }
+#undef DASR_WGRAD_LAUNCH
   long total = (long)K * p->cout;
   wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(part, dw, splits, K, p->cin, p->cout, p->kh * p->kw,
                                                          accumulate);
@@ -443,10 +524,19 @@ int dasr_conv2d_f32(const float* in, const float* w, const float* bias, const fl
   bool vec = (p->cin % 16 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
              ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec)
-    conv2d_f32_kernel<true><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
-  else
-    conv2d_f32_kernel<false><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
+  const int math = resolve_math(p->math);
+  DASR_REQUIRE(math >= MATH_FMA && math <= MATH_TF32X3, "conv2d_f32: math=%d", p->math);
+#define DASR_CONV_LAUNCH(V, M) conv2d_f32_kernel<V, M><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p)
+  if (vec) {
+    if (math == MATH_FMA) DASR_CONV_LAUNCH(true, MATH_FMA);
+    else if (math == MATH_TF32) DASR_CONV_LAUNCH(true, MATH_TF32);
+    else DASR_CONV_LAUNCH(true, MATH_TF32X3);
+  } else {
+    if (math == MATH_FMA) DASR_CONV_LAUNCH(false, MATH_FMA);
+    else if (math == MATH_TF32) DASR_CONV_LAUNCH(false, MATH_TF32);
+    else DASR_CONV_LAUNCH(false, MATH_TF32X3);
+  }
+#undef DASR_CONV_LAUNCH
   return check_launch("conv2d_f32");
 }
 

@@ -407,12 +407,16 @@ __global__ void bias_grad_partial_kernel(const T* __restrict__ d, float* __restr
     part[(long)blockIdx.y * C + c] = t;
   }
 }
+// one warp per channel: lanes stride over the per-block partials (fixed order -> deterministic), shuffle tree at the end
 __global__ void bias_grad_reduce_kernel(const float* __restrict__ part, float* __restrict__ db, int nblk, int C, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += part[(long)b * C + c];
-  db[c] = accumulate ? db[c] + s : s;
+  for (int b = lane; b < nblk; b += 32) s += part[(long)b * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) db[c] = accumulate ? db[c] + s : s;
 }
 
 // ---- Haar J=1 split (pytorch_wavelets DWTForward 'haar', even H,W) ------------------------------
@@ -807,24 +811,28 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
 int dasr_bias_grad(const void* dout, float* db, long npix, int C, int cs, int coff, int is_bf16, int accumulate,
                    float* partials, void* stream) {
   DASR_REQUIRE(npix > 0 && C > 0 && cs >= coff + C && partials, "bias_grad: bad arguments");
+  // partials holds >= max(64 * C, 32768) floats (include/dasr_b200.h): up to 32768 / C blocks, at least 64
+  long cap = 32768 / C;
+  if (cap < 64) cap = 64;
+  if (cap > 592) cap = 592;
   long nblk = (npix + 2047) / 2048;
-  if (nblk > 64) nblk = 64;                       // partials: >= 64 * C floats
+  if (nblk > 64) nblk = 64;
   long ppb = (npix + nblk - 1) / nblk;
   dim3 grid(cdiv(C, 32), (unsigned)nblk), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (is_bf16 && C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && cs % 8 == 0 && coff % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
-    nblk = (npix + 255) / 256;
-    if (nblk > 64) nblk = 64;
-    ppb = (npix + nblk - 1) / nblk;
     const int nplane = 256 / (C / 8);
+    nblk = (npix + 4 * nplane - 1) / (4 * nplane);      // >= 4 pixels per thread
+    if (nblk > cap) nblk = cap;
+    ppb = (npix + nblk - 1) / nblk;
     bias_grad_partial_bf16x8_kernel<<<(unsigned)nblk, 256, (size_t)nplane * C * sizeof(float), st>>>(
         (const __nv_bfloat16*)dout, partials, npix, C, cs, coff, ppb);
   } else if (is_bf16)
     bias_grad_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dout, partials, npix, C, cs, coff, ppb);
   else
     bias_grad_partial_kernel<float><<<grid, block, 0, st>>>((const float*)dout, partials, npix, C, cs, coff, ppb);
-  bias_grad_reduce_kernel<<<cdiv(C, 128), 128, 0, st>>>(partials, db, (int)nblk, C, accumulate);
+  bias_grad_reduce_kernel<<<cdiv(C, 4), 128, 0, st>>>(partials, db, (int)nblk, C, accumulate);
   return check_launch("bias_grad");
 }
 

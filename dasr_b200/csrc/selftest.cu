@@ -67,6 +67,7 @@ static void cpu_conv(const std::vector<float>& in, int N, int H, int W, int cin,
         }
 }
 
+static int g_math = 0;   // DasrConvF32Params.math of the conv_f32 tests (0 = default FMA, 2 = tf32, 3 = tf32x3)
 static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, int pad, int ups) {
   char name[160];
   int in_cs = cin + 8, in_coff = 4;
@@ -82,6 +83,7 @@ static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, 
   h2d(din, in); h2d(dw, w); h2d(db, b);
   DasrConvF32Params p;
   memset(&p, 0, sizeof(p));
+  p.math = g_math;
   p.N = N; p.H = H; p.W = W; p.cin = cin; p.in_cs = in_cs; p.in_coff = in_coff; p.OH = OH; p.OW = OW;
   p.cout = cout; p.out_cs = cout; p.out_coff = 0; p.kh = k; p.kw = k; p.stride = stride; p.pad = pad; p.ups = ups;
   p.mode = DASR_CONV_FWD; p.act = DASR_ACT_NONE; p.alpha = 1.f;
@@ -92,7 +94,7 @@ static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, 
   auto got = d2h(dout, ref.size());
   double me = 0;
   for (size_t i = 0; i < ref.size(); i++) me = fmax(me, fabs(got[i] - ref[i]));
-  snprintf(name, sizeof(name), "conv_f32 fwd N%d %dx%d cin%d cout%d k%d s%d p%d ups%d", N, H, W, cin, cout, k, stride, pad, ups);
+  snprintf(name, sizeof(name), "conv_f32%s fwd N%d %dx%d cin%d cout%d k%d s%d p%d ups%d", g_math == 2 ? " tf32" : g_math == 3 ? " tf32x3" : "", N, H, W, cin, cout, k, stride, pad, ups);
   report(name, me, 1e-4);
 
   // ---- dgrad: <dY, conv(X)> == <dgrad(dY), X>  checked element-wise against CPU transpose ----
@@ -117,6 +119,7 @@ static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, 
     h2d(ddy, dy);
     DasrConvF32Params q;
     memset(&q, 0, sizeof(q));
+  q.math = g_math;
     q.N = N; q.H = OH; q.W = OW; q.cin = cout; q.in_cs = cout; q.in_coff = 0; q.OH = H; q.OW = W; q.cout = cin;
     q.out_cs = cin; q.out_coff = 0; q.kh = k; q.kw = k; q.stride = stride; q.pad = pad; q.ups = 1;
     q.mode = DASR_CONV_DGRAD; q.alpha = 1.f;
@@ -127,7 +130,7 @@ static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, 
     auto gx = d2h(ddx, dxref.size());
     me = 0;
     for (size_t i = 0; i < dxref.size(); i++) me = fmax(me, fabs(gx[i] - dxref[i]));
-    snprintf(name, sizeof(name), "conv_f32 dgrad N%d %dx%d cin%d cout%d k%d s%d p%d", N, H, W, cin, cout, k, stride, pad);
+    snprintf(name, sizeof(name), "conv_f32%s dgrad N%d %dx%d cin%d cout%d k%d s%d p%d", g_math == 2 ? " tf32" : g_math == 3 ? " tf32x3" : "", N, H, W, cin, cout, k, stride, pad);
     report(name, me, 1e-4);
 
     // ---- wgrad ----
@@ -158,7 +161,7 @@ static void test_f32(int N, int H, int W, int cin, int cout, int k, int stride, 
     me = 0;
     for (size_t i = 0; i < w.size(); i++) me = fmax(me, fabs(gw[i] - dwref[i]));
     for (int i = 0; i < cout; i++) me = fmax(me, fabs(gb[i] - dbref[i]));
-    snprintf(name, sizeof(name), "conv_f32 wgrad N%d %dx%d cin%d cout%d k%d s%d p%d", N, H, W, cin, cout, k, stride, pad);
+    snprintf(name, sizeof(name), "conv_f32%s wgrad N%d %dx%d cin%d cout%d k%d s%d p%d", g_math == 2 ? " tf32" : g_math == 3 ? " tf32x3" : "", N, H, W, cin, cout, k, stride, pad);
     report(name, me, 2e-3);
     cudaFree(ddy); cudaFree(ddx); cudaFree(dwd); cudaFree(ws); cudaFree(ddw); cudaFree(ddb);
   }
@@ -587,14 +590,18 @@ int main(int argc, char** argv) {
   printf("device: %s sm_%d%d SMs=%d smem_optin=%zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          prop.sharedMemPerBlockOptin);
   if (do_check) {
-    test_f32(2, 9, 11, 3, 64, 3, 1, 1, 1);
-    test_f32(2, 8, 8, 32, 32, 3, 1, 1, 1);
-    test_f32(1, 7, 5, 64, 3, 3, 1, 1, 1);
-    test_f32(2, 12, 10, 9, 64, 4, 2, 1, 1);
-    test_f32(1, 9, 9, 16, 20, 4, 1, 1, 1);
-    test_f32(1, 6, 7, 16, 16, 3, 1, 1, 2);
-    test_f32(1, 8, 8, 8, 1, 4, 1, 1, 1);
-    test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
+    for (g_math = 0; g_math <= 3; g_math = g_math ? g_math + 1 : 2) {   // FMA, mma.sync tf32, 3 x tf32
+      test_f32(2, 9, 11, 3, 64, 3, 1, 1, 1);
+      test_f32(2, 8, 8, 32, 32, 3, 1, 1, 1);
+      test_f32(1, 7, 5, 64, 3, 3, 1, 1, 1);
+      test_f32(2, 12, 10, 9, 64, 4, 2, 1, 1);
+      test_f32(1, 9, 9, 16, 20, 4, 1, 1, 1);
+      test_f32(1, 6, 7, 16, 16, 3, 1, 1, 2);
+      test_f32(1, 8, 8, 8, 1, 4, 1, 1, 1);
+      test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
+      test_f32(2, 16, 16, 64, 128, 4, 2, 1, 1);      // discriminator layer shape
+    }
+    g_math = 0;
     test_wgrad_tc(1, 16, 8, 32, 32);
     test_wgrad_tc(1, 16, 8, 64, 32);
     test_wgrad_tc(2, 20, 13, 96, 32);

@@ -13,6 +13,16 @@ def train_iteration(model_g, model_d, g_loss_module, optimizer_g, optimizer_d, i
                     grad_sync=None, log=True):
     """One DeResnet iteration (no ragan / wgan, disc_freq = gen_freq = 1).  grad_sync: optional callable run
     between the backward passes and the optimiser steps (data-parallel all-reduce of both gradient sets)."""
+    import os
+    from dasr_b200 import ops
+    mixed = (getattr(model_g, 'precision', None) or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')) == 'bf16'
+    # mixed precision: the fp32 layers (stride-2 tail, 5x5 FS discriminator) take tf32 tensor-core math
+    with ops.f32_math(os.environ.get('DASR_B200_SIDE_MATH', 'tf32') if mixed else 'default'):
+        return _train_iteration(model_g, model_d, g_loss_module, optimizer_g, optimizer_d, input_img, bicubic_img, disc_img,
+                                grad_sync, log)
+
+
+def _train_iteration(model_g, model_d, g_loss_module, optimizer_g, optimizer_d, input_img, bicubic_img, disc_img, grad_sync, log):
     fake_img = model_g(input_img)                                                   # :218
     real_tex = model_d(disc_img)                                                    # :226
     fake_tex = model_d(fake_img)                                                    # :227

@@ -641,6 +641,16 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
     return out, ctx
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device.index)
+    if s is None:
+        s = _SIDE[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
 def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
     """Backward of the mixed-precision mode: input gradients (dgrad) on the tcgen05 kernel (3x3 conv with flipped,
     transposed filters; gradient contributions of a dense block accumulate in place in one bf16 buffer), filter
@@ -725,12 +735,25 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
     g_y = _empty((N, H, W, nf), dev, bf)
     ops.conv_tc(g_lr, wd(L.i_lr), None, g_y, kind=TC_DGRAD, nt=_pick_nt(nf, nf))
 
-    GB = _empty((N, H, W, CS), dev, bf)
-    g_x5 = _empty((N, H, W, nf), dev, bf)
     fused_wgrad = nf == 64 and GC == 32 and os.environ.get('DASR_B200_RDB_WGRAD', '1') == '1'
+    # The filter / bias gradients of a block depend on its finished gradient buffer but nothing downstream depends on
+    # them: they run on a SIDE stream (fork / join inside the captured graph) and fill the SMs the latency-bound dgrad
+    # chain of the next block leaves idle.  Two gradient buffers alternate; the main stream waits for the side stream's
+    # readers of a buffer before the block after next overwrites it.
+    overlap = fused_wgrad and os.environ.get('DASR_B200_BWD_OVERLAP', '1') == '1'
+    pair_dgrad = PAIR_MODE and nf == 64 and GC == 32 and os.environ.get('DASR_B200_PAIR_DGRAD', '0') == '1'
+    nset = 2 if overlap else 1
+    GBs = [_empty((N, H, W, CS), dev, bf) for _ in range(nset)]
+    gx5s = [_empty((N, H, W, nf), dev, bf) for _ in range(nset)]
+    main = torch.cuda.current_stream()
+    side = _side_stream(dout.device) if overlap else None
+    side_done = [None] * nset
     g_rrdb = None
-    for r in reversed(range(n_rdb)):
+    for idx, r in enumerate(reversed(range(n_rdb))):
         b = bufs[r]
+        GB, g_x5 = GBs[idx % nset], gx5s[idx % nset]
+        if side_done[idx % nset] is not None:
+            main.wait_event(side_done[idx % nset])
         if r % 3 == 2:
             a5, b1 = 0.04, 0.2
             g_rrdb = g_y
@@ -738,10 +761,10 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
             a5, b1 = 0.2, 1.0
         ops.axpby(g_y, a5, None, 0.0, g_x5)
         ci = L.rdb_conv(r, 5)
-        if fused_wgrad:
-            ops.bias_grad(g_x5, gB(ci))
-        else:
+        if not fused_wgrad:
             wgrad(View(b, CS, 0), g_x5, ci)
+        elif not overlap:
+            ops.bias_grad(g_x5, gB(ci))
         if PAIR_STAGE1 and nf == 64 and GC == 32:                                          # K=64 -> N=192 on a CTA pair
             ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True)
         else:
@@ -756,20 +779,38 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
                 wgrad(View(b, cin, 0), gk, ci, bias=False)
             o = View(GB, cin, 0)
             if k > 1:
-                ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o)                      # accumulate in place
+                ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o, pair=pair_dgrad)     # accumulate in place
             elif r % 3 == 0 and g_rrdb is not None:
                 # conv1's dgrad completes the block's input gradient: + what conv2..5 left in the x slot + the block skip
                 # (b1 * g_y) + the RRDB skip, written straight to the next gradient buffer (no separate add kernels)
-                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1, res2=g_rrdb, beta2=1.0)
+                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1, res2=g_rrdb, beta2=1.0,
+                            pair=pair_dgrad)
                 g_rrdb = None
             else:
-                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1)
-        # bias gradients of conv1..4 in one reduction: their masked output gradients are the final x1..x4 slices of GB
-        c1 = L.rdb_conv(r, 1)
-        ops.bias_grad(View(GB, 4 * GC, nf), flat[b_off[c1]:b_off[c1] + 4 * GC])
-        if fused_wgrad:     # all five filter gradients of the block: one tcgen05 launch + one reduction
-            ops.rdb_wgrad_tc(b, GB, nf, g_x5, 0, [gW(L.rdb_conv(r, k)) for k in range(1, 6)])
+                ops.conv_tc(gk, wd(ci), None, g_new, kind=TC_DGRAD, pre=o, res1=g_y, beta1=b1, pair=pair_dgrad)
+        c1, c5 = L.rdb_conv(r, 1), L.rdb_conv(r, 5)
+
+        def reductions(b=b, GB=GB, g_x5=g_x5, c1=c1, c5=c5, r=r):
+            # bias gradients of conv1..4 in one reduction (their masked output gradients are the final x1..x4 slices of GB),
+            # conv5's, and all five filter gradients of the block: one tcgen05 launch + one reduction
+            ops.bias_grad(View(GB, 4 * GC, nf), flat[b_off[c1]:b_off[c1] + 4 * GC])
+            if fused_wgrad:
+                if overlap:
+                    ops.bias_grad(g_x5, gB(c5))
+                ops.rdb_wgrad_tc(b, GB, nf, g_x5, 0, [gW(L.rdb_conv(r, k)) for k in range(1, 6)])
+        if overlap:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                reductions()
+                side_done[idx % nset] = torch.cuda.Event()
+                side_done[idx % nset].record(side)
+        else:
+            reductions()
         g_y = g_new
+    if overlap:
+        main.wait_stream(side)
     g_fea = _empty((N, H, W, nf), dev, bf)
     ops.axpby(g_y, 1.0, g_lr, 1.0, g_fea)
     wgrad(xin, g_fea, L.i_fea, cin_real=in_nc)

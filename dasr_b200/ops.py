@@ -77,6 +77,28 @@ def as_view(x):
 # fp32 generic conv
 # --------------------------------------------------------------------------------------------------
 
+F32_MATH = {'default': 0, 'fma': 1, 'tf32': 2, 'tf32x3': 3}      # DASR_F32_MATH_* (include/dasr_b200.h)
+_f32_math = [0]
+
+
+class f32_math:
+    """Arithmetic of the generic fp32 conv kernels (conv2d_f32 / wgrad) for everything launched inside the `with` block,
+    backward passes included when .backward() is called inside it:
+      'fma'    exact fp32 FMA (CUDA cores),   'tf32'   mma.sync tf32 operands / fp32 accumulate,
+      'tf32x3' hi/lo split, three MMAs (fp32-level error),   'default' = library default (env DASR_B200_F32_MATH, else fma).
+    Mixed-precision training wraps its step in f32_math('tf32'): discriminators, stride-2 / 5x5 / Cin-3 layers."""
+
+    def __init__(self, mode):
+        self.mode = F32_MATH[mode] if isinstance(mode, str) else int(mode)
+
+    def __enter__(self):
+        _f32_math.append(self.mode)
+
+    def __exit__(self, *exc):
+        _f32_math.pop()
+        return False
+
+
 def conv_f32_params(inp, out, k, stride, pad, ups=1, mode=FWD, act=ACT_NONE, slope=0.2, alpha=1.0,
                     res1=None, beta1=0.0, res2=None, beta2=0.0):
     inp, out = as_view(inp), as_view(out)
@@ -90,6 +112,7 @@ def conv_f32_params(inp, out, k, stride, pad, ups=1, mode=FWD, act=ACT_NONE, slo
     p.kh = p.kw = k
     p.stride, p.pad, p.ups, p.mode = stride, pad, ups, mode
     p.act, p.slope, p.alpha = act, slope, alpha
+    p.math = _f32_math[-1]
     if res1 is not None:
         res1 = as_view(res1)
         p.beta1, p.res1_cs, p.res1_coff = beta1, res1.cs, res1.coff
@@ -121,7 +144,7 @@ def _workspace(nbytes, device):
     pointer into the shared tensor that a later, larger eager call would replace."""
     if _capturing():
         return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-    key = str(device)
+    key = (str(device), torch.cuda.current_stream().cuda_stream)      # one scratch per stream: side-stream reductions may overlap
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
@@ -171,7 +194,7 @@ _bg_cache = {}
 def bias_grad(dy, db, accumulate=False):
     dy = as_view(dy)
     npix = dy.t.numel() // dy.cs
-    key = str(dy.t.device)
+    key = (str(dy.t.device), torch.cuda.current_stream().cuda_stream)
     if _capturing():      # graph-private partials (see _workspace)
         part = torch.empty(64 * max(dy.c, 512), dtype=torch.float32, device=dy.t.device)
     else:

@@ -43,6 +43,17 @@ def _params_frozen(net):
             p.requires_grad_(True)
 
 
+def _side_math(netG):
+    """'tf32' when the generator trains in mixed precision (DASR_B200_SIDE_MATH overrides: fma | tf32 | tf32x3), else the
+    library default (exact FMA unless DASR_B200_F32_MATH says otherwise)."""
+    import os
+    net = netG.module if hasattr(netG, 'module') else netG
+    tp = getattr(net, 'train_precision', None) or os.environ.get('DASR_B200_TRAIN_PRECISION', 'fp32')
+    if tp != 'bf16':
+        return 'default'
+    return os.environ.get('DASR_B200_SIDE_MATH', 'tf32')
+
+
 def _ragan_pair(cri_gan, pred_real, pred_fake, for_G):
     """Relativistic average GAN term of the generator (DASR_model.py:242-246): each set's scores relative to the batch
     mean (dim 0, per patch position) of the other set; the real scores carry no gradient."""
@@ -169,6 +180,11 @@ class DASR_Model(BaseModel):
 
     # ------------------------------------------------------------------------------------------ step
     def optimize_parameters(self, step):
+        # mixed-precision training: the fp32 side nets (discriminator, Cin-3 / strided layers) take tf32 tensor-core math
+        with ops.f32_math(_side_math(self.netG)):
+            self._optimize_parameters(step)
+
+    def _optimize_parameters(self, step):
         with ops.nvtx('G/forward'):
             self.fake_H = self.netG(self.var_L)
         with ops.nvtx('frequency_separation'):

@@ -65,7 +65,13 @@ typedef struct {
   float alpha;
   float beta1; int res1_cs, res1_coff;
   float beta2; int res2_cs, res2_coff;
+  int math;               /* arithmetic of the tile product: 0 = library default (env DASR_B200_F32_MATH, else FMA),
+                             DASR_F32_MATH_FMA (exact fp32 FMA), _TF32 (mma.sync tf32 operands, fp32 accumulate),
+                             _TF32X3 (hi/lo split, three tf32 MMAs: fp32-level error on tensor cores) */
 } DasrConvF32Params;
+#define DASR_F32_MATH_FMA 1
+#define DASR_F32_MATH_TF32 2
+#define DASR_F32_MATH_TF32X3 3
 
 int dasr_conv2d_f32(const float* in, const float* w_packed, const float* bias, const float* res1,
                     const float* res2, float* out, const DasrConvF32Params* p, void* stream);
@@ -91,7 +97,7 @@ size_t dasr_conv3x3_wgrad_tc_workspace(int N, int H, int W, int cin, int cout);
 int dasr_conv3x3_wgrad_tc(const void* x_bf16, int x_cs, int x_coff, const void* dy_bf16, int dy_cs, int dy_coff,
                           float* dw_oihw, int N, int H, int W, int cin, int cout, int accumulate, void* workspace,
                           size_t workspace_bytes, void* stream);
-/* db[c] (+)= sum over pixels of dout[p][c] on an NHWC channel slice (fp32 or bf16); partials >= 64*C floats */
+/* db[c] (+)= sum over pixels of dout[p][c] on an NHWC channel slice (fp32 or bf16); partials >= max(64*C, 32768) floats */
 int dasr_bias_grad(const void* dout, float* db, long npix, int C, int cs, int coff, int is_bf16, int accumulate,
                    float* partials, void* stream);
 

@@ -27,7 +27,8 @@ for r in rows[1:]:
     d = per.setdefault(kid, {'name': r[iK]})
     v = float(r[iV].replace(',', ''))
     u = r[iU]
-    scale = {'nsecond': 1e-9, 'usecond': 1e-6, 'msecond': 1e-3, 'second': 1.0, 'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1.0)
+    scale = {'ns': 1e-9, 'nsecond': 1e-9, 'us': 1e-6, 'usecond': 1e-6, 'ms': 1e-3, 'msecond': 1e-3, 's': 1.0, 'second': 1.0,
+             'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1.0)
     d[r[iM]] = v * scale
 agg = OrderedDict()
 for d in per.values():
