@@ -25,6 +25,8 @@ def main(argv):
     mirrors = [os.path.join(here, 'dsn')] if os.path.basename(sdir) == 'DSN' else [os.path.join(here, 'srn')]
     sys.path[:0] = mirrors + [root, sdir]
     sys.argv = [script] + list(argv[1:])
+    from dasr_b200.overlay import _drop_in_defaults
+    _drop_in_defaults()                      # reference scripts train in mixed precision unless DASR_B200_TRAIN_PRECISION=fp32
     os.chdir(sdir)
     runpy.run_path(script, run_name='__main__')
     return 0
