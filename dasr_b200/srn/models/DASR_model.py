@@ -322,6 +322,7 @@ class DASR_Model(BaseModel):
                 log['disc_Score/D_fake_source_H'] = L.mean(pred_d_source_fake.detach())
 
     def test(self, tsamples=False):
+        self._log_eval_precision(self.netG)
         self.netG.eval()
         with torch.no_grad():
             if self.chop:

@@ -71,6 +71,7 @@ class SRModel(BaseModel):
         self.log_dict['l_pix'] = loss.item()
 
     def test(self):
+        self._log_eval_precision(self.netG)
         self.netG.eval()
         with torch.no_grad():
             self.fake_H = forward_chop(self.var_L, self.scale, self.netG) if self.chop else self.netG(self.var_L)

@@ -96,6 +96,18 @@ class BaseModel():
         net = unwrap(network)
         return str(net), sum(p.numel() for p in net.parameters())
 
+    def _log_eval_precision(self, net):
+        """Once per model: which arithmetic produces the validation / test images (the reference validates in fp32; here
+        the default is the bf16 tensor-core path, DASR_B200_PRECISION=fp16 | fp32 for closer metrics)."""
+        if getattr(self, '_eval_precision_logged', False):
+            return
+        self._eval_precision_logged = True
+        import logging
+        import os
+        net = net.module if hasattr(net, 'module') else net
+        prec = getattr(net, 'precision', None) or os.environ.get('DASR_B200_PRECISION', 'bf16')
+        logging.getLogger('base').info('dasr_b200: test() / validation forward runs in precision [%s]' % prec)
+
     @staticmethod
     def _is_writer():
         """Under torch.distributed every replica holds the same weights: only rank 0 writes checkpoint files."""
