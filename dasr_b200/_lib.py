@@ -65,6 +65,7 @@ SYMBOLS = {
     'dasr_last_error': (C.c_char_p, []),
     'dasr_version': (_i, []),
     'dasr_conv2d_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _vp]),
+    'dasr_conv2d_in_lrelu_f32': (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _f, _vp]),
     'dasr_conv2d_wgrad_f32_workspace': (_sz, [C.POINTER(ConvF32Params)]),
     'dasr_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),
     'dasr_conv2d_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, C.POINTER(ConvF32Params), _i, _vp, _sz, _vp]),

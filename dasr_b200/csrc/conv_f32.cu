@@ -260,6 +260,154 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// conv + InstanceNorm2d(affine=False) + LeakyReLU as ONE kernel (the middle layers of NLayerDiscriminator,
+// architecture.py:998-1018: Conv2d(4x4, stride 2 | 1) -> InstanceNorm2d -> LeakyReLU(0.2)).
+// A thread-block CLUSTER owns (image n, 64 output channels): CTA `mt` of the cluster computes the 64-pixel tile mt of the
+// image with the same gathered 64x64x16 tile product as conv2d_f32_kernel (FMA or tf32 mma.sync), keeps its tile in shared
+// memory, publishes per-channel partial sums (double) there; after a cluster barrier every CTA reads all partials through
+// distributed shared memory in a fixed order (deterministic), and writes its normalised, activated tile ONCE.  Same
+// parallelism as the plain conv, no second launch, the pre-norm tensor never exists in HBM.
+// stats[n][c] = (mean, rstd) for the backward (dasr_instnorm_lrelu_bwd).  Cluster size = ceil(OH*OW / 64) <= 8.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cl_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_peer_f64(const double* local, uint32_t rank) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <bool VEC, int MATH>
+__global__ void __launch_bounds__(256) conv2d_in_lrelu_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              float* __restrict__ stats, DasrConvF32Params p, float eps,
+                                                              int mtiles) {
+  __shared__ __align__(16) float As[BK][Pad<MATH>::A];
+  __shared__ __align__(16) float Bs[BK][Pad<MATH>::B];
+  __shared__ float T[BM][BN + 1];
+  __shared__ double psum[2][BN];
+  __shared__ float s_mean[BN], s_rstd[BN];
+  const int t = threadIdx.x;
+  const int n = blockIdx.x / mtiles;
+  const int mt = (int)cl_rank();                 // == blockIdx.x % mtiles (cluster dims (mtiles, 1, 1))
+  const int co0 = blockIdx.y * BN;
+  const int HW = p.OH * p.OW;
+  const int K = p.kh * p.kw * p.cin;
+  const int a_pix = t >> 2, a_kq = t & 3;
+  const int b_k = t >> 4, b_cq = t & 15;
+  const int pm0 = mt * BM;
+  const int pl = pm0 + a_pix;
+  const bool pa_ok = pl < HW;
+  const int aoy = pa_ok ? pl / p.OW : 0, aox = pa_ok ? pl - aoy * p.OW : 0;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; e++) acc[e] = 0.f;
+  for (int kk = 0; kk < K; kk += BK) {
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (VEC) {
+        int k0 = kk + a_kq * 4;
+        int tap = k0 / p.cin, ci = k0 - tap * p.cin;
+        int dy = tap / p.kw, dx = tap - dy * p.kw;
+        int iy, ix;
+        if (pa_ok && gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
+          const float4 q = *reinterpret_cast<const float4*>(in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int k = kk + a_kq * 4 + j;
+          if (pa_ok && k < K) {
+            int tap = k / p.cin, ci = k - tap * p.cin;
+            int dy = tap / p.kw, dx = tap - dy * p.kw;
+            int iy, ix;
+            if (gather_coord(p, aoy, aox, dy, dx, iy, ix)) v[j] = in[((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) As[a_kq * 4 + j][a_pix] = v[j];
+    }
+    {
+      int k = kk + b_k;
+      int c = co0 + b_cq * 4;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const float* wp = w + (long)k * p.cout + c;
+        if (VEC) {
+          if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);
+        } else {
+          if (c + 0 < p.cout) q.x = wp[0];
+          if (c + 1 < p.cout) q.y = wp[1];
+          if (c + 2 < p.cout) q.z = wp[2];
+          if (c + 3 < p.cout) q.w = wp[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = q;
+    }
+    __syncthreads();
+    tile_product<MATH>(As, Bs, acc, t);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < 16; e++) {
+    int row, col;
+    acc_coord<MATH>(t, e, row, col);
+    const int co = co0 + col;
+    const bool ok = (pm0 + row < HW) && (co < p.cout);
+    T[row][col] = ok ? acc[e] + (bias ? bias[co] : 0.f) : 0.f;
+  }
+  __syncthreads();
+  const int rows = max(0, min(BM, HW - pm0));
+  if (t < BN) {
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < rows; r++) {
+      const double v = (double)T[r][t];
+      a += v;
+      b += v * v;
+    }
+    psum[0][t] = a;
+    psum[1][t] = b;
+  }
+  cl_barrier();                                   // every CTA of the image has published its partial sums
+  if (t < BN) {
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < mtiles; r++) {            // fixed order: identical statistics in every CTA of the cluster
+      a += ld_peer_f64(&psum[0][t], (uint32_t)r);
+      b += ld_peer_f64(&psum[1][t], (uint32_t)r);
+    }
+    const double mu = a / (double)HW;
+    double var = b / (double)HW - mu * mu;        // biased variance; double sums of fp32 values
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[t] = mean;
+    s_rstd[t] = rstd;
+    if (mt == 0 && co0 + t < p.cout) {
+      stats[((long)n * p.cout + co0 + t) * 2 + 0] = mean;
+      stats[((long)n * p.cout + co0 + t) * 2 + 1] = rstd;
+    }
+  }
+  cl_barrier();                                   // peers are done reading this CTA's shared memory; s_mean / s_rstd visible
+  const int ncol = min(BN, p.cout - co0);
+  for (int i = t; i < rows * BN; i += 256) {
+    const int r = i / BN, c = i - r * BN;
+    if (c >= ncol) continue;
+    const float v = (T[r][c] - s_mean[c]) * s_rstd[c];
+    out[((long)n * HW + pm0 + r) * p.out_cs + p.out_coff + co0 + c] = v > 0.f ? v : v * p.slope;
+  }
+}
+
 template <typename T> __device__ __forceinline__ float4 load4(const T* p);
 template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
 template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
@@ -538,6 +686,48 @@ int dasr_conv2d_f32(const float* in, const float* w, const float* bias, const fl
   }
 #undef DASR_CONV_LAUNCH
   return check_launch("conv2d_f32");
+}
+
+int dasr_conv2d_in_lrelu_f32(const float* in, const float* w, const float* bias, float* out, float* stats,
+                             const DasrConvF32Params* p, float eps, void* stream) {
+  int rc = check_conv_params(p);
+  if (rc) return rc;
+  DASR_REQUIRE(in && w && out && stats, "conv2d_in_lrelu: null argument");
+  DASR_REQUIRE(p->mode == DASR_CONV_FWD && p->ups == 1 && p->alpha == 1.f && p->beta1 == 0.f && p->beta2 == 0.f,
+               "conv2d_in_lrelu: plain forward conv only");
+  const int mtiles = cdiv((long)p->OH * p->OW, BM);
+  DASR_REQUIRE(mtiles >= 1 && mtiles <= 8 && p->slope != 0.f,
+               "conv2d_in_lrelu: %dx%d output pixels per image need a cluster of %d CTAs (max 8)", p->OH, p->OW, mtiles);
+  bool vec = (p->cin % 16 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
+             ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  const int math = resolve_math(p->math);
+  DASR_REQUIRE(math >= MATH_FMA && math <= MATH_TF32X3, "conv2d_in_lrelu: math=%d", p->math);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p->N * mtiles), (unsigned)cdiv(p->cout, BN), 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)mtiles;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+#define DASR_CIL_LAUNCH(V, M) e = cudaLaunchKernelEx(&cfg, conv2d_in_lrelu_kernel<V, M>, in, w, bias, out, stats, *p, eps, mtiles)
+  if (vec) {
+    if (math == MATH_FMA) DASR_CIL_LAUNCH(true, MATH_FMA);
+    else if (math == MATH_TF32) DASR_CIL_LAUNCH(true, MATH_TF32);
+    else DASR_CIL_LAUNCH(true, MATH_TF32X3);
+  } else {
+    if (math == MATH_FMA) DASR_CIL_LAUNCH(false, MATH_FMA);
+    else if (math == MATH_TF32) DASR_CIL_LAUNCH(false, MATH_TF32);
+    else DASR_CIL_LAUNCH(false, MATH_TF32X3);
+  }
+#undef DASR_CIL_LAUNCH
+  DASR_REQUIRE(e == cudaSuccess, "conv2d_in_lrelu: launch failed: %s", cudaGetErrorString(e));
+  return check_launch("conv2d_in_lrelu");
 }
 
 size_t dasr_conv2d_wgrad_f32_workspace(const DasrConvF32Params* p) {

@@ -973,11 +973,17 @@ def nlayer_d_forward(x, params, n_layers=2, save=False):
             raise ops._lib.DasrError('NLayerDiscriminator: input %dx%d too small' % (H, W))
         o = _empty((N, h, w, wt.shape[0]), x)
         first, last = li == 0, li == n_conv - 1
-        ops.conv2d_f32(acts[-1], ops.pack_filter_f32(wt), bs, o, 4, s, 1, act=ACT_LRELU if first else ACT_NONE, slope=0.2)
-        if not first and not last:
+        if not first and not last and ops.conv_in_lrelu_fused_ok(N, h, w, wt.shape[0]):
+            # Conv2d(4x4) -> InstanceNorm2d -> LeakyReLU(0.2) as ONE kernel (architecture.py:1005-1007, 1013-1015)
             st = _empty((N, wt.shape[0], 2), x)
-            ops.instnorm_lrelu_fwd(o, st, 1e-5, 0.2)
+            ops.conv2d_in_lrelu(acts[-1], ops.pack_filter_f32(wt), bs, o, st, 4, s, 1, 1e-5, 0.2)
             stats.append(st)
+        else:
+            ops.conv2d_f32(acts[-1], ops.pack_filter_f32(wt), bs, o, 4, s, 1, act=ACT_LRELU if first else ACT_NONE, slope=0.2)
+            if not first and not last:
+                st = _empty((N, wt.shape[0], 2), x)
+                ops.instnorm_lrelu_fwd(o, st, 1e-5, 0.2)
+                stats.append(st)
         acts.append(o)
     out = _empty((N, 1, h, w), x)
     ops.nhwc_to_nchw(acts[-1], out)

@@ -130,6 +130,20 @@ def conv2d_f32(inp, w_packed, bias, out, k, stride, pad, **kw):
                               res2.ptr if res2 else None, out.ptr, C.byref(p), _stream()), 'conv2d_f32')
 
 
+FUSED_IN_MAX_PIXELS = 512      # conv + InstanceNorm + LeakyReLU in one kernel: one cluster of <= 8 CTAs (64 pixels each) per image
+
+
+def conv_in_lrelu_fused_ok(n, oh, ow, cout):
+    return os.environ.get('DASR_B200_FUSED_IN', '1') != '0' and oh * ow <= FUSED_IN_MAX_PIXELS
+
+
+def conv2d_in_lrelu(inp, w_packed, bias, out, stats, k, stride, pad, eps=1e-5, slope=0.2):
+    """out = lrelu(instance_norm(conv(inp) + bias)), stats[n][c] = (mean, rstd): ONE kernel (dasr_conv2d_in_lrelu_f32)."""
+    p, inp, out, _, _ = conv_f32_params(inp, out, k, stride, pad, slope=slope)
+    check(_lib.load().dasr_conv2d_in_lrelu_f32(inp.ptr, _p(w_packed), _p(bias), out.ptr, _p(stats), C.byref(p), eps, _stream()),
+          'conv2d_in_lrelu')
+
+
 _ws_cache = {}
 
 

@@ -43,9 +43,15 @@ def forward_nhwc(a, layers, params, save=True):
     x = a
     H, W = a.shape[1], a.shape[2]
     acts, aux, res_stack = [a], [], []
-    for L in layers:
+    fused_next = None
+    for li, L in enumerate(layers):
         cur = acts[-1]
         op = L['op']
+        if fused_next is not None:          # this in_lrelu was computed inside the preceding conv's kernel
+            acts.append(cur)
+            aux.append(fused_next)
+            fused_next = None
+            continue
         if op == 'conv':
             wt = params[L['w']]
             if L.get('view') is not None:
@@ -57,7 +63,14 @@ def forward_nhwc(a, layers, params, save=True):
             if oh <= 0 or ow <= 0:
                 raise ops._lib.DasrError('input %dx%d too small for the network' % (H, W))
             o = torch.empty((n, oh, ow, wt.shape[0]), dtype=torch.float32, device=x.device)
-            ops.conv2d_f32(cur, ops.pack_filter_f32(wt), bs, o, L['k'], L['s'], L['p'], ups=ups, act=L.get('act', ACT_NONE), slope=0.2)
+            nxt = layers[li + 1] if li + 1 < len(layers) else None
+            if (nxt is not None and nxt['op'] == 'in_lrelu' and ups == 1 and L.get('act', ACT_NONE) == ACT_NONE
+                    and ops.conv_in_lrelu_fused_ok(n, oh, ow, wt.shape[0])):
+                # conv -> InstanceNorm -> LeakyReLU(0.2) as ONE kernel; the in_lrelu entry that follows only records the statistics
+                fused_next = torch.empty((n, wt.shape[0], 2), dtype=torch.float32, device=x.device)
+                ops.conv2d_in_lrelu(cur, ops.pack_filter_f32(wt), bs, o, fused_next, L['k'], L['s'], L['p'], 1e-5, 0.2)
+            else:
+                ops.conv2d_f32(cur, ops.pack_filter_f32(wt), bs, o, L['k'], L['s'], L['p'], ups=ups, act=L.get('act', ACT_NONE), slope=0.2)
             aux.append(None)
         elif op == 'prelu':
             o = torch.empty_like(cur)

@@ -76,6 +76,15 @@ typedef struct {
 int dasr_conv2d_f32(const float* in, const float* w_packed, const float* bias, const float* res1,
                     const float* res2, float* out, const DasrConvF32Params* p, void* stream);
 
+/* conv + InstanceNorm2d(affine=False, biased variance, eps) + LeakyReLU(p->slope) in ONE kernel: the middle layers of
+ * NLayerDiscriminator (architecture.py:998-1018, Conv2d 4x4 s2|s1 -> InstanceNorm2d -> LeakyReLU(0.2)).  A thread-block
+ * cluster per (image, 64 output channels): each CTA computes one 64-pixel tile, the channel statistics are exchanged through
+ * distributed shared memory, every tile is written once, normalised and activated.
+ * out = lrelu((conv(in) + bias - mean) * rstd), stats[n][c] = (mean, rstd) for dasr_instnorm_lrelu_bwd.
+ * p: FWD, ups 1, alpha 1, no residuals; p->act is ignored; OH*OW <= 512 (cluster of <= 8 CTAs). */
+int dasr_conv2d_in_lrelu_f32(const float* in, const float* w_packed, const float* bias /*nullable*/, float* out,
+                             float* stats /* [N][cout][2] */, const DasrConvF32Params* p, float eps, void* stream);
+
 /* Filter gradient of a FWD conv: dW (OIHW fp32, same layout as the nn.Parameter) and db.
  * Replaces autograd's conv weight/bias gradient for the convs above.  Deterministic (two-stage
  * split-K reduction, no atomics).  workspace >= dasr_conv2d_wgrad_f32_workspace(p) bytes. */

@@ -151,6 +151,38 @@ def test_nlayer_d_vs_golden(golden):
         assert abs(float(named[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
 
 
+@pytest.mark.parametrize('n_layers,hw,math', [(2, (64, 64), 'fma'), (3, (64, 48), 'fma'), (2, (44, 36), 'tf32')])
+def test_nlayer_d_one_kernel_layers_vs_oracle_and_unfused(n_layers, hw, math, monkeypatch):
+    """Conv2d(4x4) -> InstanceNorm2d -> LeakyReLU as ONE kernel (dasr_conv2d_in_lrelu_f32, taken when the batch gives >= 32
+    (image, 64-channel) CTAs): batch 16 against the CPU oracle of the reference module and against the two-kernel path
+    (forward, input gradient, parameter gradients).  tf32: the same with tensor-core math, tolerance of tf32 operands."""
+    from dasr_b200 import ops
+    from dasr_b200.srn.models.modules.architecture import NLayerDiscriminator
+    sd = O.synth_state_dict(O.nlayer_d_shapes(9, 64, n_layers), 121, 1.0)
+    x = O.synth_image((16, 9) + hw, 122)
+    ref = O.nlayer_d_forward(x[:2], sd, n_layers)
+    res = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('DASR_B200_FUSED_IN', fused)
+        net = NLayerDiscriminator(9, n_layers=n_layers)
+        net.load_state_dict(sd, strict=True)
+        net.cuda()
+        xg = x.cuda().requires_grad_(True)
+        launches = ops._lib.LAUNCHES
+        with ops.f32_math(math):
+            out = net(xg)
+            (out * O.synth(tuple(out.shape), 123).cuda()).sum().backward()
+        res[fused] = (out.detach(), xg.grad, [p.grad for p in net.parameters()], ops._lib.LAUNCHES - launches)
+    tol = FP32_TOL if math == 'fma' else 2e-2
+    assert rel_linf(res['1'][0][:2], ref) < tol
+    eq = 1e-5 if math == 'fma' else 2e-2
+    assert rel_linf(res['1'][0], res['0'][0]) < eq
+    assert rel_linf(res['1'][1], res['0'][1]) < eq * 10
+    for a, b in zip(res['1'][2], res['0'][2]):
+        assert rel_linf(a, b) < eq * 10
+    assert res['1'][3] == res['0'][3] - n_layers          # one launch less per normalised layer
+
+
 @pytest.mark.parametrize('in_nc,hw', [(3, (36, 28)), (9, (18, 22))])
 def test_nlayer_d_ragged_vs_oracle(in_nc, hw):
     from dasr_b200.srn.models.modules.architecture import NLayerDiscriminator
