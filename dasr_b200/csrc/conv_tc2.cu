@@ -76,7 +76,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int cout = p.cout;
+  const int cout = p.nt;                          // Cout tile of this CTA pair (grid.y walks the tiles; nt == cout: one tile)
+  const int co_base = (int)blockIdx.y * p.nt;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -98,7 +99,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < cout; i += TC2_THREADS) sBias[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < cout; i += TC2_THREADS) sBias[i] = a.bias ? a.bias[co_base + i] : 0.f;
   cluster_sync();                       // barriers of both CTAs initialised before any cross-CTA signal
   if (warp == 1) tmem_alloc2(tmem_ptr, 512);
   tc_fence_before();
@@ -126,7 +127,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       for (int tap = 0; tap < 9; tap++)
         for (int c = 0; c < a.nchunks; c++) {
           const int slot = tap * a.nchunks + c;
-          const int row = slot * cout + (int)rank * a.n_half;
+          const int row = slot * p.cout + co_base + (int)rank * a.n_half;
           tma2_load_2d(sW + (size_t)slot * a.n_half * ROW_B, &tmap_w, w_bar, 0, row);
         }
       pdl_wait();                       // activations are written by the previous launch
@@ -205,7 +206,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         tile_of((long)kt, x0, y0, n);                // tail tile (n >= N): zero-filled boxes still complete the barrier
         const int i = (int)(k - kt * nb);
         const int wide = i < a.nb64 ? 1 : 0;          // 64-channel block | 32-channel tail block
-        const int col = i * 64;
+        const int col = co_base + i * 64;
         mbar_expect_tx(&pre_bar[b], nld * (uint32_t)(wide ? EPI_BLK64_BYTES : EPI_BLK32_BYTES));
         if constexpr (HAS_PRE) tma_load_4d(sS + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
         if constexpr (NRES >= 1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
@@ -227,7 +228,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         const uint32_t b = k % nblk;
         if (i == 0) live = tile_of((long)(k / nb), x0, y0, n);
         mbar_wait(&sfull_bar[b], (k / nblk) & 1);
-        if (live) tma_store_4d(&em.m[(int)i < a.nb64 ? 0 : 1], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + (int)i * 64, x0, y0, n);
+        if (live) tma_store_4d(&em.m[(int)i < a.nb64 ? 0 : 1], sS + (size_t)b * EPI_BLK64_BYTES, p.out_coff + co_base + (int)i * 64, x0, y0, n);
         bulk_commit();                                // (an empty group for the tail tile keeps the group count uniform)
         if (k >= 1) {
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // everything but the newest store has been read
@@ -288,7 +289,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
           if (h == 1 && !wide) break;
           const uint32_t* rr = h ? rb : ra;
           const int cg = h ? c1 : c0;
-          const bool do_act = (act != DASR_ACT_NONE) && (cg + 16 <= p.act_cols);
+          const bool do_act = (act != DASR_ACT_NONE) && (co_base + cg + 16 <= p.act_cols);
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rr[j]);
@@ -404,7 +405,7 @@ extern "C" {
 
 static int tc2_plan(const DasrConvTcParams* p, int has_pre, int nres, int* stages_out, int* nblk_out) {
   const int nchunks = p->cin / CHUNK;
-  const long w_bytes = (long)9 * nchunks * (p->cout / 2) * ROW_B;
+  const long w_bytes = (long)9 * nchunks * (p->nt / 2) * ROW_B;
   const int a_stage = (A_HALO_BYTES + 1023) / 1024 * 1024;
   const int bar_bytes = 40 * 8 + 256 * 4 + 64;
   const int per_blk = (1 + nres) * EPI_BLK64_BYTES;
@@ -432,13 +433,15 @@ static int tc2_plan(const DasrConvTcParams* p, int has_pre, int nres, int* stage
 }
 
 int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
-  // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 epilogue in 64-channel blocks (this query assumes the
-  // worst case of a pre addend and two residual tensors)
+  // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 epilogue in 64-channel blocks
   if (!p) return 0;
   if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
-  if (p->cout % 32 != 0 || p->cout < 32 || p->cout > 256 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
+  if (p->nt % 32 != 0 || p->nt < 32 || p->nt > 256 || p->cout % p->nt != 0 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
+  // pre / residual tensors are announced through their channel strides (pre_cs, res1_cs, res2_cs > 0), as dasr_conv_tc2
+  // callers fill them; each one costs one more 16 KB block array per ring slot
   int st, nb;
-  return tc2_plan(p, 1, 2, &st, &nb);
+  const int nres = (p->res1_cs > 0 ? 1 : 0) + (p->res2_cs > 0 ? 1 : 0);
+  return tc2_plan(p, p->pre_cs > 0 ? 1 : 0, nres, &st, &nb);
 }
 
 int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
@@ -446,7 +449,8 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   DASR_REQUIRE(p && in && w && out, "conv_tc2: null argument");
   DASR_REQUIRE(p->nvar == 1 && p->ntaps == 9 && p->out_mul == 1 && p->epi_mode == 0 && p->a_mode == 0 && !p->tile_rev,
                "conv_tc2: plain 3x3 geometry with the staged epilogue only");
-  DASR_REQUIRE(p->cout % 32 == 0 && p->cout >= 32 && p->cout <= 256, "conv_tc2: cout must be a multiple of 32 in [32, 256] (got %d)", p->cout);
+  DASR_REQUIRE(p->nt % 32 == 0 && p->nt >= 32 && p->nt <= 256 && p->cout % p->nt == 0,
+               "conv_tc2: the Cout tile nt must be a multiple of 32 in [32, 256] that divides cout (nt=%d cout=%d)", p->nt, p->cout);
   DASR_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "conv_tc2: bad dims");
   DASR_REQUIRE((long)p->N * cdiv(p->W, TILE_W) * cdiv(p->H, TILE_H) < (1L << 30), "conv_tc2: too many tiles for 32-bit tile arithmetic");
   DASR_REQUIRE(p->cin > 0 && p->cin % CHUNK == 0, "conv_tc2: cin must be a multiple of 32 (got %d)", p->cin);
@@ -473,14 +477,14 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   a.p = *p;
   a.bias = bias;
   a.nchunks = p->cin / CHUNK;
-  a.n_half = p->cout / 2;
+  a.n_half = p->nt / 2;
   a.tiles_x = cdiv(p->W, TILE_W);
   a.tiles_y = cdiv(p->H, TILE_H);
   a.ntiles = (long)p->N * a.tiles_x * a.tiles_y;
   a.w_bytes = 9 * a.nchunks * a.n_half * ROW_B;
   a.a_stage_bytes = (A_HALO_BYTES + 1023) / 1024 * 1024;
-  a.nb64 = p->cout / 64;
-  a.nb = a.nb64 + ((p->cout & 32) ? 1 : 0);
+  a.nb64 = p->nt / 64;
+  a.nb = a.nb64 + ((p->nt & 32) ? 1 : 0);
   a.acc_stride = 256;
   const int bar_bytes = 40 * 8 + 256 * 4 + 64;
   int stages = 0, nblk = 0;
@@ -525,7 +529,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
       em.m[2 * t] = em.m[2 * t + 1] = tm_in;      // placeholders when unused
       if (!bases[t]) continue;
       for (int narrow = 0; narrow < 2; narrow++) {
-        if (narrow ? !(p->cout & 32) : (a.nb64 == 0)) continue;
+        if (narrow ? !(p->nt & 32) : (a.nb64 == 0)) continue;
         const int width = narrow ? 32 : 64;
         cuuint64_t gdim[4] = {(cuuint64_t)css[t], (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
         cuuint64_t gstr[3] = {(cuuint64_t)css[t] * 2, (cuuint64_t)p->W * css[t] * 2, (cuuint64_t)p->H * p->W * css[t] * 2};
@@ -553,7 +557,7 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   int gx = num_sms() & ~1;
   if ((long)gx > 2 * npairs) gx = (int)(2 * npairs);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(gx, 1, 1);
+  cfg.gridDim = dim3(gx, p->cout / p->nt, 1);
   cfg.blockDim = dim3(TC2_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;

@@ -638,6 +638,11 @@ int main(int argc, char** argv) {
         test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);       // N = 96: 64-block + tail block, pre + residuals
         test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);     // N = 160: two blocks + tail, pre only
         test_tc(1, 19, 11, 64, 96, 96, 0, 0, 4);       // N = 96 without loads
+        test_tc(1, 16, 8, 64, 128, 64, 0, 0, 4);       // Cout tiling on the pair kernel: grid.y = 2 tiles of 64
+        test_tc(2, 24, 16, 64, 128, 32, 0, 0, 5);      // 4 tiles of 32 with a pre addend (activation boundary crosses tiles)
+        test_tc(1, 20, 13, 96, 192, 96, 0, 0, 4);      // 2 tiles of 96 (64-block + tail block each)
+        test_tc(1, 16, 16, 512, 64, 32, 0, 0, 4);      // VGG conv4-like: K = 512, tiles of 32
+        test_tc(1, 16, 16, 128, 64, 64, 1, 0, 4);      // dgrad with Cout tiling (GEMM-N = 128 as 2 tiles of 64)
         g_f16 = 1;                                     // IEEE half operands / activations (inference precision 'fp16')
         test_tc(2, 32, 16, 64, 192, 192, 0, 0, 4);
         test_tc(1, 20, 13, 96, 64, 64, 0, 0, 5);

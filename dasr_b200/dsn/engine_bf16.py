@@ -6,10 +6,16 @@ weights, fp32 filter gradients.  Opt-in: De_resnet.precision = 'bf16' or DASR_B2
 import torch
 
 from dasr_b200 import ops, seqnet
+from dasr_b200 import engine as _engine
 from dasr_b200.engine import _PackCache, _pad_filter, _pick_nt_staged
 from dasr_b200.ops import ACT_NONE, TC_DGRAD, TC_FPROP, View
 
 BF = torch.bfloat16
+
+
+def _pair(nf):
+    """64 -> 64 trunk convs on the CTA-pair kernel: 64 instead of 84 cycles per MMA (DASR_B200_PAIR=0 switches back)."""
+    return _engine.PAIR_MODE and nf % 64 == 0 and nf <= 256
 
 
 def forward(x, params, n_res, tail_layers, tail_params, save):
@@ -31,11 +37,11 @@ def forward(x, params, n_res, tail_layers, tail_params, save):
     for i in range(n_res):
         w1, b1, a, w2, b2 = params[3 + 5 * i:8 + 5 * i]
         z1 = torch.empty_like(y)
-        ops.conv_tc(y, pk(w1, TC_FPROP), b1, z1, nt=nt)
+        ops.conv_tc(y, pk(w1, TC_FPROP), b1, z1, nt=nt, pair=_pair(nf))
         y1 = torch.empty_like(y)
         ops.prelu_fwd(z1, a, y1)
         yo = torch.empty_like(y)
-        ops.conv_tc(y1, pk(w2, TC_FPROP), b2, yo, nt=nt, res1=y, beta1=1.0)          # x + residual (model.py:224)
+        ops.conv_tc(y1, pk(w2, TC_FPROP), b2, yo, nt=nt, res1=y, beta1=1.0, pair=_pair(nf))          # x + residual (model.py:224)
         blocks.append((y, z1, y1))
         y = yo
     t = torch.empty((N, H, W, nf), dtype=torch.float32, device=dev)
@@ -70,14 +76,14 @@ def backward(ctx, params, n_res, tail_layers, tail_params, dout):
         ops.conv3x3_wgrad_tc(y1, gy, gw2)
         ops.bias_grad(gy, gb2)
         gy1 = torch.empty_like(gy)
-        ops.conv_tc(gy, pk(w2), None, gy1, kind=TC_DGRAD, nt=nt)
+        ops.conv_tc(gy, pk(w2), None, gy1, kind=TC_DGRAD, nt=nt, pair=_pair(nf))
         gz1 = torch.empty_like(gy)
         ops.prelu_bwd(z1, gy1, a, gz1, ga)
         del gy1
         ops.conv3x3_wgrad_tc(y_in, gz1, gw1)
         ops.bias_grad(gz1, gb1)
         gin = torch.empty_like(gy)
-        ops.conv_tc(gz1, pk(w1), None, gin, kind=TC_DGRAD, nt=nt, res1=gy, beta1=1.0)   # + gradient of the skip connection
+        ops.conv_tc(gz1, pk(w1), None, gin, kind=TC_DGRAD, nt=nt, res1=gy, beta1=1.0, pair=_pair(nf))   # + gradient of the skip connection
         gy = gin
     gz0 = torch.empty_like(gy)
     ops.prelu_bwd(z0, gy, params[2], gz0, grads[2])

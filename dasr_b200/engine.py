@@ -1126,6 +1126,19 @@ def vgg_backward(ctx, params, std, dout, cache=None):
     return dx
 
 
+_VGG_NT = {}
+
+
+def _vgg_pair_nt(k_ch, n_ch):
+    """Cout tile of a VGG conv (GEMM-K = k_ch, GEMM-N = n_ch channels) on the CTA-pair kernel, or None (DASR_B200_PAIR=0)."""
+    if not PAIR_MODE or os.environ.get('DASR_B200_VGG_PAIR', '1') == '0' or k_ch % 32 or n_ch % 32:
+        return None
+    key = (k_ch, n_ch)
+    if key not in _VGG_NT:
+        _VGG_NT[key] = ops.pick_nt_pair(k_ch, n_ch)
+    return _VGG_NT[key]
+
+
 def vgg_forward_bf16(x, params, mean, std, feature_layer=34, save=False, cache=None):
     """VGG19 features on the tcgen05 conv (bf16 activations/filters, fp32 accumulate).  Filters of the 256/512-channel
     layers do not fit shared memory whole, so those layers run as Cout/nt column tiles (grid.y) of 16..64 channels."""
@@ -1151,8 +1164,12 @@ def vgg_forward_bf16(x, params, mean, std, feature_layer=34, save=False, cache=N
             mk = lambda wt=wt, cin=cin: ops.pack_filter_tc(_pad_filter(wt, cin_to=cin), TC_FPROP)
             pk = cache.get(('vtf', key), wt, mk) if cache is not None else mk()
             o = torch.empty((N, h, w, wt.shape[0]), dtype=torch.bfloat16, device=x.device)
-            ops.conv_tc(cur, pk, bs, o, kind=TC_FPROP, nt=_pick_nt_staged(wt.shape[0], cin),
-                        act=ACT_RELU if step[1] else ACT_NONE)
+            ntp = _vgg_pair_nt(cin, wt.shape[0])
+            if ntp:     # CTA pair: twice the resident-filter budget -> Cout tiles of 32..128 instead of 16..64 at 64-cycle MMAs
+                ops.conv_tc(cur, pk, bs, o, kind=TC_FPROP, nt=ntp, act=ACT_RELU if step[1] else ACT_NONE, pair=True)
+            else:
+                ops.conv_tc(cur, pk, bs, o, kind=TC_FPROP, nt=_pick_nt_staged(wt.shape[0], cin),
+                            act=ACT_RELU if step[1] else ACT_NONE)
         acts.append(o)
     Cf = acts[-1].shape[3]
     out = _empty((N, Cf, h, w), x)
@@ -1181,7 +1198,11 @@ def vgg_backward_bf16(ctx, params, std, dout, cache=None):
             mk = lambda wt=wt, cin=cin: ops.pack_filter_tc(_pad_filter(wt, cin_to=cin), TC_DGRAD)
             pk = cache.get(('vtd', pi), wt, mk) if cache is not None else mk()
             gin = torch.empty_like(acts[li])
-            ops.conv_tc(g, pk, None, gin, kind=TC_DGRAD, nt=_pick_nt_staged(cin, wt.shape[0]))
+            ntp = _vgg_pair_nt(wt.shape[0], cin)
+            if ntp:
+                ops.conv_tc(g, pk, None, gin, kind=TC_DGRAD, nt=ntp, pair=True)
+            else:
+                ops.conv_tc(g, pk, None, gin, kind=TC_DGRAD, nt=_pick_nt_staged(cin, wt.shape[0]))
         g = gin
     dx = _empty((N, C0, H, W), dout)
     inv_std = (1.0 / std.float()).contiguous() if std is not None else None

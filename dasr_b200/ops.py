@@ -308,13 +308,31 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     if pair:
         if mask is not None:
             raise _lib.DasrError('conv_tc: the CTA-pair kernel has no mask input')
-        p.nt = p.cout
+        p.nt = nt if nt else p.cout              # Cout tile per CTA pair (grid.y = cout / nt); default: one tile
         p.epi_mode = 0
         check(lib.dasr_conv_tc2(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
                                 res2.ptr if res2 else None, out.ptr, C.byref(p), _stream()), 'conv_tc2')
         return
     check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
                            res2.ptr if res2 else None, mask.ptr if mask else None, out.ptr, C.byref(p), _stream()), 'conv_tc')
+
+
+def pick_nt_pair(cin, cout):
+    """Largest Cout tile (multiple of 32, <= 256, divides cout) whose half filter set + epilogue ring + A stages fit one SM
+    of a CTA pair (dasr_conv_tc2_supported); None if the layer cannot run on the pair kernel."""
+    lib = _lib.load()
+    p = ConvTcParams()
+    check(lib.dasr_conv_tc_setup(C.byref(p), TC_FPROP), 'conv_tc_setup', 0)
+    p.N = p.H = p.W = 1
+    p.cin, p.cout = cin, cout
+    nt = min(cout, 256)
+    while nt >= 32:
+        if cout % nt == 0 and nt % 32 == 0:
+            p.nt = nt
+            if lib.dasr_conv_tc2_supported(C.byref(p)):
+                return nt
+        nt //= 2
+    return None
 
 
 def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):

@@ -174,8 +174,10 @@ int dasr_conv_tc(const void* in_bf16, const void* w_packed_bf16, const float* bi
  * the filter rows resident and each load the A tile of their own pixel tile; one M=256 instruction feeds both tensor
  * cores (measured: 64 cycles per K step and pixel tile for N <= 128, N/2 above, against 84 / N/2+5 on one CTA), and a
  * filter set twice as large fits (dense-block launch 1: K = 64, N = 192).
- * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0, cout % 32 == 0; pre / res1 / res2 as in
- * dasr_conv_tc (nullable).  `nt` is ignored (one Cout tile = cout). */
+ * Supported: plain 3x3 geometry (dasr_conv_tc_setup kind 0/1), epi_mode 0; `nt` = Cout tile of a CTA pair (multiple of
+ * 32, <= 256, divides cout; grid.y walks the tiles — VGG's 256/512-channel layers run as tiles of 32..128); pre / res1 /
+ * res2 as in dasr_conv_tc (nullable).  dasr_conv_tc2_supported answers for the loads announced by pre_cs / res1_cs /
+ * res2_cs > 0. */
 int dasr_conv_tc2_supported(const DasrConvTcParams* p);
 int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* pre_bf16,
                   const void* res1_bf16, const void* res2_bf16, void* out_bf16, const DasrConvTcParams* p, void* stream);

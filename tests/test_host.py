@@ -328,3 +328,31 @@ def test_ddm_window_ranges_reproduce_the_reference_scatter(golden):
                 out[y, x] = blk.sum() / blk.size if blk.size else np.nan
         ref = c['ddm'].numpy()[0, 0]
         assert np.allclose(out, ref, rtol=1e-12, atol=1e-12, equal_nan=True), c['name']
+
+
+def test_f32_math_context_and_fused_layer_eligibility(monkeypatch):
+    """ops.f32_math nests (the arithmetic of the generic conv kernels inside a step); the one-kernel discriminator layer is
+    taken for feature maps of at most 8 x 64 pixels (cluster of <= 8 CTAs) and can be switched off."""
+    from dasr_b200 import ops
+    assert ops._f32_math[-1] == 0
+    with ops.f32_math('tf32'):
+        assert ops._f32_math[-1] == ops.F32_MATH['tf32'] == 2
+        with ops.f32_math('fma'):
+            assert ops._f32_math[-1] == 1
+        assert ops._f32_math[-1] == 2
+    assert ops._f32_math[-1] == 0
+    assert ops.conv_in_lrelu_fused_ok(32, 16, 16, 128) and ops.conv_in_lrelu_fused_ok(1, 22, 23, 64)
+    assert not ops.conv_in_lrelu_fused_ok(32, 32, 32, 128)
+    monkeypatch.setenv('DASR_B200_FUSED_IN', '0')
+    assert not ops.conv_in_lrelu_fused_ok(32, 16, 16, 128)
+
+
+def test_drop_in_entry_points_default_to_mixed_precision(monkeypatch):
+    """dasr_b200.launch / the import overlay set DASR_B200_TRAIN_PRECISION=bf16 unless the user chose a mode."""
+    from dasr_b200 import overlay
+    monkeypatch.delenv('DASR_B200_TRAIN_PRECISION', raising=False)
+    overlay._drop_in_defaults()
+    assert os.environ['DASR_B200_TRAIN_PRECISION'] == 'bf16'
+    monkeypatch.setenv('DASR_B200_TRAIN_PRECISION', 'fp32')
+    overlay._drop_in_defaults()
+    assert os.environ['DASR_B200_TRAIN_PRECISION'] == 'fp32'
