@@ -233,6 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // Feeds the staged epilogue: pre-activation / residual tiles in (nbuf tiles ahead), finished tiles out.
     if constexpr (EPI_MODE == 0) {
       const int co_base = p.out_coff + ntile * nt;
+      const int omap = (p.out_mul == 2) ? 2 * var : 0;      // sub-pixel variants: one strided output map pair per parity
       const uint32_t load_bytes = (uint32_t)(((HAS_PRE ? 1 : 0) + NRES) * a.epi_bytes);
       pdl_wait();                      // pre / residual tiles and the output slots belong to earlier launches until now
       auto tile_xyz = [&](long tile, int& x0, int& y0, int& n) {
@@ -290,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           for (int i = 0; i < nb64 + (tail32 ? 1 : 0); i++) {
             const int wide = i < nb64;
             const int off = wide ? i * EPI_BLK64_BYTES : nb64 * EPI_BLK64_BYTES;
-            tma_store_4d(&em.m[wide ? 0 : 1], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
+            tma_store_4d(&em.m[(wide ? 0 : 1) + omap], sS + b * a.epi_bytes + off, co_base + (wide ? i * 64 : nb64 * 64), x0, y0, n);
           }
           bulk_commit();
           if (prev_tile >= 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the previous tile's stores have read their buffer
@@ -756,10 +757,13 @@ int dasr_pack_filter_tc_batch(const DasrPackJob* jobs_dev, int njobs, int blocks
   return check_launch("pack_filter_tc_batch");
 }
 
+// mul = 1: the [N, H, W, cs] tensor at `base`.  mul = 2: the sub-pixel view out[n, 2y + py, 2x + px, c] of a [N, 2H, 2W, cs]
+// tensor (the caller offsets `base` to pixel (py, px)): same W x H index space as the input tiles, doubled pixel strides —
+// the four parity variants of the fused nearest-x2 conv store their tiles through TMA like any other layer.
 static int encode_act_map(PFN_encodeTiled enc, CUtensorMap* tm, const void* base, int cs, int W, int H, int N,
-                          int width, const char* what) {
+                          int width, const char* what, int mul = 1) {
   cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)mul * cs * 2, (cuuint64_t)mul * (mul * W) * cs * 2, (cuuint64_t)(mul * H) * (mul * W) * cs * 2};
   cuuint32_t box[4] = {(cuuint32_t)width, TILE_W, TILE_H, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
@@ -800,7 +804,9 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
     DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc: output slice");
   }
   if (p->epi_mode == 0) {
-    DASR_REQUIRE(p->out_mul == 1 && p->nt % 32 == 0 && !mask_src, "conv_tc: staged epilogue needs out_mul=1, nt%%32==0, no mask");
+    DASR_REQUIRE(p->nt % 32 == 0 && !mask_src, "conv_tc: staged epilogue needs nt%%32==0, no mask");
+    DASR_REQUIRE(p->out_mul == 1 || (!pre && !res1 && !res2),
+                 "conv_tc: the staged epilogue of the sub-pixel (out_mul=2) variants has no pre / residual inputs");
   } else {
     DASR_REQUIRE(!pre, "conv_tc: the pre-activation addend is only supported by the staged epilogue (epi_mode 0)");
   }
@@ -901,6 +907,15 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
     const int css[4] = {p->out_cs, p->pre_cs, p->res1_cs, p->res2_cs};
     const int used[4] = {1, a.has_pre, a.has_res1, a.has_res2};
     const char* names[4] = {"output", "pre", "res1", "res2"};
+    if (p->out_mul == 2) {
+      // one output map pair per parity variant (slots 2v, 2v + 1; no pre / residual maps in this mode)
+      for (int v = 0; v < p->nvar && v < 4; v++) {
+        const char* vb = (const char*)out + ((size_t)p->out_py[v] * (2 * p->W) + p->out_px[v]) * p->out_cs * 2;
+        int rc;
+        if (p->nt >= 64 && (rc = encode_act_map(enc, &em.m[2 * v], vb, p->out_cs, p->W, p->H, p->N, 64, "output", 2))) return rc;
+        if ((p->nt & 32) && (rc = encode_act_map(enc, &em.m[2 * v + 1], vb, p->out_cs, p->W, p->H, p->N, 32, "output", 2))) return rc;
+      }
+    } else
     for (int t = 0; t < 4; t++) {
       if (!used[t]) continue;
       int rc;

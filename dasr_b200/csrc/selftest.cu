@@ -175,6 +175,7 @@ static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
 }
 // 16-bit storage of the tensor-core conv tests: bf16, or IEEE half bits carried in the same 2-byte slots (g_f16)
 static int g_f16 = 0;
+static int g_up_staged = 0;   // sub-pixel upconv variants through the staged TMA-store epilogue (strided output maps)
 static std::vector<__nv_bfloat16> to_h16(const std::vector<float>& v) {
   if (!g_f16) return to_bf16(v);
   std::vector<__nv_bfloat16> o(v.size());
@@ -273,7 +274,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
   p.a_mode = a_mode;
   p.f16 = g_f16;
-  p.epi_mode = (kind == 2 || epi == 1 || nt % 32) ? 1 : 0;
+  p.epi_mode = ((kind == 2 && !g_up_staged) || epi == 1 || nt % 32) ? 1 : 0;
   float* dnchw = nullptr;
   if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
   rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind | (g_f16 ? DASR_TC_PACK_F16 : 0), 0);
@@ -654,6 +655,13 @@ int main(int argc, char** argv) {
         g_f16 = 0;
       }
       test_tc(1, 16, 16, 64, 64, 64, 2, am, 1);        // upsample-fused
+      if (am == 0) {
+        g_up_staged = 1;                               // the same through strided output tensor maps + TMA stores
+        test_tc(1, 16, 16, 64, 64, 64, 2, am, 0);
+        test_tc(2, 19, 9, 64, 64, 64, 2, am, 0);       // ragged tiles: TMA clips in the (W, H) index space of the variant view
+        test_tc(1, 20, 13, 32, 96, 96, 2, am, 0);      // 64-block + 32-tail block
+        g_up_staged = 0;
+      }
       test_tc(2, 19, 9, 64, 64, 32, 2, am, 0);
     }
   }

@@ -288,7 +288,11 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     p.nt = nt if nt else out.c
     p.act, p.slope, p.alpha = act, slope, alpha
     p.act_cols = (out.c if act != ACT_NONE else 0) if act_cols is None else act_cols
-    p.epi_mode = 0 if (p.out_mul == 1 and p.nt % 32 == 0 and mask is None) else 1
+    # staged (TMA-store) epilogue whenever the tile is a multiple of 32 channels; the sub-pixel upconv variants (out_mul 2)
+    # take it when they carry no pre / residual inputs (DASR_B200_UP_STAGED=0: direct stores)
+    staged_up = (p.out_mul == 2 and pre is None and res1 is None and res2 is None
+                 and os.environ.get('DASR_B200_UP_STAGED', '1') != '0')
+    p.epi_mode = 0 if ((p.out_mul == 1 or staged_up) and p.nt % 32 == 0 and mask is None) else 1
     if pre is not None:
         pre = as_view(pre)
         p.pre_cs, p.pre_coff = pre.cs, pre.coff
