@@ -174,7 +174,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the tcgen05.mma
     // instructions, so descriptors live in uniform registers and no per-lane serialisation is emitted.
     const uint32_t idesc = make_idesc_16(128, nt, p.f16);
-    const uint32_t a_sbo = (p.a_mode == 0) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
+    // EPI_MODE 3 ("taps in N", last layer): the halo tile is read as a PLAIN 180-row K-major tile (8-row groups 512 B apart)
+    const uint32_t a_sbo = (p.a_mode == 0 && EPI_MODE != 3) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
     const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
     const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
     const uint32_t a_lo0 = smem_u32(sA) >> 4;
@@ -211,14 +212,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage_lo;
           uint32_t b_lo = b_lo0 + (uint32_t)c * b_slot_lo;
           const uint32_t b_tap_step = (uint32_t)a.nchunks * b_slot_lo;
+          if constexpr (EPI_MODE == 3) {
+            // D'[halo pixel][tap * out_nc + c] = A[halo pixel][K] * B'[K][tap * out_nc + c]: every halo pixel against the
+            // filters of ALL taps at once — 2 M-halves (halo rows 0..127, 128..255; rows >= 180 are never read) x 2 K steps
+            // instead of 9 taps x 2 K steps; the epilogue adds the nine shifted partial results.
 #pragma unroll
-          for (int tap = 0; tap < 9; tap++) {
-            if (tap < ntaps) {
-              const uint32_t al = a_lo + tap_lo[tap];
-              umma_bf16(d_tmem, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
-                        (uint32_t)((c | tap) != 0));
-              umma_bf16(d_tmem, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
-              b_lo += b_tap_step;
+            for (int mh = 0; mh < 2; mh++) {
+              const uint32_t al = a_lo + (uint32_t)mh * ((128u * ROW_B) >> 4);
+              umma_bf16(d_tmem + (uint32_t)mh * 32u, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
+                        (uint32_t)(c != 0));
+              umma_bf16(d_tmem + (uint32_t)mh * 32u, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+              if (tap < ntaps) {
+                const uint32_t al = a_lo + tap_lo[tap];
+                umma_bf16(d_tmem, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
+                          (uint32_t)((c | tap) != 0));
+                umma_bf16(d_tmem, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
+                b_lo += b_tap_step;
+              }
             }
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
@@ -354,6 +368,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         else if (it >= (uint32_t)nbuf) mbar_wait(&sfree_bar[sb], sphase ^ 1); // stores of tile it-nbuf have read the buffer
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      if constexpr (EPI_MODE == 3) {
+        // phase 1: D' rows (halo pixels) -> shared memory.  Warpgroup wg holds halo rows wg*128 + q*32 + lane.
+        float* S = reinterpret_cast<float*>(sS);
+        constexpr int SROW = 29;                                   // floats per halo pixel (27 used; odd stride: no bank conflicts)
+        const int hrow = wg * 128 + m;
+        uint32_t r0[16], r1[16];
+        tmem_ld16(t_addr + wg * 32, r0);
+        tmem_ld16(t_addr + wg * 32 + 16, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);              // accumulator free for the MMA warp
+        if (hrow < HALO_W * HALO_H) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) S[hrow * SROW + j] = __uint_as_float(r0[j]);
+#pragma unroll
+          for (int j = 0; j < 11; j++) S[hrow * SROW + 16 + j] = __uint_as_float(r1[j]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        // phase 2: output pixel (py, px) of the tile = sum over the nine taps of the partial result of its neighbour
+        if (wg == 0 && valid) {
+          float* of = reinterpret_cast<float*>(a.out);
+          const long plane = (long)OH * OW;
+          const int onc = p.out_nc;
+          for (int c = 0; c < onc; c++) {
+            float v = has_bias ? sBias[c] : 0.f;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; t9++) v += S[((py + t9 / 3) * HALO_W + (px + t9 % 3)) * SROW + t9 * onc + c];
+            if (act != DASR_ACT_NONE && p.act_cols > 0) v = (act == DASR_ACT_LRELU) ? fmaxf(v, v * slope) : fmaxf(v, 0.f);
+            of[((long)n * onc + c) * plane + (long)oy * OW + ox] = v * alpha;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // S may be overwritten by the next tile
+        continue;
+      }
       // One 16-column group: registers -> (+bias, +pre) -> act -> scale -> (+residuals) -> bf16 -> staged tile / global.
       auto process = [&](const uint32_t* rr, int g) {
         const int cg = g << 4;
@@ -512,6 +561,19 @@ __global__ void pack_filter_tc_kernel(const float* __restrict__ w, unsigned shor
                                       int kind, int f16) {
   const int gn = (kind == 1) ? cin : cout;   // GEMM N (output channels of this conv)
   const int gk = (kind == 1) ? cout : cin;   // GEMM K channels
+  if (kind == 3) {      // "taps in N" (last layer, cout <= 3): [chunk][n' = tap * cout + c (padded to 32)][32 channels]
+    const long total3 = (long)(cin / CHUNK) * 32 * CHUNK;
+    const long i3 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i3 >= total3) return;
+    const int kc3 = (int)(i3 % CHUNK), n3 = (int)((i3 / CHUNK) % 32), c3 = (int)(i3 / (CHUNK * 32));
+    float v3 = 0.f;
+    if (n3 < 9 * cout) {
+      const int tap = n3 / cout, co = n3 - tap * cout;
+      v3 = w[((long)co * cin + c3 * CHUNK + kc3) * 9 + tap];
+    }
+    o[i3] = f16 ? __half_as_ushort(__float2half_rn(v3)) : __bfloat16_as_ushort(__float2bfloat16(v3));
+    return;
+  }
   const int nvar = (kind == 2) ? 4 : 1, ntaps = (kind == 2) ? 4 : 9, nchunks = gk / CHUNK;
   long total = (long)nvar * ntaps * nchunks * gn * CHUNK;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -727,6 +789,12 @@ int dasr_conv_tc_setup(DasrConvTcParams* p, int kind) {
         p->tap_dx[v][t] = (int8_t)(px + (t & 1));
       }
     }
+  } else if (kind == 3) {      // last layer with the taps folded into GEMM-N (epi_mode 3): one plain pass over the halo tile
+    p->nvar = 1;
+    p->ntaps = 1;
+    p->out_mul = 1;
+    p->tap_dy[0][0] = p->tap_dx[0][0] = 0;
+    p->out_py[0] = p->out_px[0] = 0;
   } else {
     set_error("conv_tc_setup: unknown kind %d", kind);
     return DASR_E_BADARG;
@@ -735,6 +803,7 @@ int dasr_conv_tc_setup(DasrConvTcParams* p, int kind) {
 }
 
 size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind) {
+  if (kind == 3) return (size_t)(cin / CHUNK) * 32 * CHUNK * 2;
   int nvar = (kind == 2) ? 4 : 1, ntaps = (kind == 2) ? 4 : 9;
   return (size_t)nvar * ntaps * cout * cin * 2;
 }
@@ -742,7 +811,8 @@ size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind) {
 int dasr_pack_filter_tc(const float* w, void* o, int cout, int cin, int kind, void* stream) {
   const int f16 = (kind & DASR_TC_PACK_F16) != 0;      // IEEE half instead of bf16 (inference precision 'fp16')
   kind &= ~DASR_TC_PACK_F16;
-  DASR_REQUIRE(kind >= 0 && kind <= 2, "pack_filter_tc: kind");
+  DASR_REQUIRE(kind >= 0 && kind <= 3, "pack_filter_tc: kind");
+  DASR_REQUIRE(kind != 3 || (cout >= 1 && 9 * cout <= 32), "pack_filter_tc: kind 3 (taps in N) needs cout <= 3");
   int gk = (kind == 1) ? cout : cin;
   DASR_REQUIRE(gk % CHUNK == 0, "pack_filter_tc: contraction channels (%d) must be a multiple of 32", gk);
   long total = (long)dasr_pack_filter_tc_bytes(cout, cin, kind) / 2;
@@ -794,12 +864,16 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
                p->nt, p->cout);
   DASR_REQUIRE(p->nvar >= 1 && p->nvar <= 4 && p->ntaps >= 1 && p->ntaps <= 9, "conv_tc: variants/taps");
   DASR_REQUIRE(p->out_mul == 1 || p->out_mul == 2, "conv_tc: out_mul");
-  DASR_REQUIRE(p->epi_mode >= 0 && p->epi_mode <= 2, "conv_tc: epi_mode");
+  DASR_REQUIRE(p->epi_mode >= 0 && p->epi_mode <= 3, "conv_tc: epi_mode");
   DASR_REQUIRE(p->f16 == 0 || (p->f16 == 1 && !mask_src), "conv_tc: f16 must be 0/1; the dgrad mask input is bf16 only");
   DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc: act_cols must be a multiple of 16");
   if (p->epi_mode == 2) {
     DASR_REQUIRE(p->out_nc >= 1 && p->out_nc <= 16 && p->nt == p->cout && !res1 && !res2 && !pre && !mask_src,
                  "conv_tc: NCHW-fp32 epilogue supports out_nc<=16, one Cout tile, no residuals");
+  } else if (p->epi_mode == 3) {
+    DASR_REQUIRE(p->out_nc >= 1 && 9 * p->out_nc <= 32 && p->nt == 32 && p->cout == 32 && p->ntaps == 1 && p->nvar == 1 &&
+                     p->a_mode == 0 && p->out_mul == 1 && !res1 && !res2 && !pre && !mask_src && !p->tile_rev,
+                 "conv_tc: epi_mode 3 (taps in N, NCHW fp32 out) needs dasr_conv_tc_setup kind 3, out_nc <= 3, nt = cout = 32");
   } else {
     DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc: output slice");
   }
@@ -836,23 +910,23 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   a.ntiles = (long)p->N * a.tiles_x * a.tiles_y;
   a.w_bytes = p->ntaps * a.nchunks * p->nt * ROW_B;
   a.a_stage_bytes = (p->a_mode == 0) ? ((A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
-  a.acc_stride = pow2_at_least(p->nt);
+  a.acc_stride = (p->epi_mode == 3) ? 64 : pow2_at_least(p->nt);      // mode 3: two M-halves of 32 columns
   a.nacc = (a.acc_stride <= 128) ? 4 : 2;          // 512 TMEM columns: 4 accumulators up to N = 128, else 2
   a.tmem_cols = a.nacc * a.acc_stride;
   if (a.tmem_cols < 32) a.tmem_cols = 32;
   a.has_pre = (p->epi_mode == 0 && pre) ? 1 : 0;
   a.has_res1 = (p->epi_mode == 0 && res1) ? 1 : 0;
   a.has_res2 = (p->epi_mode == 0 && res2) ? 1 : 0;
-  a.epi_bytes = (p->epi_mode == 0) ? p->nt * 128 * 2 : 0;
+  a.epi_bytes = (p->epi_mode == 0) ? p->nt * 128 * 2 : (p->epi_mode == 3 ? 21504 : 0);   // mode 3: 180 halo pixels x 29 floats
   const int bar_bytes = (2 * MAX_STAGES + 22) * 8 + 256 * 4 + 16;
   // staged-epilogue buffers: as many (<= 4) as still leave 4 A stages; loads of pre / residual tiles are issued nbuf
   // tiles ahead, which hides their latency (with 2 the read-modify-write launches are bound by that round trip)
-  int nbuf = (p->epi_mode == 0) ? 4 : 2;
+  int nbuf = (p->epi_mode == 0) ? 4 : (p->epi_mode == 3 ? 1 : 2);
   int epi_total = 0, avail = 0;
   for (;; nbuf--) {
     epi_total = nbuf * a.epi_bytes * (1 + a.has_res1 + a.has_res2);
     avail = SMEM_LIMIT - 1024 /*alignment slack*/ - a.w_bytes - epi_total - bar_bytes;
-    if (nbuf == 2 || avail >= 4 * a.a_stage_bytes) break;
+    if (nbuf <= 2 || avail >= 4 * a.a_stage_bytes) break;
   }
   a.nbuf = nbuf;
   int stages = avail / a.a_stage_bytes;
@@ -925,13 +999,13 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   }
 
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const TcKernelArgs);
-  static const KernelFn kernels[8] = {
+  static const KernelFn kernels[9] = {
       conv_tc_kernel<0, false, 0>, conv_tc_kernel<0, false, 1>, conv_tc_kernel<0, false, 2>,
       conv_tc_kernel<0, true, 0>,  conv_tc_kernel<0, true, 1>,  conv_tc_kernel<0, true, 2>,
-      conv_tc_kernel<1, false, 0>, conv_tc_kernel<2, false, 0>};
-  const int ki = (p->epi_mode == 0) ? (a.has_pre * 3 + a.has_res1 + a.has_res2) : (p->epi_mode == 1 ? 6 : 7);
+      conv_tc_kernel<1, false, 0>, conv_tc_kernel<2, false, 0>, conv_tc_kernel<3, false, 0>};
+  const int ki = (p->epi_mode == 0) ? (a.has_pre * 3 + a.has_res1 + a.has_res2) : (5 + p->epi_mode);
   if (p->epi_mode == 0) DASR_REQUIRE(!(a.has_res2 && !a.has_res1), "conv_tc: res2 without res1");
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  static bool attr_set[9] = {false, false, false, false, false, false, false, false, false};
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) {

@@ -277,7 +277,16 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   p.epi_mode = ((kind == 2 && !g_up_staged) || epi == 1 || nt % 32) ? 1 : 0;
   float* dnchw = nullptr;
   if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
-  rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, kind | (g_f16 ? DASR_TC_PACK_F16 : 0), 0);
+  int pack_kind = kind;
+  if (epi == 6) {      // last layer with the taps folded into GEMM-N: real cout = gn (<= 3), the kernel sees nt = cout = 32
+    rc |= dasr_conv_tc_setup(&p, 3);
+    p.cout = 32; p.nt = 32; p.out_cs = 32; p.out_coff = 0; p.act_cols = 0;
+    p.epi_mode = 3; p.out_nc = gn; pack_kind = 3; p.act = DASR_ACT_NONE; p.alpha = 1.f;
+    dnchw = dalloc<float>((size_t)N * 3 * OH * OW);
+    cudaFree(db); db = dalloc<float>(32); h2d(db, b);
+    cudaFree(dwp); CK(cudaMalloc(&dwp, dasr_pack_filter_tc_bytes(cout, cin, 3)));
+  }
+  rc |= dasr_pack_filter_tc(dw, dwp, cout, cin, pack_kind | (g_f16 ? DASR_TC_PACK_F16 : 0), 0);
   // res2 for epi 2 = res1 shifted by one pixel (same buffer, pointer offset of gn elements, wraps at the end -> use a copy)
   __nv_bfloat16* dres2 = nullptr;
   if ((epi == 2 || epi == 5) && gn <= 96) {
@@ -292,7 +301,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     rc |= dasr_conv_tc2(din, dwp, db, dmsk, gn <= 96 ? dres : nullptr, dres2, dout, &p, 0);
   else
     rc |= dasr_conv_tc(din, dwp, db, epi == 2 ? dmsk : nullptr, (epi == 1 || (epi == 2 && gn <= 96)) ? dres : nullptr, dres2,
-                       epi == 1 ? dmsk : nullptr, epi == 3 ? (void*)dnchw : (void*)dout, &p, 0);
+                       epi == 1 ? dmsk : nullptr, (epi == 3 || epi == 6) ? (void*)dnchw : (void*)dout, &p, 0);
   cudaError_t e = cudaDeviceSynchronize();
   snprintf(name, sizeof(name), "conv_tc%s kind%d amode%d N%d %dx%d K%d N%d nt%d epi%d mode%d", g_f16 ? " f16" : "", kind, a_mode, N, H, W, gk, gn, nt, epi, p.epi_mode);
   if (rc == DASR_E_SMEM && e == cudaSuccess) {
@@ -306,13 +315,14 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     return;
   }
   double me = 0, mref = 0;
-  if (epi == 3) {
+  if (epi == 3 || epi == 6) {
     auto gotf = d2h(dnchw, (size_t)N * 3 * OH * OW);
+    const int nch = (epi == 6) ? gn : 3;
     for (int n = 0; n < N; n++)
-      for (int c = 0; c < 3; c++)
+      for (int c = 0; c < nch; c++)
         for (size_t pp = 0; pp < (size_t)OH * OW; pp++) {
           double r = ref[((size_t)n * OH * OW + pp) * gn + c];
-          double g = gotf[((size_t)n * 3 + c) * OH * OW + pp];
+          double g = gotf[((size_t)n * nch + c) * OH * OW + pp];
           me = fmax(me, fabs(g - r) / (1.0 + fabs(r)));
         }
     report(name, me, 1e-5);
@@ -621,6 +631,11 @@ int main(int argc, char** argv) {
       test_tc(1, 40, 24, 32, 160, 160, 0, am, 2);      // fused dense-block launch shape: K=32 -> N=160
       test_tc(1, 19, 11, 64, 192, 96, 0, am, 2);       // K=64 -> N=192 as 2 x 96
       test_tc(1, 21, 10, 64, 16, 16, 0, am, 3);        // last layer: Cout padded to 16, NCHW fp32 out
+      if (am == 0) {
+        test_tc(1, 21, 10, 64, 3, 32, 0, am, 6);       // last layer, taps in N (epi_mode 3): ragged tiles
+        test_tc(2, 32, 24, 64, 3, 32, 0, am, 6);       // several tiles per CTA: the shared staging array is reused
+        test_tc(1, 16, 8, 32, 1, 32, 0, am, 6);        // one chunk, one output channel
+      }
       test_tc(1, 24, 24, 160, 32, 160, 1, am, 1);      // dgrad conv4-like: K=32 -> N=160
       test_tc(1, 16, 16, 192, 64, 96, 1, am, 0);       // dgrad conv5-like: K=64 -> N=192 split 2x96
       if (am == 0) {                                   // CTA-pair kernel (cta_group::2): dense-block launch 1 and conv5's dgrad

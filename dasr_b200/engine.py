@@ -421,7 +421,7 @@ class _BatchPacker:
             add(('wd', i), w, TC_DGRAD, w.shape[1], kp, [(w, 0, w.shape[1], 0, kp, 0)], 9)
 
         def bias_alias(i):
-            self.cache.d[('b', i)] = (ver(Bv(i)), Bv(i))
+            self.cache.d[('b', i, None)] = (ver(Bv(i)), Bv(i))
 
         def bias_copy(key, param, src, n):
             dst = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -436,7 +436,12 @@ class _BatchPacker:
         for u in range(L.n_up):
             fprop(L.i_up0 + u, TC_UPCONV); bias_alias(L.i_up0 + u); dgrad(L.i_up0 + u)
         fprop(L.i_hr0); bias_alias(L.i_hr0); dgrad(L.i_hr0)
-        fprop(L.i_hr1, cout_to=16); bias_copy(('b', L.i_hr1), Bv(L.i_hr1), Bv(L.i_hr1), 16); dgrad(L.i_hr1, cout_to=32)
+        if ops.tapn_enabled(W(L.i_hr1).shape[0]):
+            # last layer with the taps in GEMM-N: its 4 KB filter pack (kind 3) is made by the single-filter kernel inside the graph
+            bias_copy(('b', L.i_hr1, 32), Bv(L.i_hr1), Bv(L.i_hr1), 32)
+        else:
+            fprop(L.i_hr1, cout_to=16); bias_copy(('b', L.i_hr1, 16), Bv(L.i_hr1), Bv(L.i_hr1), 16)
+        dgrad(L.i_hr1, cout_to=32)
         for r in range(L.n_rdb):
             for j in range(1, 6):
                 lo, hi = (0, nf) if j == 1 else (nf + (j - 2) * GC, nf + (j - 1) * GC)
@@ -474,6 +479,18 @@ def _rdb_stage1(b, w, bias, out, nf):
         ops.conv_tc(View(b, nf, 0), w, bias, out, nt=out.c // 2, act=ACT_LRELU, slope=0.2, act_cols=GC)
 
 
+def _last_layer(h0, out, w, i, cache, wk, bk, hk, dtype):
+    """HR_conv1 (nf -> out_nc <= 3 channels, NCHW fp32 out).  An MMA costs the same 84 cycles for N = 16 as for N = 128, so
+    the nine taps go into GEMM-N: one pass over the halo tile gives every halo pixel's product with all 27 (tap, channel)
+    filter rows, the epilogue adds the nine shifted partial results (8 MMAs per pixel tile instead of 36)."""
+    out_nc = w.shape[0]
+    if ops.tapn_enabled(out_nc):
+        w3 = cache.get(('w3' + hk, i), w, lambda: ops.pack_filter_tc(w.detach().float().contiguous(), ops.TC_TAPN, dtype))
+        ops.conv_tc(h0, w3, bk(i, 32), None, nchw_out=out, tapn=True)
+    else:
+        ops.conv_tc(h0, wk(i, cout_to=16), bk(i, 16), None, nchw_out=out, cout=16)
+
+
 def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=False):
     """tcgen05 bf16 forward (inference).  NCHW fp32 in -> NCHW fp32 out; bf16 NHWC in between.
 
@@ -507,7 +524,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=Fal
 
     def bk(i, n=None):
         p = params[2 * i + 1]
-        return cache.get(('b', i), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
+        return cache.get(('b', i, n), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
 
     xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)       # Cin 3 -> one zero-padded 32-channel chunk
     ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
@@ -573,7 +590,7 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=Fal
     out_nc = Wt(L.i_hr1).shape[0]
     out = _empty((N, out_nc, h, w), x)
     # last layer: Cout 3 -> one 16-wide UMMA N tile, epilogue writes the 3 real channels straight to NCHW fp32
-    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), None, nchw_out=out, cout=16)
+    _last_layer(h0, out, Wt(L.i_hr1), L.i_hr1, cache, wk, bk, hk, bf)
     _mark('tc_end')
     return out
 
@@ -598,7 +615,7 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
 
     def bk(i, n=None):
         p = params[2 * i + 1]
-        return cache.get(('b', i), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
+        return cache.get(('b', i, n), p, lambda: _pad_vec(p.float(), n or p.shape[0]).contiguous())
 
     xin = torch.zeros((N, H, W, 32), dtype=bf, device=x.device)
     ops.nchw_to_nhwc(x.contiguous().float(), View(xin, in_nc, 0))
@@ -636,7 +653,7 @@ def rrdb_forward_bf16_train(x, params, nb, upscale=4, cache=None):
     ops.conv_tc(cur, wk(L.i_hr0), bk(L.i_hr0), h0, nt=_pick_nt(nf, nf), act=ACT_LRELU, slope=0.2)
     out_nc = Wt(L.i_hr1).shape[0]
     out = _empty((N, out_nc, h, w), x)
-    ops.conv_tc(h0, wk(L.i_hr1, cout_to=16), bk(L.i_hr1, 16), None, nchw_out=out, cout=16)
+    _last_layer(h0, out, Wt(L.i_hr1), L.i_hr1, cache, wk, bk, '', bf)
     ctx = dict(L=L, xin=xin, fea=fea, bufs=bufs, ups=ups, h0=h0, shape=(N, in_nc, H, W))
     return out, ctx
 

@@ -13,7 +13,7 @@ from ._lib import ConvF32Params, ConvTcParams, check
 
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 FWD, DGRAD = 0, 1
-TC_FPROP, TC_DGRAD, TC_UPCONV = 0, 1, 2
+TC_FPROP, TC_DGRAD, TC_UPCONV, TC_TAPN = 0, 1, 2, 3
 
 
 def _stream():
@@ -260,7 +260,7 @@ def pack_filter_tc(w, kind, dtype=torch.bfloat16):
 
 def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slope=0.2, alpha=1.0, act_cols=None,
             pre=None, res1=None, beta1=0.0, res2=None, beta2=0.0, mask=None, mask_c0=0, mask_c1=0, mask_slope=0.2,
-            a_mode=0, nchw_out=None, cout=None, tile_rev=False, chunks=None, pair=None):
+            a_mode=0, nchw_out=None, cout=None, tile_rev=False, chunks=None, pair=None, tapn=False):
     """tcgen05 3x3 conv on NHWC bf16 channel slices; chunks = optional list of 32-channel chunk offsets of `inp`'s buffer; `inp`/`out`/`pre`/`res*`/`mask` are Views (or tensors).
     v = alpha*act(acc + bias + pre) + beta1*res1 + beta2*res2, activation on the first `act_cols` channels only.
     nchw_out: fp32 NCHW tensor — the launch writes its first nchw_out.shape[1] channels there (last layer).
@@ -269,7 +269,7 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
     inp = as_view(inp)
     N, H, W, _ = inp.t.shape
     if nchw_out is not None:
-        return _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode)
+        return _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode, tapn)
     out = as_view(out)
     p = ConvTcParams()
     lib = _lib.load()
@@ -339,19 +339,33 @@ def pick_nt_pair(cin, cout):
     return None
 
 
-def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode):
+def tapn_enabled(out_nc):
+    """Last layer with the nine taps folded into GEMM-N (dasr_conv_tc epi_mode 3): out_nc <= 3, DASR_B200_TAPN=0 switches it off."""
+    return 9 * out_nc <= 32 and os.environ.get('DASR_B200_TAPN', '1') != '0'
+
+
+def _conv_tc_nchw(inp, w_packed, bias, nchw_out, cout, act, slope, alpha, a_mode, tapn=False):
+    """Last layer: NCHW fp32 output of the first nchw_out.shape[1] channels.
+    tapn=False: Cout padded to `cout` (16) columns, nine taps x two K steps of N = 16 MMAs per chunk (epi_mode 2).
+    tapn=True : filters packed with TC_TAPN — D'[halo pixel][tap * out_nc + c] in ONE pass over the halo tile (N = 32, two
+                M-halves), the epilogue adds the nine shifted partial results from shared memory (epi_mode 3): 8 MMAs per
+                pixel tile instead of 36."""
     N, H, W, _ = inp.t.shape
     p = ConvTcParams()
     lib = _lib.load()
-    check(lib.dasr_conv_tc_setup(C.byref(p), TC_FPROP), 'conv_tc_setup', 0)
+    check(lib.dasr_conv_tc_setup(C.byref(p), TC_TAPN if tapn else TC_FPROP), 'conv_tc_setup', 0)
     p.N, p.H, p.W = N, H, W
     p.f16 = int(inp.t.dtype == torch.float16)
     if w_packed.dtype != inp.t.dtype:
         raise _lib.DasrError('conv_tc: operands of different 16-bit types (%s vs %s)' % (w_packed.dtype, inp.t.dtype))
     p.cin, p.in_cs, p.in_coff = inp.c, inp.cs, inp.coff
+    if tapn:
+        cout = 32
+        if bias is not None and bias.numel() < 32:
+            raise _lib.DasrError('conv_tc (taps in N): the bias vector must be padded to 32 floats')
     p.cout, p.out_cs, p.out_coff, p.nt = cout, cout, 0, cout
     p.act, p.slope, p.alpha, p.act_cols = act, slope, alpha, (cout if act != ACT_NONE else 0)
-    p.epi_mode, p.out_nc, p.a_mode = 2, nchw_out.shape[1], a_mode
+    p.epi_mode, p.out_nc, p.a_mode = (3 if tapn else 2), nchw_out.shape[1], a_mode
     check(lib.dasr_conv_tc(inp.ptr, _p(w_packed), _p(bias), None, None, None, None, _p(nchw_out), C.byref(p), _stream()),
           'conv_tc')
 

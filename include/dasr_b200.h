@@ -148,8 +148,12 @@ typedef struct {
   int a_mode;                  /* 0 = one halo tile per chunk + shifted UMMA descriptors (fast);
                                   1 = one aligned TMA tile per tap (validation path) */
   int epi_mode;                /* 0 = staged: tile -> swizzled shared memory -> TMA store; pre/res tiles arrive by TMA
-                                  1 = direct bf16 NHWC stores (sub-pixel out_mul=2 variants, dgrad mask)
-                                  2 = direct NCHW fp32 store of the first out_nc channels (last layer) */
+                                      (also the sub-pixel out_mul=2 variants without pre / residual inputs: one strided
+                                      output map per parity)
+                                  1 = direct bf16 NHWC stores (dgrad mask; out_mul=2 variants with residual inputs)
+                                  2 = direct NCHW fp32 store of the first out_nc channels (last layer)
+                                  3 = last layer with the nine taps folded into GEMM-N (dasr_conv_tc_setup kind 3, filters packed
+                                      with kind 3, out_nc <= 3, nt = cout = 32, bias padded to 32 floats): NCHW fp32 out */
   int act_cols;                /* only output channels [0, act_cols) of this launch get the activation
                                   (dense-block fused launches finish one conv and extend partial sums of the others) */
   int pre_cs, pre_coff;        /* pre-activation addend (bf16 NHWC): v = act(acc + bias + pre) */
@@ -185,6 +189,8 @@ int dasr_conv_tc2(const void* in_bf16, const void* w_packed_bf16, const float* b
 /* OIHW fp32 3x3 filter -> tc packing.  kind: 0 = plain 3x3 fprop (1 variant, 9 taps)
  *                                            1 = dgrad of a 3x3 s1 p1 conv (flipped, in/out swapped)
  *                                            2 = nearest-x2-upsample + 3x3 (4 variants x 4 taps, pre-summed)
+ *                                            3 = last layer, taps in GEMM-N (cout <= 3): [chunk][tap * cout + c, padded to 32][32]
+ *                                                for dasr_conv_tc epi_mode 3 (dasr_pack_filter_tc only, not the batch form)
  * Fills the tap tables / variant fields of *p as well (host side). */
 int dasr_conv_tc_setup(DasrConvTcParams* p, int kind);
 size_t dasr_pack_filter_tc_bytes(int cout, int cin, int kind);

@@ -302,8 +302,11 @@ def test_batch_packer_matches_per_filter_packs():
     bp = engine._BatchPacker(params, L, L.nf)
     bp.launch()
     torch.cuda.synchronize()
-    assert set(ref.d.keys()) == set(bp.cache.d.keys())
+    single = {k for k in ref.d if k[0] == 'w3'}          # last layer, taps in GEMM-N: packed by the single-filter kernel (4 KB)
+    assert set(ref.d.keys()) - single == set(bp.cache.d.keys())
     for k, (_, t) in ref.d.items():
+        if k in single:
+            continue
         got = bp.cache.d[k][1]
         assert got.shape == t.shape and got.dtype == t.dtype, k
         assert torch.equal(got, t), k

@@ -179,5 +179,7 @@ def test_mixed_precision_dasr_steps_vs_reference_fixture(golden, monkeypatch):
             assert v < 3e-2, (k, v)
         elif k.startswith('disc_Score'):
             assert v < 2e-2, (k, v)
+        elif k == 'loss/l_g_fea':
+            assert v < 1.5e-2, (k, v)        # L1 of bf16 VGG19 features: 4.5e-3 .. 6.2e-3 measured across builds (summation order)
         else:
             assert v < 5e-3, (k, v)
