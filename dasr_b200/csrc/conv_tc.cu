@@ -46,6 +46,8 @@ struct TcKernelArgs {
   const __nv_bfloat16* mask_src;
   void* out;
   int nchunks;       // cin / 32
+  int chunk64;       // 1: A tiles are loaded as 64-channel chunks (128 B rows, SWIZZLE_128B): half the TMA requests per byte
+  int nloads;        // A loads per pixel tile: nchunks, or nchunks / 2 with chunk64
   int n_ntiles;      // cout / nt
   int tiles_x, tiles_y;
   long ntiles;       // N * tiles_y * tiles_x
@@ -151,10 +153,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const int ty = (int)(r - (uint32_t)n * (uint32_t)a.tiles_y);
       int x0 = tx * TILE_W, y0 = ty * TILE_H;
       if (lane == 0) {
-        for (int c = 0; c < a.nchunks; c++) {
+        for (int c = 0; c < a.nloads; c++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* dst = sA + (size_t)stage * a.a_stage_bytes;
-          if (p.a_mode == 0) {
+          if (a.chunk64) {
+            // 64 channels per load: the TMA engine is request-bound at ~4 cycles per row (measured: 15.5 B/clk/SM with 64 B
+            // rows, 31-34 with 128 B rows), and a K = 64 tile with few MMAs (sub-pixel upconv, last layer) waits for it
+            mbar_expect_tx(&full_bar[stage], 2 * A_HALO_BYTES);
+            tma_load_4d(dst, &tmap_in, &full_bar[stage], p.in_coff + c * 2 * CHUNK, x0 - 1, y0 - 1, n);
+          } else if (p.a_mode == 0) {
             mbar_expect_tx(&full_bar[stage], A_HALO_BYTES);
             tma_load_4d(dst, &tmap_in, &full_bar[stage], p.nchunk_list ? p.chunk_off[c] : p.in_coff + c * CHUNK, x0 - 1, y0 - 1, n);
           } else {
@@ -175,8 +182,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // instructions, so descriptors live in uniform registers and no per-lane serialisation is emitted.
     const uint32_t idesc = make_idesc_16(128, nt, p.f16);
     // EPI_MODE 3 ("taps in N", last layer): the halo tile is read as a PLAIN 180-row K-major tile (8-row groups 512 B apart)
-    const uint32_t a_sbo = (p.a_mode == 0 && EPI_MODE != 3) ? (uint32_t)(HALO_W * ROW_B) : (uint32_t)(8 * ROW_B);
-    const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
+    const uint32_t a_row = a.chunk64 ? 2u * ROW_B : (uint32_t)ROW_B;          // bytes per pixel row of an A tile
+    const uint32_t a_sbo = (p.a_mode == 0 && EPI_MODE != 3) ? (uint32_t)HALO_W * a_row : 8u * a_row;
+    // layout type: SWIZZLE_64B (4) for 64 B rows, SWIZZLE_128B (2) for the 64-channel chunks
+    const uint64_t a_hi = ((uint64_t)((a_sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(a.chunk64 ? 2 : 4) << 61) | ((uint64_t)1 << 16);
+    const int ksteps = a.chunk64 ? 4 : 2;                                      // K = 16 steps per A load
     const uint64_t b_hi = ((uint64_t)(((8 * ROW_B) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61) | ((uint64_t)1 << 16);
     const uint32_t a_lo0 = smem_u32(sA) >> 4;
     const uint32_t a_stage_lo = (uint32_t)a.a_stage_bytes >> 4;
@@ -186,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
     for (int t = 0; t < 9; t++) {
       int tt = t < ntaps ? t : 0;
-      tap_lo[t] = (p.a_mode == 0) ? (uint32_t)((p.tap_dy[var][tt] * HALO_W + p.tap_dx[var][tt]) * ROW_B) >> 4
+      tap_lo[t] = (p.a_mode == 0) ? ((uint32_t)(p.tap_dy[var][tt] * HALO_W + p.tap_dx[var][tt]) * a_row) >> 4
                                   : (uint32_t)(tt * A_TAP_BYTES) >> 4;
     }
     mbar_wait(w_bar, 0);
@@ -196,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     uint32_t it = 0;
     for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
       if ((it % MMA_WARPS) != mi) {          // the other issuer's tile: only walk the ring position past it
-        for (int c = 0; c < a.nchunks; c++)
+        for (int c = 0; c < a.nloads; c++)
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         continue;
       }
@@ -205,38 +215,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-      for (int c = 0; c < a.nchunks; c++) {
+      for (int c = 0; c < a.nloads; c++) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage_lo;
-          uint32_t b_lo = b_lo0 + (uint32_t)c * b_slot_lo;
           const uint32_t b_tap_step = (uint32_t)a.nchunks * b_slot_lo;
+          // K step ks of this load reads 32 B at offset 32 * ks of every A row and the 32-channel filter chunk
+          // cb + (ks >> 1) at offset 32 * (ks & 1) of its rows
+          const uint32_t cb = a.chunk64 ? 2u * (uint32_t)c : (uint32_t)c;
           if constexpr (EPI_MODE == 3) {
             // D'[halo pixel][tap * out_nc + c] = A[halo pixel][K] * B'[K][tap * out_nc + c]: every halo pixel against the
-            // filters of ALL taps at once — 2 M-halves (halo rows 0..127, 128..255; rows >= 180 are never read) x 2 K steps
-            // instead of 9 taps x 2 K steps; the epilogue adds the nine shifted partial results.
+            // filters of ALL taps at once — 2 M-halves (halo rows 0..127, 128..255; rows >= 180 are never read) x K steps
+            // instead of 9 taps x K steps; the epilogue adds the nine shifted partial results.
 #pragma unroll
             for (int mh = 0; mh < 2; mh++) {
-              const uint32_t al = a_lo + (uint32_t)mh * ((128u * ROW_B) >> 4);
-              umma_bf16(d_tmem + (uint32_t)mh * 32u, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
-                        (uint32_t)(c != 0));
-              umma_bf16(d_tmem + (uint32_t)mh * 32u, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
+              const uint32_t al = a_lo + (uint32_t)mh * ((128u * a_row) >> 4);
+              for (int ks = 0; ks < ksteps; ks++) {
+                const uint32_t bl = b_lo0 + (cb + (uint32_t)(ks >> 1)) * b_slot_lo + 2u * (uint32_t)(ks & 1);
+                umma_bf16(d_tmem + (uint32_t)mh * 32u, a_hi | (uint64_t)((al + 2u * ks) & 0x3FFF), b_hi | (uint64_t)(bl & 0x3FFF), idesc,
+                          (uint32_t)((c | ks) != 0));
+              }
             }
           } else {
 #pragma unroll
             for (int tap = 0; tap < 9; tap++) {
               if (tap < ntaps) {
                 const uint32_t al = a_lo + tap_lo[tap];
-                umma_bf16(d_tmem, a_hi | (uint64_t)(al & 0x3FFF), b_hi | (uint64_t)(b_lo & 0x3FFF), idesc,
-                          (uint32_t)((c | tap) != 0));
-                umma_bf16(d_tmem, a_hi | (uint64_t)((al + 2) & 0x3FFF), b_hi | (uint64_t)((b_lo + 2) & 0x3FFF), idesc, 1u);
-                b_lo += b_tap_step;
+                for (int ks = 0; ks < ksteps; ks++) {
+                  const uint32_t bl = b_lo0 + (cb + (uint32_t)(ks >> 1)) * b_slot_lo + (uint32_t)tap * b_tap_step + 2u * (uint32_t)(ks & 1);
+                  umma_bf16(d_tmem, a_hi | (uint64_t)((al + 2u * ks) & 0x3FFF), b_hi | (uint64_t)(bl & 0x3FFF), idesc,
+                            (uint32_t)((c | tap | ks) != 0));
+                }
               }
             }
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (c == a.nchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          if (c == a.nloads - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -909,7 +924,15 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
   a.tiles_y = cdiv(p->H, TILE_H);
   a.ntiles = (long)p->N * a.tiles_x * a.tiles_y;
   a.w_bytes = p->ntaps * a.nchunks * p->nt * ROW_B;
-  a.a_stage_bytes = (p->a_mode == 0) ? ((A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
+  static int chunk64_ok = -1;
+  if (chunk64_ok < 0) {
+    const char* e = getenv("DASR_TC_CHUNK64");
+    chunk64_ok = (e && e[0] == '0') ? 0 : 1;
+  }
+  // 64-channel A chunks: contiguous input slice whose channel count is a multiple of 64
+  a.chunk64 = (chunk64_ok && p->a_mode == 0 && p->nchunk_list == 0 && p->cin % (2 * CHUNK) == 0) ? 1 : 0;
+  a.nloads = a.chunk64 ? a.nchunks / 2 : a.nchunks;
+  a.a_stage_bytes = (p->a_mode == 0) ? (((a.chunk64 ? 2 : 1) * A_HALO_BYTES + 1023) / 1024 * 1024) : p->ntaps * A_TAP_BYTES;
   a.acc_stride = (p->epi_mode == 3) ? 64 : pow2_at_least(p->nt);      // mode 3: two M-halves of 32 columns
   a.nacc = (a.acc_stride <= 128) ? 4 : 2;          // 512 TMEM columns: 4 accumulators up to N = 128, else 2
   a.tmem_cols = a.nacc * a.acc_stride;
@@ -947,14 +970,14 @@ int dasr_conv_tc(const void* in, const void* w, const float* bias, const void* p
     cuuint64_t gdim[4] = {(cuuint64_t)p->in_cs, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t gstr[3] = {(cuuint64_t)p->in_cs * 2, (cuuint64_t)p->W * p->in_cs * 2,
                           (cuuint64_t)p->H * p->W * p->in_cs * 2};
-    cuuint32_t box[4] = {CHUNK, (cuuint32_t)(p->a_mode == 0 ? HALO_W : TILE_W),
+    cuuint32_t box[4] = {(cuuint32_t)(a.chunk64 ? 2 * CHUNK : CHUNK), (cuuint32_t)(p->a_mode == 0 ? HALO_W : TILE_W),
                          (cuuint32_t)(p->a_mode == 0 ? HALO_H : TILE_H), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     // a 32-channel chunk is 64 B of a wider pixel row: promoting its L2 fills to 128 B doubled the DRAM reads of A
     // (ncu: dram__bytes_read 311 MB for 234 MB requested by the SMs in a one-chunk launch)
     CUresult r = enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                     p->in_cs > CHUNK ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, a.chunk64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     (p->in_cs > CHUNK && !a.chunk64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("conv_tc: cuTensorMapEncodeTiled(input) failed: %d", (int)r);

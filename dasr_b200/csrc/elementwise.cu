@@ -99,6 +99,10 @@ __device__ __forceinline__ uint4 f_to_bf8(const float* f) {
 }
 __global__ void act_bwd_bf16x8_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, long npix, int C8,
                                       int g_cs, int g_coff, int y_cs, int y_coff, float slope) {
+  // programmatic dependent launch (no-ops without the launch attribute): the next tensor-core conv may run its prologue
+  // while this grid drains; this grid itself waits for the conv before it touches that conv's output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * C8) return;
   long pp = i / C8;
@@ -122,6 +126,8 @@ __global__ void act_bwd_bf16x8_kernel(__nv_bfloat16* __restrict__ g, const __nv_
 __global__ void axpby_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                                     __nv_bfloat16* __restrict__ d, long npix, int C8, int x_cs, int x_coff, int y_cs,
                                     int y_coff, int d_cs, int d_coff, float a, float b) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // see act_bwd_bf16x8_kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * C8) return;
   long pp = i / C8;
@@ -707,6 +713,22 @@ static int run_loss(const float* a, const float* b, const float* w, float* loss,
 
 using namespace dasr;
 
+// launch with the programmatic-stream-serialization attribute (DASR_B200_PDL=0: plain launch semantics)
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), long grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 extern "C" {
 
 int dasr_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_cs, int dst_coff,
@@ -745,8 +767,8 @@ int dasr_act_bwd(void* g, const void* y, long npix, int C, int g_cs, int g_coff,
   long total = npix * C;
   if (is_bf16 && C % 8 == 0 && g_cs % 8 == 0 && g_coff % 8 == 0 && y_cs % 8 == 0 && y_coff % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)
-    act_bwd_bf16x8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        (__nv_bfloat16*)g, (const __nv_bfloat16*)y, npix, C / 8, g_cs, g_coff, y_cs, y_coff, slope);
+    launch_pdl(act_bwd_bf16x8_kernel, cdiv(total / 8, 256), 256, (cudaStream_t)stream, (__nv_bfloat16*)g, (const __nv_bfloat16*)y,
+               npix, C / 8, g_cs, g_coff, y_cs, y_coff, slope);
   else if (is_bf16)
     act_bwd_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)g, (const __nv_bfloat16*)y, npix, C, g_cs, g_coff, y_cs, y_coff, slope);
@@ -795,9 +817,8 @@ int dasr_axpby(const void* x, const void* y, void* dst, long npix, int C, int x_
                    (!y || (y_cs % 8 == 0 && y_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)) &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   if (vec)
-    axpby_bf16x8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C / 8, x_cs, x_coff, y_cs, y_coff, d_cs,
-        d_coff, a, b);
+    launch_pdl(axpby_bf16x8_kernel, cdiv(total / 8, 256), 256, (cudaStream_t)stream, (const __nv_bfloat16*)x,
+               (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C / 8, x_cs, x_coff, y_cs, y_coff, d_cs, d_coff, a, b);
   else if (is_bf16)
     axpby_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dst, npix, C, x_cs, x_coff, y_cs, y_coff, d_cs,
