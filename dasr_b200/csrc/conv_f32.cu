@@ -65,7 +65,8 @@ __device__ __forceinline__ bool gather_coord(const DasrConvF32Params& p, int oy,
   }
 }
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 64, BN = 64, BK = 64;     // K slab per shared-memory round trip (four 16-wide sub-slabs: four loads in flight per thread)
+constexpr int KSUB = BK / 16;
 
 // Arithmetic of the 64x64x16 tile product (DasrConvF32Params.math, DASR_F32_MATH_*):
 //   FMA    : fp32 FMA on CUDA cores, 4x4 outputs per thread                      (exact mode, default)
@@ -191,52 +192,62 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
   for (int e = 0; e < 16; e++) acc[e] = 0.f;
 
   for (int kk = 0; kk < K; kk += BK) {
-    // ---- load A tile (gathered activations) ----
+    // ---- load A (gathered activations) and B (filters): all global loads of the slab first, then the shared-memory stores,
+    // so one memory latency covers 64 K values (the layers on this kernel have few CTAs per SM to hide it otherwise)
     {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (VEC) {
-        int k0 = kk + a_kq * 4;  // cin % 16 == 0: the 16-wide k step stays inside one tap
-        int tap = k0 / p.cin, ci = k0 - tap * p.cin;
-        int dy = tap / p.kw, dx = tap - dy * p.kw;
-        int iy, ix;
-        if (pa_ok && gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
-          const float4 q = *reinterpret_cast<const float4*>(
-              in + ((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        }
-      } else {
+      float va[KSUB][4];
+      float4 qb[KSUB];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          int k = kk + a_kq * 4 + j;
-          if (pa_ok && k < K) {
-            int tap = k / p.cin, ci = k - tap * p.cin;
+      for (int sb = 0; sb < KSUB; sb++) {
+        const int kb = kk + 16 * sb;
+#pragma unroll
+        for (int j = 0; j < 4; j++) va[sb][j] = 0.f;
+        if (VEC) {
+          int k0 = kb + a_kq * 4;  // cin % 16 == 0: a 16-wide sub-slab stays inside one tap
+          if (pa_ok && k0 < K) {
+            int tap = k0 / p.cin, ci = k0 - tap * p.cin;
             int dy = tap / p.kw, dx = tap - dy * p.kw;
             int iy, ix;
-            if (gather_coord(p, aoy, aox, dy, dx, iy, ix))
-              v[j] = in[((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+            if (gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
+              const float4 q = *reinterpret_cast<const float4*>(in + ((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
+              va[sb][0] = q.x; va[sb][1] = q.y; va[sb][2] = q.z; va[sb][3] = q.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            int k = kb + a_kq * 4 + j;
+            if (pa_ok && k < K) {
+              int tap = k / p.cin, ci = k - tap * p.cin;
+              int dy = tap / p.kw, dx = tap - dy * p.kw;
+              int iy, ix;
+              if (gather_coord(p, aoy, aox, dy, dx, iy, ix))
+                va[sb][j] = in[((long)(an * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+            }
           }
         }
+        const int k = kb + b_k;
+        const int c = co0 + b_cq * 4;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          const float* wp = w + (long)k * p.cout + c;
+          if (VEC) {
+            if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);  // cout % 4 == 0
+          } else {
+            if (c + 0 < p.cout) q.x = wp[0];
+            if (c + 1 < p.cout) q.y = wp[1];
+            if (c + 2 < p.cout) q.z = wp[2];
+            if (c + 3 < p.cout) q.w = wp[3];
+          }
+        }
+        qb[sb] = q;
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) As[a_kq * 4 + j][a_pix] = v[j];
-    }
-    // ---- load B tile (filters) ----
-    {
-      int k = kk + b_k;
-      int c = co0 + b_cq * 4;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < K) {
-        const float* wp = w + (long)k * p.cout + c;
-        if (VEC) {
-          if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);  // cout % 4 == 0
-        } else {
-          if (c + 0 < p.cout) q.x = wp[0];
-          if (c + 1 < p.cout) q.y = wp[1];
-          if (c + 2 < p.cout) q.z = wp[2];
-          if (c + 3 < p.cout) q.w = wp[3];
-        }
+      for (int sb = 0; sb < KSUB; sb++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) As[16 * sb + a_kq * 4 + j][a_pix] = va[sb][j];
+        *reinterpret_cast<float4*>(&Bs[16 * sb + b_k][b_cq * 4]) = qb[sb];
       }
-      *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = q;
     }
     __syncthreads();
     tile_product<MATH>(As, Bs, acc, t);
@@ -292,9 +303,12 @@ __global__ void __launch_bounds__(256) conv2d_in_lrelu_kernel(const float* __res
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               float* __restrict__ stats, DasrConvF32Params p, float eps,
                                                               int mtiles) {
-  __shared__ __align__(16) float As[BK][Pad<MATH>::A];
-  __shared__ __align__(16) float Bs[BK][Pad<MATH>::B];
-  __shared__ float T[BM][BN + 1];
+  // the output tile T aliases the operand tiles (it is written after the last tile product has been read)
+  __shared__ __align__(16) float opnd[BK * (Pad<MATH>::A + Pad<MATH>::B)];
+  float (*As)[Pad<MATH>::A] = reinterpret_cast<float (*)[Pad<MATH>::A]>(opnd);
+  float (*Bs)[Pad<MATH>::B] = reinterpret_cast<float (*)[Pad<MATH>::B]>(opnd + BK * Pad<MATH>::A);
+  float (*T)[BN + 1] = reinterpret_cast<float (*)[BN + 1]>(opnd);
+  static_assert(BM * (BN + 1) <= BK * (Pad<MATH_FMA>::A + Pad<MATH_FMA>::B), "output tile must fit the operand tiles");
   __shared__ double psum[2][BN];
   __shared__ float s_mean[BN], s_rstd[BN];
   const int t = threadIdx.x;
@@ -313,48 +327,62 @@ __global__ void __launch_bounds__(256) conv2d_in_lrelu_kernel(const float* __res
 #pragma unroll
   for (int e = 0; e < 16; e++) acc[e] = 0.f;
   for (int kk = 0; kk < K; kk += BK) {
+    // ---- load A (gathered activations) and B (filters): all global loads of the slab first, then the shared-memory stores,
+    // so one memory latency covers 64 K values (the layers on this kernel have few CTAs per SM to hide it otherwise)
     {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (VEC) {
-        int k0 = kk + a_kq * 4;
-        int tap = k0 / p.cin, ci = k0 - tap * p.cin;
-        int dy = tap / p.kw, dx = tap - dy * p.kw;
-        int iy, ix;
-        if (pa_ok && gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
-          const float4 q = *reinterpret_cast<const float4*>(in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        }
-      } else {
+      float va[KSUB][4];
+      float4 qb[KSUB];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          int k = kk + a_kq * 4 + j;
-          if (pa_ok && k < K) {
-            int tap = k / p.cin, ci = k - tap * p.cin;
+      for (int sb = 0; sb < KSUB; sb++) {
+        const int kb = kk + 16 * sb;
+#pragma unroll
+        for (int j = 0; j < 4; j++) va[sb][j] = 0.f;
+        if (VEC) {
+          int k0 = kb + a_kq * 4;  // cin % 16 == 0: a 16-wide sub-slab stays inside one tap
+          if (pa_ok && k0 < K) {
+            int tap = k0 / p.cin, ci = k0 - tap * p.cin;
             int dy = tap / p.kw, dx = tap - dy * p.kw;
             int iy, ix;
-            if (gather_coord(p, aoy, aox, dy, dx, iy, ix)) v[j] = in[((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+            if (gather_coord(p, aoy, aox, dy, dx, iy, ix)) {
+              const float4 q = *reinterpret_cast<const float4*>(in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci);
+              va[sb][0] = q.x; va[sb][1] = q.y; va[sb][2] = q.z; va[sb][3] = q.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            int k = kb + a_kq * 4 + j;
+            if (pa_ok && k < K) {
+              int tap = k / p.cin, ci = k - tap * p.cin;
+              int dy = tap / p.kw, dx = tap - dy * p.kw;
+              int iy, ix;
+              if (gather_coord(p, aoy, aox, dy, dx, iy, ix))
+                va[sb][j] = in[((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff + ci];
+            }
           }
         }
+        const int k = kb + b_k;
+        const int c = co0 + b_cq * 4;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          const float* wp = w + (long)k * p.cout + c;
+          if (VEC) {
+            if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);  // cout % 4 == 0
+          } else {
+            if (c + 0 < p.cout) q.x = wp[0];
+            if (c + 1 < p.cout) q.y = wp[1];
+            if (c + 2 < p.cout) q.z = wp[2];
+            if (c + 3 < p.cout) q.w = wp[3];
+          }
+        }
+        qb[sb] = q;
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) As[a_kq * 4 + j][a_pix] = v[j];
-    }
-    {
-      int k = kk + b_k;
-      int c = co0 + b_cq * 4;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < K) {
-        const float* wp = w + (long)k * p.cout + c;
-        if (VEC) {
-          if (c < p.cout) q = *reinterpret_cast<const float4*>(wp);
-        } else {
-          if (c + 0 < p.cout) q.x = wp[0];
-          if (c + 1 < p.cout) q.y = wp[1];
-          if (c + 2 < p.cout) q.z = wp[2];
-          if (c + 3 < p.cout) q.w = wp[3];
-        }
+      for (int sb = 0; sb < KSUB; sb++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) As[16 * sb + a_kq * 4 + j][a_pix] = va[sb][j];
+        *reinterpret_cast<float4*>(&Bs[16 * sb + b_k][b_cq * 4]) = qb[sb];
       }
-      *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = q;
     }
     __syncthreads();
     tile_product<MATH>(As, Bs, acc, t);
@@ -455,16 +483,19 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restri
   for (int e = 0; e < 16; e++) acc[e] = 0.f;
 
   for (long pp = pbeg; pp < pend; pp += BK) {
-    long pix = pp + l_p;
-    bool ok = pix < pend;
-    int n = 0, oy = 0, ox = 0;
-    if (ok) {
-      n = (int)(pix / ((long)p.OH * p.OW));
-      int r = (int)(pix - (long)n * p.OH * p.OW);
-      oy = r / p.OW;
-      ox = r - oy * p.OW;
-    }
-    {
+    // four 16-pixel sub-slabs: all global loads first (one memory latency per 64 pixels), then the shared-memory stores
+    float4 va[KSUB], vb[KSUB];
+#pragma unroll
+    for (int sb = 0; sb < KSUB; sb++) {
+      const long pix = pp + 16 * sb + l_p;
+      const bool ok = pix < pend;
+      int n = 0, oy = 0, ox = 0;
+      if (ok) {
+        n = (int)(pix / ((long)p.OH * p.OW));
+        int r = (int)(pix - (long)n * p.OH * p.OW);
+        oy = r / p.OW;
+        ox = r - oy * p.OW;
+      }
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (ok) {
         if (VEC) {
@@ -486,11 +517,9 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restri
           }
         }
       }
-      *reinterpret_cast<float4*>(&As[l_p][l_q * 4]) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    {
+      va[sb] = make_float4(v[0], v[1], v[2], v[3]);
       float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      int c = co0 + l_q * 4;
+      const int c = co0 + l_q * 4;
       if (ok) {
         const T* dp = dout + pix * p.out_cs + p.out_coff + c;
         if (VEC) {
@@ -502,7 +531,12 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_f32_kernel(const T* __restri
           if (c + 3 < p.cout) q.w = load1<T>(dp + 3);
         }
       }
-      *reinterpret_cast<float4*>(&Bs[l_p][l_q * 4]) = q;
+      vb[sb] = q;
+    }
+#pragma unroll
+    for (int sb = 0; sb < KSUB; sb++) {
+      *reinterpret_cast<float4*>(&As[16 * sb + l_p][l_q * 4]) = va[sb];
+      *reinterpret_cast<float4*>(&Bs[16 * sb + l_p][l_q * 4]) = vb[sb];
     }
     __syncthreads();
     tile_product<MATH>(As, Bs, acc, t);
