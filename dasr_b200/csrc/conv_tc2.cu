@@ -109,14 +109,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   pdl_launch_dependents();              // the next launch may start its prologue on SMs this grid has left
 
   auto tile_of = [&](long it, int& x0, int& y0, int& n) -> bool {     // tile of THIS CTA in pair-iteration `it`
-    const uint32_t t = 2u * (uint32_t)(pair + it * npairs) + rank;     // tile counts fit 32 bits (checked on the host)
+    uint32_t t = 2u * (uint32_t)(pair + it * npairs) + rank;           // tile counts fit 32 bits (checked on the host)
+    const bool live = (long)t < a.ntiles;
+    // tile_rev: walk the grid backwards — a launch that re-reads what the previous launch wrote last (partial sums, the
+    // activations just produced) then starts with the tiles still resident in the 126 MB L2
+    if (p.tile_rev && live) t = (uint32_t)(a.ntiles - 1) - t;
     const uint32_t r = t / (uint32_t)a.tiles_x;
     const uint32_t tx = t - r * (uint32_t)a.tiles_x;
     n = (int)(r / (uint32_t)a.tiles_y); // n >= N for the odd tail tile: TMA zero-fills, nothing is stored
     const uint32_t ty = r - (uint32_t)n * (uint32_t)a.tiles_y;
     x0 = (int)tx * TILE_W;
     y0 = (int)ty * TILE_H;
-    return (long)t < a.ntiles;
+    return live;
   };
   const long niter = (a.ntiles / 2 + (a.ntiles & 1) - pair + npairs - 1) / npairs;   // pair-iterations of this pair
 
@@ -436,7 +440,7 @@ int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
   // pair kernel: plain 3x3 fprop/dgrad geometry, staged bf16 epilogue in 64-channel blocks
   if (!p) return 0;
   if (p->nvar != 1 || p->ntaps != 9 || p->out_mul != 1 || p->epi_mode != 0 || p->a_mode != 0) return 0;
-  if (p->nt % 32 != 0 || p->nt < 32 || p->nt > 256 || p->cout % p->nt != 0 || p->cin % CHUNK != 0 || p->cin <= 0 || p->tile_rev) return 0;
+  if (p->nt % 32 != 0 || p->nt < 32 || p->nt > 256 || p->cout % p->nt != 0 || p->cin % CHUNK != 0 || p->cin <= 0) return 0;
   // pre / residual tensors are announced through their channel strides (pre_cs, res1_cs, res2_cs > 0), as dasr_conv_tc2
   // callers fill them; each one costs one more 16 KB block array per ring slot
   int st, nb;
@@ -447,7 +451,7 @@ int dasr_conv_tc2_supported(const DasrConvTcParams* p) {
 int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* pre, const void* res1, const void* res2,
                   void* out, const DasrConvTcParams* p, void* stream) {
   DASR_REQUIRE(p && in && w && out, "conv_tc2: null argument");
-  DASR_REQUIRE(p->nvar == 1 && p->ntaps == 9 && p->out_mul == 1 && p->epi_mode == 0 && p->a_mode == 0 && !p->tile_rev,
+  DASR_REQUIRE(p->nvar == 1 && p->ntaps == 9 && p->out_mul == 1 && p->epi_mode == 0 && p->a_mode == 0,
                "conv_tc2: plain 3x3 geometry with the staged epilogue only");
   DASR_REQUIRE(p->nt % 32 == 0 && p->nt >= 32 && p->nt <= 256 && p->cout % p->nt == 0,
                "conv_tc2: the Cout tile nt must be a multiple of 32 in [32, 256] that divides cout (nt=%d cout=%d)", p->nt, p->cout);

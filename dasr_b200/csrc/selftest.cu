@@ -175,6 +175,7 @@ static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
 }
 // 16-bit storage of the tensor-core conv tests: bf16, or IEEE half bits carried in the same 2-byte slots (g_f16)
 static int g_f16 = 0;
+static int g_tile_rev = 0;    // pair kernel: walk the tile grid backwards
 static int g_up_staged = 0;   // sub-pixel upconv variants through the staged TMA-store epilogue (strided output maps)
 static std::vector<__nv_bfloat16> to_h16(const std::vector<float>& v) {
   if (!g_f16) return to_bf16(v);
@@ -274,6 +275,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
   p.a_mode = a_mode;
   p.f16 = g_f16;
+  p.tile_rev = (epi == 4 || epi == 5) ? g_tile_rev : 0;
   p.epi_mode = ((kind == 2 && !g_up_staged) || epi == 1 || nt % 32) ? 1 : 0;
   float* dnchw = nullptr;
   if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
@@ -654,6 +656,12 @@ int main(int argc, char** argv) {
         test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);       // N = 96: 64-block + tail block, pre + residuals
         test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);     // N = 160: two blocks + tail, pre only
         test_tc(1, 19, 11, 64, 96, 96, 0, 0, 4);       // N = 96 without loads
+        g_tile_rev = 1;                                // reversed tile walk (odd tile count, several iterations, loads)
+        test_tc(1, 19, 11, 64, 192, 192, 0, 0, 4);
+        test_tc(4, 96, 64, 64, 192, 192, 0, 0, 4);
+        test_tc(3, 48, 40, 64, 64, 64, 0, 0, 5);
+        test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);
+        g_tile_rev = 0;
         test_tc(1, 16, 8, 64, 128, 64, 0, 0, 4);       // Cout tiling on the pair kernel: grid.y = 2 tiles of 64
         test_tc(2, 24, 16, 64, 128, 32, 0, 0, 5);      // 4 tiles of 32 with a pre addend (activation boundary crosses tiles)
         test_tc(1, 20, 13, 96, 192, 96, 0, 0, 4);      // 2 tiles of 96 (64-block + tail block each)

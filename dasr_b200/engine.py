@@ -467,14 +467,15 @@ class _BatchPacker:
 
 PAIR_MODE = os.environ.get('DASR_B200_PAIR', '1') != '0'      # run eligible launches on the CTA-pair kernel (conv_tc2)
 PAIR_STAGE1 = PAIR_MODE
+TILE_REV = os.environ.get('DASR_B200_TILE_REV', '1') != '0'
 
 
-def _rdb_stage1(b, w, bias, out, nf):
+def _rdb_stage1(b, w, bias, out, nf, tile_rev=False):
     """Launch 1 of a dense block: x (K = nf) against the stacked filters of conv1..5 (N = 4*GC + nf = 192), LeakyReLU on the
     first GC columns (= x1).  One CTA cannot keep the 192-wide filter set resident, so the single-CTA kernel runs it as
     two Cout tiles of 96; the CTA-pair kernel splits the filters over the two SMs of a TPC and issues M=256, N=192."""
     if PAIR_STAGE1 and nf == 64 and GC == 32:
-        ops.conv_tc(View(b, nf, 0), w, bias, out, act=ACT_LRELU, slope=0.2, act_cols=GC, pair=True)
+        ops.conv_tc(View(b, nf, 0), w, bias, out, act=ACT_LRELU, slope=0.2, act_cols=GC, pair=True, tile_rev=tile_rev)
     else:
         ops.conv_tc(View(b, nf, 0), w, bias, out, nt=out.c // 2, act=ACT_LRELU, slope=0.2, act_cols=GC)
 
@@ -545,7 +546,10 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=Fal
             tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
         if sched is not None:
             fw = _sched_rdb_filters(cache, params, L, r, nf, sched, 's' + sched_id + hk, bf)
-            _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf)
+            # consecutive launches walk the tile grid in opposite directions: each one starts with the tiles the previous
+            # one wrote last, which are still in L2 (DASR_B200_TILE_REV=0: always forwards)
+            rev = lambda j: TILE_REV and PAIR_MODE and ((5 * r + j) & 1) == 1
+            _rdb_stage1(b, fw[0][0], fw[0][1], View(b, BW - nf, nf), nf, tile_rev=rev(1))
             for j in (2, 3, 4, 5):
                 ks = sched[j - 1][1]
                 width = sum(nf if k == 5 else GC for k in ks)
@@ -553,9 +557,9 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=Fal
                 if j < 5:
                     o = View(b, width, nf + (j - 1) * GC)                  # slots of conv j .. conv ks[-1], partial sums in place
                     ops.conv_tc(b, fw[j - 1][0], fw[j - 1][1], o, act=ACT_LRELU, slope=0.2, act_cols=GC, pre=o,
-                                chunks=fw[j - 1][2], pair=pair)
+                                chunks=fw[j - 1][2], pair=pair, tile_rev=rev(j))
                 else:
-                    ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], pair=pair, **tail)
+                    ops.conv_tc(b, fw[4][0], fw[4][1], dst, pre=View(b, nf, CS), chunks=fw[4][2], pair=pair, tile_rev=rev(5), **tail)
         elif fused:
             if half:
                 raise ops._lib.DasrError('half precision needs dense-block schedule 2 or 3 (DASR_B200_SCHED) or fused=False')
