@@ -510,3 +510,27 @@ def test_sr_model_test_x8_self_ensemble_vs_oracle():
                 outs.append(o)
     ref = torch.stack(outs, 0).mean(0)
     assert rel_linf(model.fake_H, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize('sched', ['2', '3', '4'])
+def test_dense_block_schedules_agree_with_one_launch_per_conv(sched, monkeypatch):
+    """Every dense-block schedule (which launch computes which (conv, input chunk) product, partial sums in HBM) gives the
+    per-layer result up to bf16 rounding of the partial sums; ragged tiles, odd tile count, three RRDBs."""
+    from dasr_b200.srn.models.modules.architecture import RRDBNet
+    monkeypatch.setenv('DASR_B200_SCHED', sched)
+    monkeypatch.setenv('DASR_B200_GRAPH', '0')
+    nb = 3
+    sd = O.synth_state_dict(O.rrdbnet_shapes(nb=nb), 131, 0.3)
+    net = RRDBNet(3, 3, 64, nb, gc=32, upscale=4)
+    net.load_state_dict(sd, strict=True)
+    net.cuda().eval()
+    x = O.synth_image((3, 3, 40, 44), 132).cuda()
+    with torch.no_grad():
+        net.precision = 'bf16_layer'
+        ref = net(x)
+        net.precision = 'bf16'
+        out = net(x)
+        net.precision = 'fp32'
+        exact = net(x)
+    assert rel_linf(out, ref) < 1e-2, rel_linf(out, ref)
+    assert rel_linf(out, exact) < 3e-2
