@@ -157,11 +157,11 @@ class DASR_Model(BaseModel):
     # ------------------------------------------------------------------------------------------ data
     def feed_data(self, data, istrain):
         if istrain and 'HR' in data:
-            HR_pair = data['HR'].to(self.device)
-            HR_unpair = data['HR_unpair'].to(self.device)
-            fake_w = data['fake_w'].to(self.device).float().contiguous()
-            real_LR = data['LR_real'].to(self.device)
-            fake_LR = data['LR_fake'].to(self.device)
+            HR_pair = self._to_device(data['HR'])
+            HR_unpair = self._to_device(data['HR_unpair'])
+            fake_w = self._to_device(data['fake_w']).float().contiguous()
+            real_LR = self._to_device(data['LR_real'])
+            fake_LR = self._to_device(data['LR_fake'])
             self.var_L = torch.cat([fake_LR, real_LR], dim=0)
             self.var_H = torch.cat([HR_pair, HR_unpair], dim=0)
             # bilinear (align_corners=False) resize of the domain-distance map to the HR crop
@@ -171,9 +171,9 @@ class DASR_Model(BaseModel):
             B = self.var_L.shape[0]
             self.mask = [0] * (B // 2) + [1] * (B - B // 2)
         else:
-            self.var_L = data['LR'].to(self.device)
+            self.var_L = self._to_device(data['LR'])
             if 'HR' in data:
-                self.var_H = data['HR'].to(self.device)
+                self.var_H = self._to_device(data['HR'])
                 self.needHR = True
             else:
                 self.needHR = False

@@ -64,10 +64,10 @@ class SRRaGANModel(BaseModel):
         self.print_network()
 
     def feed_data(self, data, istrain=True):
-        self.var_L = data['LR'].to(self.device)
-        self.var_H = data['HR'].to(self.device)
+        self.var_L = self._to_device(data['LR'])
+        self.var_H = self._to_device(data['HR'])
         if istrain:
-            self.var_ref = (data['ref'] if 'ref' in data else data['HR']).to(self.device)
+            self.var_ref = self._to_device(data['ref'] if 'ref' in data else data['HR'])
 
     def _g_gan(self):
         """generator GAN term (SRRaGAN_model.py:133-138 / SRGAN_model.py:131-133), D's filters frozen"""

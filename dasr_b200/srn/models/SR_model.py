@@ -58,9 +58,9 @@ class SRModel(BaseModel):
         self.log_dict = OrderedDict()
 
     def feed_data(self, data, need_HR=True):
-        self.var_L = data['LR'].to(self.device)
+        self.var_L = self._to_device(data['LR'])
         if 'HR' in data:
-            self.real_H = data['HR'].to(self.device)
+            self.real_H = self._to_device(data['HR'])
 
     def optimize_parameters(self, step):
         self.optimizer_G.zero_grad()

@@ -96,6 +96,11 @@ class BaseModel():
         net = unwrap(network)
         return str(net), sum(p.numel() for p in net.parameters())
 
+    def _to_device(self, t):
+        """Host -> device copy of a batch tensor: asynchronous when the source is pinned (DataLoader pin_memory, bench.py) so
+        the host does not stall behind the previous step's GPU work; pageable sources copy synchronously as in the reference."""
+        return t.to(self.device, non_blocking=bool(getattr(t, 'is_pinned', lambda: False)()))
+
     def _log_eval_precision(self, net):
         """Once per model: which arithmetic produces the validation / test images (the reference validates in fp32; here
         the default is the bf16 tensor-core path, DASR_B200_PRECISION=fp16 | fp32 for closer metrics)."""
