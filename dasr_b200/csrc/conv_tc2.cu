@@ -203,6 +203,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t nb = (uint32_t)a.nb, nblk = (uint32_t)a.nblk;
       const uint32_t total = (uint32_t)niter * nb;
       const uint32_t nld = (uint32_t)((HAS_PRE ? 1 : 0) + NRES);
+      // mask mode (dgrad): res1 is the ACTIVATION whose sign gates output channels [mask_c0, mask_c1) (LeakyReLU backward of
+      // the slot this launch completes); only the blocks that intersect the range are loaded
+      const bool mask_mode = (NRES >= 1) && (p.mask_c1 > p.mask_c0);
       auto issue_loads = [&](uint32_t k) {
         const uint32_t b = k % nblk;
         int x0, y0, n;
@@ -211,9 +214,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         const int i = (int)(k - kt * nb);
         const int wide = i < a.nb64 ? 1 : 0;          // 64-channel block | 32-channel tail block
         const int col = co_base + i * 64;
-        mbar_expect_tx(&pre_bar[b], nld * (uint32_t)(wide ? EPI_BLK64_BYTES : EPI_BLK32_BYTES));
+        const bool need_r1 = !mask_mode || (col < p.mask_c1 && col + (wide ? 64 : 32) > p.mask_c0);
+        mbar_expect_tx(&pre_bar[b], (nld - (need_r1 ? 0u : 1u)) * (uint32_t)(wide ? EPI_BLK64_BYTES : EPI_BLK32_BYTES));
         if constexpr (HAS_PRE) tma_load_4d(sS + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 2 : 3], &pre_bar[b], p.pre_coff + col, x0, y0, n);
-        if constexpr (NRES >= 1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+        if constexpr (NRES >= 1) {
+          if (need_r1) tma_load_4d(sR1 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 4 : 5], &pre_bar[b], p.res1_coff + col, x0, y0, n);
+        }
         if constexpr (NRES >= 2) tma_load_4d(sR2 + (size_t)b * EPI_BLK64_BYTES, &em.m[wide ? 6 : 7], &pre_bar[b], p.res2_coff + col, x0, y0, n);
       };
       if constexpr (HAS_LOADS)
@@ -328,8 +334,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
             for (int j = 0; j < 16; j++) v[j] *= alpha;
           }
           if constexpr (NRES >= 1) {
-            fma_h16x8(v, lds128(bR1 + o0), p.beta1, f16);
-            fma_h16x8(v + 8, lds128(bR1 + o1), p.beta1, f16);
+            if (p.mask_c1 > p.mask_c0) {
+              const int co = co_base + cg;
+              if (co >= p.mask_c0 && co < p.mask_c1) {      // 16-column groups never straddle the range (multiples of 16)
+                const uint4 m0 = lds128(bR1 + o0), m1 = lds128(bR1 + o1);
+                const short* ms0 = reinterpret_cast<const short*>(&m0);
+                const short* ms1 = reinterpret_cast<const short*>(&m1);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {               // a positive finite bf16 / half is a positive 16-bit integer
+                  if (!(ms0[j] > 0)) v[j] *= p.mask_slope;
+                  if (!(ms1[j] > 0)) v[8 + j] *= p.mask_slope;
+                }
+              }
+            } else {
+              fma_h16x8(v, lds128(bR1 + o0), p.beta1, f16);
+              fma_h16x8(v + 8, lds128(bR1 + o1), p.beta1, f16);
+            }
           }
           if constexpr (NRES >= 2) {
             fma_h16x8(v, lds128(bR2 + o0), p.beta2, f16);
@@ -468,6 +488,9 @@ int dasr_conv_tc2(const void* in, const void* w, const float* bias, const void* 
   DASR_REQUIRE(p->out_cs % 8 == 0 && p->out_coff % 8 == 0 && p->out_coff + p->cout <= p->out_cs, "conv_tc2: output slice");
   DASR_REQUIRE(p->act_cols % 16 == 0, "conv_tc2: act_cols must be a multiple of 16");
   DASR_REQUIRE(!(res2 && !res1), "conv_tc2: res2 without res1");
+  if (p->mask_c1 > p->mask_c0)
+    DASR_REQUIRE(res1 && !res2 && p->mask_c0 % 16 == 0 && p->mask_c1 % 16 == 0 && p->mask_c1 <= p->cout,
+                 "conv_tc2: mask mode takes the activation as res1 (no res2) and a range of whole 16-channel groups");
   if (pre) DASR_REQUIRE(p->pre_cs % 8 == 0 && p->pre_coff % 8 == 0 && p->pre_coff + p->cout <= p->pre_cs, "conv_tc2: pre slice");
   if (res1) DASR_REQUIRE(p->res1_cs % 8 == 0 && p->res1_coff % 8 == 0 && p->res1_coff + p->cout <= p->res1_cs, "conv_tc2: res1 slice");
   if (res2) DASR_REQUIRE(p->res2_cs % 8 == 0 && p->res2_coff % 8 == 0 && p->res2_coff + p->cout <= p->res2_cs, "conv_tc2: res2 slice");

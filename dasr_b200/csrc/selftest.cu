@@ -243,6 +243,13 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
       if (c < act_cols) v = v > 0 ? v : v * slope;
       ref[i] = alpha * v + beta1 * res1[i] + beta2 * res1[(i + gn) % ref.size()];
     }
+  if (epi == 7)      // CTA-pair dgrad form: acc + bias + pre, then the LeakyReLU-backward gate on the last 32 channels
+    for (size_t i = 0; i < ref.size(); i++) {
+      int c = (int)(i % gn);
+      double v = ref[i] + msk[i];
+      if (c >= gn - 32 && !(res1[i] > 0.f)) v *= mslope;
+      ref[i] = v;
+    }
   if (epi == 4)      // CTA-pair kernel: bias + LeakyReLU on the first act_cols channels + scale, no pre / residual tiles
     for (size_t i = 0; i < ref.size(); i++) {
       int c = (int)(i % gn);
@@ -275,7 +282,7 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
   p.mask_cs = gn; p.mask_coff = mc0; p.mask_c0 = mc0; p.mask_c1 = mc1; p.mask_slope = mslope;
   p.a_mode = a_mode;
   p.f16 = g_f16;
-  p.tile_rev = (epi == 4 || epi == 5) ? g_tile_rev : 0;
+  p.tile_rev = (epi == 4 || epi == 5 || epi == 7) ? g_tile_rev : 0;
   p.epi_mode = ((kind == 2 && !g_up_staged) || epi == 1 || nt % 32) ? 1 : 0;
   float* dnchw = nullptr;
   if (epi == 3) { p.epi_mode = 2; p.out_nc = 3; dnchw = dalloc<float>((size_t)N * 3 * OH * OW); }
@@ -297,7 +304,12 @@ static void test_tc(int N, int H, int W, int cin, int cout, int nt, int kind, in
     dres2 = dalloc<__nv_bfloat16>(r2.size());
     h2d(dres2, r2);
   }
-  if (epi == 4)
+  if (epi == 4 || epi == 5) p.mask_c0 = p.mask_c1 = 0;      // the pair kernel reads a non-empty range as mask mode
+  if (epi == 7) {
+    p.act = DASR_ACT_NONE; p.alpha = 1.f; p.act_cols = 0; p.beta1 = 0.f; p.beta2 = 0.f;
+    p.mask_c0 = gn - 32; p.mask_c1 = gn;
+    rc |= dasr_conv_tc2(din, dwp, db, dmsk, dres, nullptr, dout, &p, 0);
+  } else if (epi == 4)
     rc |= dasr_conv_tc2(din, dwp, db, nullptr, nullptr, nullptr, dout, &p, 0);
   else if (epi == 5)      // CTA-pair kernel with the full staged-epilogue contract of epi 2
     rc |= dasr_conv_tc2(din, dwp, db, dmsk, gn <= 96 ? dres : nullptr, dres2, dout, &p, 0);
@@ -656,6 +668,10 @@ int main(int argc, char** argv) {
         test_tc(1, 20, 13, 32, 96, 96, 0, 0, 5);       // N = 96: 64-block + tail block, pre + residuals
         test_tc(2, 32, 24, 32, 160, 160, 0, 0, 5);     // N = 160: two blocks + tail, pre only
         test_tc(1, 19, 11, 64, 96, 96, 0, 0, 4);       // N = 96 without loads
+        test_tc(2, 24, 16, 160, 32, 160, 1, 0, 7);     // dgrad4-like: K = 32 -> N = 160, pre + mask on the tail block (x3 slot)
+        test_tc(1, 20, 13, 128, 32, 128, 1, 0, 7);     // dgrad3-like: mask on the second half of the last 64-block
+        test_tc(2, 32, 24, 96, 32, 96, 1, 0, 7);       // dgrad2-like
+        test_tc(1, 19, 11, 192, 64, 192, 1, 0, 7);     // dgrad5-like shape (with a pre addend)
         g_tile_rev = 1;                                // reversed tile walk (odd tile count, several iterations, loads)
         test_tc(1, 19, 11, 64, 192, 192, 0, 0, 4);
         test_tc(4, 96, 64, 64, 192, 192, 0, 0, 4);

@@ -774,6 +774,9 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
     # readers of a buffer before the block after next overwrites it.
     overlap = fused_wgrad and os.environ.get('DASR_B200_BWD_OVERLAP', '1') == '1'
     pair_dgrad = PAIR_MODE and nf == 64 and GC == 32 and os.environ.get('DASR_B200_PAIR_DGRAD', '0') == '1'
+    # LeakyReLU backward of x1..x4 inside the epilogue of the dgrad launch that completes each slot (pair kernel): 276 mask
+    # launches less per step
+    fuse_mask = PAIR_STAGE1 and nf == 64 and GC == 32 and os.environ.get('DASR_B200_FUSE_MASK', '1') == '1'
     nset = 2 if overlap else 1
     GBs = [_empty((N, H, W, CS), dev, bf) for _ in range(nset)]
     gx5s = [_empty((N, H, W, nf), dev, bf) for _ in range(nset)]
@@ -798,7 +801,11 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
         elif not overlap:
             ops.bias_grad(g_x5, gB(ci))
         if PAIR_STAGE1 and nf == 64 and GC == 32:                                          # K=64 -> N=192 on a CTA pair
-            ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True)
+            if fuse_mask:      # ... which also completes the gradient of x4: its LeakyReLU mask is applied in the epilogue
+                ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True, mask=View(b, CS, 0),
+                            mask_c0=nf + 3 * GC, mask_c1=nf + 4 * GC, mask_slope=0.2)
+            else:
+                ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, pair=True)
         else:
             ops.conv_tc(g_x5, wd(ci), None, View(GB, CS, 0), kind=TC_DGRAD, nt=CS // 2)    # ... or as 2 x 96
         g_new = _empty((N, H, W, nf), dev, bf)
@@ -806,11 +813,17 @@ def rrdb_backward_bf16(ctx, params, dout, cache=None, flat=None):
             ci = L.rdb_conv(r, k)
             cin = _rdb_cin(nf, k)
             gk = View(GB, GC, nf + (k - 1) * GC)
-            ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
+            if not fuse_mask:
+                ops.act_bwd(gk, View(b, GC, nf + (k - 1) * GC), 0.2)
             if not fused_wgrad:
                 wgrad(View(b, cin, 0), gk, ci, bias=False)
             o = View(GB, cin, 0)
-            if k > 1:
+            if k > 1 and fuse_mask:
+                # accumulate in place; this launch completes the gradient of x_{k-1} (the last 32 of its output channels):
+                # the LeakyReLU mask of that slot is applied in the epilogue instead of by a separate kernel
+                ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o, pair=True, mask=View(b, cin, 0),
+                            mask_c0=cin - GC, mask_c1=cin, mask_slope=0.2)
+            elif k > 1:
                 ops.conv_tc(gk, wd(ci), None, o, kind=TC_DGRAD, pre=o, pair=pair_dgrad)     # accumulate in place
             elif r % 3 == 0 and g_rrdb is not None:
                 # conv1's dgrad completes the block's input gradient: + what conv2..5 left in the x slot + the block skip

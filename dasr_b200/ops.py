@@ -311,7 +311,12 @@ def conv_tc(inp, w_packed, bias, out, kind=TC_FPROP, nt=None, act=ACT_NONE, slop
         pair = False
     if pair:
         if mask is not None:
-            raise _lib.DasrError('conv_tc: the CTA-pair kernel has no mask input')
+            # LeakyReLU backward fused into the dgrad epilogue: the activation rides in the res1 slot of the block ring and
+            # gates output channels [mask_c0, mask_c1) (only the blocks that intersect the range are loaded)
+            if res1 is not None or res2 is not None:
+                raise _lib.DasrError('conv_tc (pair): the mask uses the res1 slot; no residual inputs in the same launch')
+            res1 = mask
+            p.res1_cs, p.res1_coff, p.beta1 = mask.cs, mask.coff, 0.0
         p.nt = nt if nt else p.cout              # Cout tile per CTA pair (grid.y = cout / nt); default: one tile
         p.epi_mode = 0
         check(lib.dasr_conv_tc2(inp.ptr, _p(w_packed), _p(bias), pre.ptr if pre else None, res1.ptr if res1 else None,
