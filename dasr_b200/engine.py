@@ -540,11 +540,15 @@ def rrdb_forward_bf16(x, params, nb, upscale=4, cache=None, fused=True, half=Fal
     ops.conv_tc(xin, wk(L.i_fea, cin_to=32), bk(L.i_fea), fea)
     ops.axpby(fea, 1.0, None, 0.0, View(bufs[0], nf, 0))
     lr = _empty((N, H, W, nf), x, bf)
-    for r in range(n_rdb):
-        b = bufs[r]
-        dst = View(bufs[r + 1], nf, 0)
+    # DASR_B200_BATCH_SPLIT=s (experiment): every dense block runs its five launches on one s-th of the batch at a time, so a
+    # launch finds a larger share of what its predecessor wrote in L2 — at the price of s times the launches
+    nsplit = max(1, min(N, int(os.environ.get('DASR_B200_BATCH_SPLIT', '1'))))
+    bounds = [(N * i // nsplit, N * (i + 1) // nsplit) for i in range(nsplit)]
+    for r, (n0, n1) in ((r, sl) for r in range(n_rdb) for sl in bounds):
+        b = bufs[r][n0:n1]
+        dst = View(bufs[r + 1][n0:n1], nf, 0)
         if r % 3 == 2:      # (x5*0.2 + x)*0.2 + x_rrdb
-            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2], nf, 0), beta2=1.0)
+            tail = dict(alpha=0.04, res1=View(b, nf, 0), beta1=0.2, res2=View(bufs[r - 2][n0:n1], nf, 0), beta2=1.0)
         else:
             tail = dict(alpha=0.2, res1=View(b, nf, 0), beta1=1.0)
         if sched is not None:
