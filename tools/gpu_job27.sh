@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for cfg in "DASR_B200_BATCH_SPLIT=1" "DASR_B200_BATCH_SPLIT=2" "DASR_B200_BATCH_SPLIT=4" "DASR_B200_BATCH_SPLIT=1"; do
+for cfg in "DASR_B200_BATCH_SPLIT=1" "DASR_B200_BATCH_SPLIT=2" "DASR_B200_BATCH_SPLIT=4" "DASR_B200_BATCH_SPLIT=8" "DASR_B200_BATCH_SPLIT=16" "DASR_B200_BATCH_SPLIT=1"; do
   echo "== bench: $cfg"; env $cfg DASR_BENCH_FP16=0 timeout 900 python bench.py --train-steps 0 --no-cpu-baseline --steps 20 --warmup 5 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], 'frac', d['roofline']['frac'], d['clocks']['sm_mhz'], d['gpu_launches'])"
