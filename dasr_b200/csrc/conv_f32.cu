@@ -272,6 +272,82 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Thin-N form (cout <= 16, long K): the logit layers of the discriminators (512 -> 1 with 4x4 taps, 256 -> 1) and the input
+// gradient of their first layers (N = 3 / 9).  The 64-wide output tile of the implicit-GEMM kernel would be 84-98 % empty and
+// the grid tiny (18 CTAs walking K = 8192: 0.64 ms for 9 MFLOP under ncu).  Here ONE WARP owns an output pixel: the lanes stride
+// over the input channels of every tap (coalesced float4 loads), keep `cout` running sums each, and reduce them with shuffles in a
+// fixed order (deterministic).  Same operands, same epilogue contract as conv2d_f32_kernel; exact fp32 FMA arithmetic.
+// ---------------------------------------------------------------------------------------------
+constexpr int THIN_MAX = 16;
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv2d_thin_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ res1,
+                                                              const float* __restrict__ res2, float* __restrict__ out,
+                                                              DasrConvF32Params p) {
+  const int lane = threadIdx.x & 31;
+  const long pm = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long P = (long)p.N * p.OH * p.OW;
+  if (pm >= P) return;
+  const int n = (int)(pm / ((long)p.OH * p.OW));
+  const int r = (int)(pm - (long)n * p.OH * p.OW);
+  const int oy = r / p.OW, ox = r - oy * p.OW;
+  const int cout = p.cout;
+  float acc[THIN_MAX];
+#pragma unroll
+  for (int c = 0; c < THIN_MAX; c++) acc[c] = 0.f;
+  const int ntaps = p.kh * p.kw;
+  for (int tap = 0; tap < ntaps; tap++) {
+    const int dy = tap / p.kw, dx = tap - dy * p.kw;
+    int iy, ix;
+    if (!gather_coord(p, oy, ox, dy, dx, iy, ix)) continue;
+    const float* ip = in + ((long)(n * p.H + iy) * p.W + ix) * p.in_cs + p.in_coff;
+    const float* wp = w + (long)tap * p.cin * cout;
+    if (VEC) {
+      for (int ci = lane * 4; ci < p.cin; ci += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(ip + ci);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float* wr = wp + (long)(ci + j) * cout;
+#pragma unroll
+          for (int c = 0; c < THIN_MAX; c++)
+            if (c < cout) acc[c] = fmaf(av[j], wr[c], acc[c]);
+        }
+      }
+    } else {
+      for (int ci = lane; ci < p.cin; ci += 32) {
+        const float a = ip[ci];
+        const float* wr = wp + (long)ci * cout;
+#pragma unroll
+        for (int c = 0; c < THIN_MAX; c++)
+          if (c < cout) acc[c] = fmaf(a, wr[c], acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < THIN_MAX; c++) {
+    if (c < cout) {
+      float v = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[c] = v;
+    }
+  }
+  if (lane < cout) {
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < THIN_MAX; c++)
+      if (c == lane) v = acc[c];
+    v += bias ? bias[lane] : 0.f;
+    v = apply_act(v, p.act, p.slope);
+    v *= p.alpha;
+    if (res1) v = fmaf(p.beta1, res1[pm * p.res1_cs + p.res1_coff + lane], v);
+    if (res2) v = fmaf(p.beta2, res2[pm * p.res2_cs + p.res2_coff + lane], v);
+    out[pm * p.out_cs + p.out_coff + lane] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // conv + InstanceNorm2d(affine=False) + LeakyReLU as ONE kernel (the middle layers of NLayerDiscriminator,
 // architecture.py:998-1018: Conv2d(4x4, stride 2 | 1) -> InstanceNorm2d -> LeakyReLU(0.2)).
 // A thread-block CLUSTER owns (image n, 64 output channels): CTA `mt` of the cluster computes the 64-pixel tile mt of the
@@ -702,10 +778,19 @@ int dasr_conv2d_f32(const float* in, const float* w, const float* bias, const fl
   int rc = check_conv_params(p);
   if (rc) return rc;
   long P = (long)p->N * p->OH * p->OW;
+  cudaStream_t st = (cudaStream_t)stream;
+  // thin-N layers (logit convs, input gradients of Cin-3 / Cin-9 first layers): one warp per output pixel
+  if (p->cout <= THIN_MAX && (long)p->kh * p->kw * p->cin >= 256 && p->ups == 1) {
+    const bool tv = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    if (tv)
+      conv2d_thin_f32_kernel<true><<<cdiv(P, 8), 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
+    else
+      conv2d_thin_f32_kernel<false><<<cdiv(P, 8), 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
+    return check_launch("conv2d_f32(thin)");
+  }
   dim3 grid(cdiv(P, BM), cdiv(p->cout, BN));
   bool vec = (p->cin % 16 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && (p->cout % 4 == 0) &&
              ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
-  cudaStream_t st = (cudaStream_t)stream;
   const int math = resolve_math(p->math);
   DASR_REQUIRE(math >= MATH_FMA && math <= MATH_TF32X3, "conv2d_f32: math=%d", p->math);
 #define DASR_CONV_LAUNCH(V, M) conv2d_f32_kernel<V, M><<<grid, 256, 0, st>>>(in, w, bias, res1, res2, out, *p)

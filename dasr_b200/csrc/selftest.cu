@@ -625,6 +625,8 @@ int main(int argc, char** argv) {
       test_f32(1, 8, 8, 8, 1, 4, 1, 1, 1);
       test_f32(1, 10, 10, 12, 8, 5, 1, 2, 1);
       test_f32(2, 16, 16, 64, 128, 4, 2, 1, 1);      // discriminator layer shape
+      test_f32(2, 9, 9, 64, 1, 4, 1, 1, 1);          // logit layer: thin-N kernel (one warp per output pixel), K = 1024
+      test_f32(1, 11, 7, 30, 2, 3, 1, 1, 1);         // thin-N, scalar loads (cin % 4 != 0), K = 270
     }
     g_math = 0;
     test_wgrad_tc(1, 16, 8, 32, 32);
