@@ -124,8 +124,12 @@ def test_srgan_train_steps_vs_reference(golden, name):
         G, D = unwrap(model.netG).state_dict(), unwrap(model.netD).state_dict()
         for k, n in ref['G_norms'].items():       # two Adam steps of lr 1e-4: a handful of sign flips of ~0 gradients move a norm by ~1e-4
             assert abs(float(G[k].double().norm()) - n) <= 1e-3 * max(n, 1e-9), k
+        # relativistic losses (srragan) only see score differences: the gradient of the logit bias is mathematically zero,
+        # what the backward leaves there is rounding noise and Adam turns noise into a +-lr step -> not comparable
+        skip = {'linear2.bias'} if name == 'srragan' else set()
         for k, n in ref['D_norms'].items():
-            assert abs(float(D[k].double().norm()) - n) <= 2e-3 * max(n, 1e-9), k
+            if k not in skip:
+                assert abs(float(D[k].double().norm()) - n) <= 2e-3 * max(n, 1e-9), k
         for k, v in ref['D_running'].items():
             if 'num_batches' in k:
                 assert int(D[k]) == int(v), k
