@@ -780,7 +780,12 @@ int dasr_conv2d_f32(const float* in, const float* w, const float* bias, const fl
   long P = (long)p->N * p->OH * p->OW;
   cudaStream_t st = (cudaStream_t)stream;
   // thin-N layers (logit convs, input gradients of Cin-3 / Cin-9 first layers): one warp per output pixel
-  if (p->cout <= THIN_MAX && (long)p->kh * p->kw * p->cin >= 256 && p->ups == 1) {
+  static int thin_ok = -1;
+  if (thin_ok < 0) {
+    const char* e = getenv("DASR_F32_THIN");
+    thin_ok = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (thin_ok && p->cout <= THIN_MAX && (long)p->kh * p->kw * p->cin >= 256 && p->ups == 1) {
     const bool tv = (p->cin % 4 == 0) && (p->in_cs % 4 == 0) && (p->in_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
     if (tv)
       conv2d_thin_f32_kernel<true><<<cdiv(P, 8), 256, 0, st>>>(in, w, bias, res1, res2, out, *p);
