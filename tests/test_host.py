@@ -356,3 +356,14 @@ def test_drop_in_entry_points_default_to_mixed_precision(monkeypatch):
     monkeypatch.setenv('DASR_B200_TRAIN_PRECISION', 'fp32')
     overlay._drop_in_defaults()
     assert os.environ['DASR_B200_TRAIN_PRECISION'] == 'fp32'
+
+
+def test_pair_kernel_cout_tiles_for_the_vgg_layers():
+    """ops.pick_nt_pair: the Cout tile of a CTA pair is the largest multiple of 32 whose half filter set (9 taps x K x nt / 2
+    x 2 B) plus an epilogue ring and four A stages fit one SM — host-side planning through dasr_conv_tc2_supported (no GPU)."""
+    from dasr_b200 import ops
+    assert ops.pick_nt_pair(512, 512) == 32          # conv4 / conv5: 147 KB of filters per SM
+    assert ops.pick_nt_pair(256, 256) == 64
+    assert ops.pick_nt_pair(128, 256) == 128
+    assert ops.pick_nt_pair(64, 64) == 64
+    assert ops.pick_nt_pair(64, 48) is None          # not a multiple of 32
